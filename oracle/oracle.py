@@ -1,0 +1,196 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the nearest-neighbour hot path.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module.  The product package
+(``point-cloud-utils_b200``) never does, and has no CPU fallback.
+
+Two back ends with one interface:
+
+* ``impl="port"``       ``oracle/libpcu_oracle.so`` -- our own restatement of the kd-tree build and
+                        search (``oracle/kdtree_oracle.cpp``), available everywhere.
+* ``impl="reference"``  ``oracle/_ref/libpcu_ref.so`` -- the reference's *own* vendored
+                        ``nanoflann.hpp`` compiled in place by ``oracle/Makefile`` (three tree builds
+                        per call like the reference).  Present where it was built (this container)
+                        and on the GPU box as a prebuilt file.
+
+The two Python metrics restate ``/root/reference/point_cloud_utils/__init__.py:52-81``
+(``hausdorff_distance``) and ``:84-120`` (``chamfer_distance``) on top of the two binding-level
+functions (``/root/reference/src/point_cloud_distance.cpp:123-164`` and ``:186-234``), including
+their conventions: ``(n,)`` squeeze for k == 1, int64 indices, ``ValueError`` for bad arguments,
+``-1`` padding, first maximum for Hausdorff, ``>`` / ``<=`` branch rule, no 1/2 factor in Chamfer.
+
+Parity status: PINNED (see tests/test_oracle.py).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PORT_PATH = os.path.join(_HERE, "libpcu_oracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "libpcu_ref.so")
+_libs = {}
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_vp = ctypes.c_void_p
+
+
+def build(quiet=True):
+    """Compile the restatement and, where /root/reference is mounted, oracle/_ref."""
+    out = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+def have_reference():
+    return os.path.exists(_REF_PATH)
+
+
+def _lib(impl):
+    if impl in _libs:
+        return _libs[impl]
+    if impl == "port":
+        if not os.path.exists(_PORT_PATH):
+            build()
+        lib = ctypes.CDLL(_PORT_PATH)
+        prefix = "pcu_oracle"
+        knn_args = [_vp, _c_i64, _vp, _c_i64, _c_int, _c_int, _c_int, _c_int, _vp, _vp]
+    elif impl == "reference":
+        if not os.path.exists(_REF_PATH):
+            raise FileNotFoundError("oracle/_ref/libpcu_ref.so is not built (needs /root/reference)")
+        lib = ctypes.CDLL(_REF_PATH)
+        prefix = "pcu_ref"
+        knn_args = [_vp, _c_i64, _vp, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]
+    else:
+        raise ValueError("impl must be 'port' or 'reference'")
+    for sfx in ("f32", "f64"):
+        f = getattr(lib, "%s_knn_%s" % (prefix, sfx))
+        f.argtypes = knn_args
+        f.restype = _c_int
+        g = getattr(lib, "%s_one_sided_hausdorff_%s" % (prefix, sfx))
+        g.argtypes = [_vp, _c_i64, _vp, _c_i64, _c_int, _c_int, _vp, _vp, _vp]
+        g.restype = _c_int
+    getattr(lib, prefix + "_hardware_threads").restype = _c_int
+    _libs[impl] = (lib, prefix)
+    return _libs[impl]
+
+
+def hardware_threads(impl="port"):
+    lib, prefix = _lib(impl)
+    return int(getattr(lib, prefix + "_hardware_threads")())
+
+
+def _check_pair(a, b, name_a, name_b):
+    """dtype / shape rules of the binding (point_cloud_distance.cpp:124-125, :136-149)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.dtype not in (np.float32, np.float64):
+        raise ValueError("%s must have dtype float32 or float64" % name_a)
+    if b.dtype != a.dtype:
+        raise ValueError("%s must have the same dtype as %s" % (name_b, name_a))
+    if a.ndim != 2 or b.ndim != 2:
+        raise ValueError("%s and %s must be 2-D" % (name_a, name_b))
+    if a.shape[0] == 0 or b.shape[0] == 0:
+        raise ValueError("Invalid input set with zero elements")
+    if a.shape[1] != 3 or b.shape[1] != 3:
+        raise ValueError("Only 3D inputs are supported")
+    return np.ascontiguousarray(a), np.ascontiguousarray(b)
+
+
+def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False, max_points_per_leaf=10,
+                        num_threads=-1, impl="port", faithful_builds=True):
+    """point_cloud_distance.cpp:123-164."""
+    if k <= 0:
+        raise ValueError("Invalid value for k (%d) must be greater than 0." % k)
+    q, d = _check_pair(query_points, dataset_points, "query_points", "dataset_points")
+    lib, prefix = _lib(impl)
+    n, m = q.shape[0], d.shape[0]
+    dists = np.empty((n, k), dtype=q.dtype)
+    corrs = np.empty((n, k), dtype=np.int64)
+    sfx = "f32" if q.dtype == np.float32 else "f64"
+    fn = getattr(lib, "%s_knn_%s" % (prefix, sfx))
+    args = [q.ctypes.data, n, d.ctypes.data, m, int(k), int(bool(squared_distances)), int(max_points_per_leaf),
+            int(num_threads)]
+    if impl == "reference":
+        args.append(int(bool(faithful_builds)))
+    rc = fn(*args, dists.ctypes.data, corrs.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle call failed (rc=%d)" % rc)
+    if k == 1:  # npe::move squeezes size-1 dims (tests/test_examples.py:363-368)
+        return dists[:, 0], corrs[:, 0]
+    return dists, corrs
+
+
+def one_sided_hausdorff_distance(source, target, return_index=True, squared_distances=False, max_points_per_leaf=10,
+                                 impl="port"):
+    """point_cloud_distance.cpp:186-234 (note: return_index defaults to True here)."""
+    s, t = _check_pair(source, target, "source", "target")
+    lib, prefix = _lib(impl)
+    sfx = "f32" if s.dtype == np.float32 else "f64"
+    out_max = np.empty(1, dtype=s.dtype)
+    out_i = np.empty(1, dtype=np.int64)
+    out_j = np.empty(1, dtype=np.int64)
+    fn = getattr(lib, "%s_one_sided_hausdorff_%s" % (prefix, sfx))
+    rc = fn(s.ctypes.data, s.shape[0], t.ctypes.data, t.shape[0], int(bool(squared_distances)),
+            int(max_points_per_leaf), out_max.ctypes.data, out_i.ctypes.data, out_j.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle call failed (rc=%d)" % rc)
+    value = float(out_max[0])  # pybind11::cast of a C++ scalar gives a Python float
+    if return_index:
+        return value, int(out_i[0]), int(out_j[0])
+    return value
+
+
+def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_points_per_leaf=10, impl="port"):
+    """point_cloud_utils/__init__.py:52-81."""
+    h_xy, ix1, iy1 = one_sided_hausdorff_distance(x, y, True, squared_distances, max_points_per_leaf, impl=impl)
+    h_yx, iy2, ix2 = one_sided_hausdorff_distance(y, x, True, squared_distances, max_points_per_leaf, impl=impl)
+    h = max(h_xy, h_yx)
+    if return_index and h_xy > h_yx:
+        return h, ix1, iy1
+    elif return_index and h_xy <= h_yx:
+        return h, ix2, iy2
+    return h
+
+
+def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10, impl="port", faithful_builds=True):
+    """point_cloud_utils/__init__.py:84-120 (distances are recomputed from the indices with numpy)."""
+    x = np.asarray(x)
+    y = np.asarray(y)
+    _, cxy = k_nearest_neighbors(x, y, 1, False, max_points_per_leaf, impl=impl, faithful_builds=faithful_builds)
+    _, cyx = k_nearest_neighbors(y, x, 1, False, max_points_per_leaf, impl=impl, faithful_builds=faithful_builds)
+    d_xy = np.linalg.norm(x[cyx] - y, axis=-1, ord=p_norm).mean()
+    d_yx = np.linalg.norm(y[cxy] - x, axis=-1, ord=p_norm).mean()
+    cham = np.mean(d_xy) + np.mean(d_yx)
+    if return_index:
+        return cham, cxy, cyx
+    return cham
+
+
+def kd_tree(dataset_points, max_points_per_leaf=10):
+    """The restatement's built tree (order[] = nanoflann's vAcc, plus the node table), for checking
+    GPU-side replicas of the build."""
+    d = np.ascontiguousarray(dataset_points)
+    lib, _ = _lib("port")
+    sfx = "f32" if d.dtype == np.float32 else "f64"
+    fn = getattr(lib, "pcu_oracle_tree_" + sfx)
+    fn.restype = _c_i64
+    fn.argtypes = [_vp, _c_i64, _c_int, _vp, _c_i64] + [_vp] * 7
+    m = d.shape[0]
+    cap = 2 * m + 16
+    order = np.empty(m, np.int64)
+    feat = np.empty(cap, np.int32)
+    lo = np.empty(cap, d.dtype)
+    hi = np.empty(cap, d.dtype)
+    first = np.empty(cap, np.int64)
+    last = np.empty(cap, np.int64)
+    k0 = np.empty(cap, np.int32)
+    k1 = np.empty(cap, np.int32)
+    nn = fn(d.ctypes.data, m, int(max_points_per_leaf), order.ctypes.data, cap, feat.ctypes.data, lo.ctypes.data,
+            hi.ctypes.data, first.ctypes.data, last.ctypes.data, k0.ctypes.data, k1.ctypes.data)
+    return dict(order=order, feat=feat[:nn], div_lo=lo[:nn], div_hi=hi[:nn], first=first[:nn], last=last[:nn],
+                kid0=k0[:nn], kid1=k1[:nn])
