@@ -1,0 +1,155 @@
+/*
+ * pcu_b200.h -- C ABI of the B200-native nearest-neighbour path (libpcu_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of fwilliams/point-cloud-utils that this
+ * repository replaces: exact L2 k-nearest-neighbour search between two 3-D point clouds and the
+ * Chamfer / Hausdorff scalars built on it.  Each entry point names the reference interface it
+ * stands in for (paths relative to /root/reference):
+ *
+ *   pcu_b200_knn_*                   shortest_distances_nanoflann<>      src/point_cloud_distance.cpp:21-99
+ *                                    as called by k_nearest_neighbors    src/point_cloud_distance.cpp:123-164
+ *   pcu_b200_nn_stats_*              the k = 1 sweep + dists.maxCoeff    src/point_cloud_distance.cpp:219-225
+ *                                    (one_sided_hausdorff_distance       src/point_cloud_distance.cpp:186-234)
+ *                                    and norm(...).mean() of chamfer     point_cloud_utils/__init__.py:112-113
+ *   pcu_b200_chamfer_*               chamfer_distance, p_norm = 2        point_cloud_utils/__init__.py:84-120
+ *   pcu_b200_batched_chamfer_*       a Python loop of chamfer_distance over pairs (the docstring's
+ *                                    "[m, n, d] minibatch", __init__.py:89-90, which the 2-D-only
+ *                                    binding never implemented)
+ *
+ * Conventions
+ *   - Plain C: raw pointers, sizes, an opaque workspace handle and a CUDA stream passed as void*.
+ *     No C++ / torch / numpy types cross this boundary and no exception does either.
+ *   - Every function returns a pcu_b200_status; the message of the last failure on the calling
+ *     thread is available from pcu_b200_last_error().
+ *   - Point clouds are dense row-major (n, 3) arrays of float (…_f32) or double (…_f64).
+ *   - The caller owns every input and output buffer.  The library never allocates user-visible
+ *     memory; scratch lives in the workspace (grown on demand, reused across calls).  One
+ *     workspace serves one stream at a time.
+ *   - "device" entry points take DEVICE pointers, enqueue work on `stream` and return without
+ *     synchronising; results are valid once the stream reaches that point.  "host" entry points
+ *     take HOST pointers, stage through the workspace's pinned buffers (H2D, kernels, D2H) on the
+ *     workspace's own stream and return after the results have landed.
+ *   - Results follow the reference bit for bit: squared distance is ((qx-px)^2+(qy-py)^2)+(qz-pz)^2,
+ *     every operation rounded in the input precision, no FMA (nanoflann.hpp:496-507); indices are
+ *     int64 (ptrdiff_t in the reference); rows are ascending by distance; queries whose answer
+ *     depends on how equal distances are ordered are re-answered on the GPU by a replica of the
+ *     reference's kd-tree traversal (visit order decides, nanoflann.hpp:194-227) built with the
+ *     caller's max_points_per_leaf; fewer than k neighbours (k > m) pads with -1 / -1.0
+ *     (src/point_cloud_distance.cpp:90-93).
+ */
+#ifndef PCU_B200_H
+#define PCU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCU_B200_ABI_VERSION 1
+
+typedef enum pcu_b200_status {
+    PCU_B200_OK = 0,
+    PCU_B200_INVALID_ARGUMENT = 1, /* maps to ValueError in the Python layer (pybind11::value_error in the reference) */
+    PCU_B200_CUDA_ERROR = 2,       /* maps to RuntimeError */
+    PCU_B200_OUT_OF_MEMORY = 3,    /* maps to MemoryError */
+    PCU_B200_NO_DEVICE = 4,        /* no usable sm_100 device: the product has no CPU fallback */
+    PCU_B200_INTERNAL = 5
+} pcu_b200_status;
+
+typedef struct pcu_b200_workspace pcu_b200_workspace;
+
+/* Per-direction result of the fused k = 1 sweep (no per-point distance buffer is written). */
+typedef struct pcu_b200_nn_stats {
+    double sum_dist;      /* sum over queries of sqrt(d2_min), accumulated in fp64                */
+    double sum_sq_dist;   /* sum over queries of d2_min, accumulated in fp64                      */
+    double max_sq_dist;   /* largest d2_min (exact: the input-precision value widened to double)  */
+    int64_t argmax_query; /* first (lowest-index) query attaining it (Eigen maxCoeff, :221-223)   */
+    int64_t argmax_data;  /* its nearest neighbour in the dataset (:225)                          */
+    int64_t n_queries;    /* n                                                                    */
+    int64_t n_tied;       /* queries whose nearest neighbour was decided by tie order             */
+    int64_t n_far;        /* queries that needed the ring-expansion slow path (diagnostic)        */
+} pcu_b200_nn_stats;
+
+/* Tunables; zero-initialise and override what you need.  0 always means "library default". */
+typedef struct pcu_b200_options {
+    int max_points_per_leaf; /* reference kwarg; only influences how exact-distance ties are ordered (default 10) */
+    float cell_occupancy;    /* target dataset points per grid cell (default: 2 for k = 1, ~k/2 otherwise)        */
+    int disable_tie_replay;  /* 1: keep the (distance, lowest index) order for tied queries (diagnostic only)     */
+} pcu_b200_options;
+
+/* ---- library / error plumbing ------------------------------------------------------------ */
+int pcu_b200_abi_version(void);
+const char* pcu_b200_last_error(void);
+/* Number of CUDA devices this build can run on (compute capability 10.x); 0 if none. */
+int pcu_b200_device_count(void);
+/* Kernels launched by this library on the calling process since load (bench.py's gpu_launches). */
+int64_t pcu_b200_launch_count(void);
+
+/* ---- workspace ---------------------------------------------------------------------------- */
+int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws);
+int pcu_b200_workspace_destroy(pcu_b200_workspace* ws);
+/* Bytes of device scratch currently held. */
+int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws);
+/* Average kernel time per algorithm stage of the LAST call when profiling is enabled (diagnostic). */
+int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts);
+
+/* ---- k nearest neighbours, DEVICE pointers -------------------------------------------------
+ * out_dist : (n, k) row-major, input precision; sqrt(d2) unless squared != 0
+ * out_idx  : (n, k) row-major int64 indices into dataset
+ * out_n_tied (may be NULL): device int64 that receives the number of queries that went through
+ *            the tie replay.
+ * Replaces shortest_distances_nanoflann (src/point_cloud_distance.cpp:21-99).                    */
+int pcu_b200_knn_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m, int k,
+                     int squared, float* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream);
+int pcu_b200_knn_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m, int k,
+                     int squared, double* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream);
+
+/* ---- fused k = 1 sweep + reductions, DEVICE pointers ---------------------------------------
+ * out_stats : device pointer to ONE pcu_b200_nn_stats (query -> dataset direction).
+ * Replaces the k = 1 sweep, dists.maxCoeff and corrs(i, 0) of one_sided_hausdorff_distance
+ * (src/point_cloud_distance.cpp:219-225).                                                        */
+int pcu_b200_nn_stats_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m,
+                          pcu_b200_nn_stats* out_stats, void* stream);
+int pcu_b200_nn_stats_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m,
+                          pcu_b200_nn_stats* out_stats, void* stream);
+
+/* ---- fused bidirectional Chamfer (+ Hausdorff), DEVICE pointers ----------------------------
+ * out_stats : device pointer to TWO pcu_b200_nn_stats: [0] = x -> y, [1] = y -> x.
+ * out_value : device pointer to one scalar of the input precision:
+ *             chamfer = stats[0].sum_dist / n + stats[1].sum_dist / m   (no 1/2, not squared;
+ *             point_cloud_utils/__init__.py:112-115).  May be NULL.
+ * Both clouds are binned once and swept in one launch; no distance buffer is materialised.       */
+int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const float* y, int64_t m,
+                         pcu_b200_nn_stats* out_stats, float* out_value, void* stream);
+int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
+                         pcu_b200_nn_stats* out_stats, double* out_value, void* stream);
+
+/* ---- batched Chamfer over independent pairs, DEVICE pointers -------------------------------
+ * x : (B, n, 3), y : (B, m, 3) dense; out_per_pair : (B) scalars of the input precision;
+ * out_sum (may be NULL): device double = sum of the B per-pair values (the quantity a multi-GPU
+ * caller all-reduces).                                                                            */
+int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
+                                 int64_t m, float* out_per_pair, double* out_sum, void* stream);
+
+/* ---- HOST-pointer conveniences (H2D + kernels + D2H, synchronous) --------------------------
+ * The calls the numpy-facing binding makes; these are what `e2e` in bench.py times.              */
+int pcu_b200_knn_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m,
+                          int k, int squared, float* out_dist, int64_t* out_idx, int64_t* out_n_tied);
+int pcu_b200_knn_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m,
+                          int k, int squared, double* out_dist, int64_t* out_idx, int64_t* out_n_tied);
+int pcu_b200_nn_stats_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset,
+                               int64_t m, pcu_b200_nn_stats* out_stats);
+int pcu_b200_nn_stats_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset,
+                               int64_t m, pcu_b200_nn_stats* out_stats);
+int pcu_b200_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const float* y, int64_t m,
+                              pcu_b200_nn_stats* out_stats, float* out_value);
+int pcu_b200_chamfer_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
+                              pcu_b200_nn_stats* out_stats, double* out_value);
+int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
+                                      int64_t n, int64_t m, float* out_per_pair, double* out_sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCU_B200_H */

@@ -1,0 +1,358 @@
+// binding.cpp -- pybind11 module `_pcu_internal`: the Python-facing mirror of the two bindings the
+// reference generates with numpyeigen for this path,
+//     k_nearest_neighbors           /root/reference/src/point_cloud_distance.cpp:123-164
+//     one_sided_hausdorff_distance  /root/reference/src/point_cloud_distance.cpp:186-234
+// with the same argument names, defaults, dtype rules (float32 / float64, both clouds alike),
+// shape rules ((n, 3), n > 0), error type (ValueError), int64 indices and squeezed outputs
+// (tests/test_examples.py:363-368).  All computation goes through the C ABI of libpcu_b200.so
+// (include/pcu_b200.h); there is no CPU implementation behind these functions.
+//
+// Besides the numpy entry points the module exposes raw-pointer variants (`*_device`) that the
+// Python package uses for CUDA torch tensors: the caller passes data_ptr()s and a stream handle,
+// nothing is copied and nothing synchronises.
+#include <pybind11/pybind11.h>
+#include <pybind11/numpy.h>
+
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+
+#include "../../include/pcu_b200.h"
+
+namespace py = pybind11;
+
+namespace {
+
+[[noreturn]] void raise_status(int status) {
+    const std::string msg = pcu_b200_last_error();
+    switch (status) {
+        case PCU_B200_INVALID_ARGUMENT: throw py::value_error(msg);
+        case PCU_B200_OUT_OF_MEMORY: throw std::bad_alloc();
+        default: throw std::runtime_error("pcu_b200: " + msg);
+    }
+}
+inline void check(int status) { if (status != PCU_B200_OK) raise_status(status); }
+
+// One workspace per (device, stream): a workspace serves one stream at a time.
+struct Pool {
+    std::mutex mu;
+    std::map<std::pair<int, uintptr_t>, pcu_b200_workspace*> items;
+    pcu_b200_workspace* get(int device, uintptr_t stream) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto key = std::make_pair(device, stream);
+        auto it = items.find(key);
+        if (it != items.end()) return it->second;
+        pcu_b200_workspace* ws = nullptr;
+        check(pcu_b200_workspace_create(device, &ws));
+        items[key] = ws;
+        return ws;
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto& kv : items) pcu_b200_workspace_destroy(kv.second);
+        items.clear();
+    }
+};
+Pool& pool() { static Pool p; return p; }
+
+struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; };
+Options& defaults() { static Options o; return o; }
+
+void apply_options(pcu_b200_workspace* ws, int max_points_per_leaf) {
+    if (max_points_per_leaf <= 0) throw py::value_error("max_points_per_leaf must be greater than 0.");
+    pcu_b200_options o{};
+    o.max_points_per_leaf = max_points_per_leaf;
+    o.cell_occupancy = defaults().occupancy;
+    o.disable_tie_replay = defaults().disable_replay;
+    check(pcu_b200_workspace_set_options(ws, &o));
+}
+
+enum class Dt { f32, f64 };
+
+Dt common_dtype(const py::array& a, const py::array& b, const char* na, const char* nb) {
+    // numpyeigen: dense_float / dense_double only, second argument npe_matches(first)
+    // (point_cloud_distance.cpp:124-125, :187-188)
+    const bool a32 = a.dtype().is(py::dtype::of<float>()), a64 = a.dtype().is(py::dtype::of<double>());
+    if (!a32 && !a64) {
+        std::ostringstream ss;
+        ss << "Invalid scalar type (" << std::string(py::str(a.dtype())) << ") for argument '" << na
+           << "'. Expected one of ['float32', 'float64'].";
+        throw py::value_error(ss.str());
+    }
+    if (!b.dtype().is(a.dtype())) {
+        std::ostringstream ss;
+        ss << "Invalid scalar type (" << std::string(py::str(b.dtype())) << ") for argument '" << nb
+           << "'. Expected it to match argument '" << na << "' which is of type " << std::string(py::str(a.dtype())) << ".";
+        throw py::value_error(ss.str());
+    }
+    return a32 ? Dt::f32 : Dt::f64;
+}
+
+void check_shapes(const py::array& a, const py::array& b, const char* na, const char* nb) {
+    auto shape_str = [](const py::array& x) {
+        std::ostringstream ss;
+        ss << "(";
+        for (py::ssize_t i = 0; i < x.ndim(); ++i) ss << (i ? ", " : "") << x.shape(i);
+        ss << ")";
+        return ss.str();
+    };
+    if (a.ndim() != 2 || b.ndim() != 2) {
+        std::ostringstream ss;
+        ss << "Only 3D inputs are supported: " << na << " and " << nb << " must have shape (n, 3) and (m, 3). Got "
+           << na << ".shape = " << shape_str(a) << ", " << nb << ".shape = " << shape_str(b) << ".";
+        throw py::value_error(ss.str());
+    }
+    if (a.shape(0) == 0 || b.shape(0) == 0) {
+        std::ostringstream ss;
+        ss << "Invalid input set with zero elements: " << na << " and " << nb
+           << " must have shape (n, 3) and (m, 3). Got " << na << ".shape = " << shape_str(a) << ", " << nb
+           << ".shape = " << shape_str(b) << ".";
+        throw py::value_error(ss.str());
+    }
+    if (a.shape(1) != 3 || b.shape(1) != 3) {
+        std::ostringstream ss;
+        ss << "Only 3D inputs are supported: " << na << " and " << nb << " must have shape (n, 3) and (m, 3). Got "
+           << na << ".shape = " << shape_str(a) << ", " << nb << ".shape = " << shape_str(b) << ".";
+        throw py::value_error(ss.str());
+    }
+}
+
+template <typename T>
+py::array_t<T, py::array::c_style> dense(const py::array& a) {
+    return py::array_t<T, py::array::c_style | py::array::forcecast>::ensure(a);
+}
+
+int current_device_or_default(int device) { return device < 0 ? 0 : device; }
+
+template <typename T>
+py::tuple knn_numpy(const py::array& q_in, const py::array& d_in, int k, bool squared, int leaf, int device) {
+    auto q = dense<T>(q_in);
+    auto d = dense<T>(d_in);
+    const int64_t n = q.shape(0), m = d.shape(0);
+    py::array_t<T> dists({(py::ssize_t)n, (py::ssize_t)k});
+    py::array_t<int64_t> corrs({(py::ssize_t)n, (py::ssize_t)k});
+    pcu_b200_workspace* ws = pool().get(device, 0);
+    apply_options(ws, leaf);
+    int status;
+    int64_t tied = 0;
+    {
+        py::gil_scoped_release nogil;
+        if (sizeof(T) == 4)
+            status = pcu_b200_knn_host_f32(ws, (const float*)q.data(), n, (const float*)d.data(), m, k, squared,
+                                           (float*)dists.mutable_data(), corrs.mutable_data(), &tied);
+        else
+            status = pcu_b200_knn_host_f64(ws, (const double*)q.data(), n, (const double*)d.data(), m, k, squared,
+                                           (double*)dists.mutable_data(), corrs.mutable_data(), &tied);
+    }
+    check(status);
+    // npe::move hands the matrix to numpy and squeezes every size-1 dimension
+    // (pinned for (n, 1) -> (n,) by tests/test_examples.py:363-368)
+    return py::make_tuple(dists.attr("squeeze")(), corrs.attr("squeeze")());
+}
+
+py::tuple k_nearest_neighbors(const py::array& query_points, const py::array& dataset_points, int k,
+                              bool squared_distances, int max_points_per_leaf, int num_threads, int device) {
+    (void)num_threads;  // CPU thread count of the reference; results never depended on it
+    if (k <= 0) throw py::value_error("Invalid value for k (" + std::to_string(k) + ") must be greater than 0.");
+    const Dt dt = common_dtype(query_points, dataset_points, "query_points", "dataset_points");
+    check_shapes(query_points, dataset_points, "query_points", "dataset_points");
+    const int dev = current_device_or_default(device);
+    return dt == Dt::f32 ? knn_numpy<float>(query_points, dataset_points, k, squared_distances, max_points_per_leaf, dev)
+                         : knn_numpy<double>(query_points, dataset_points, k, squared_distances, max_points_per_leaf, dev);
+}
+
+py::dict stats_to_dict(const pcu_b200_nn_stats& s) {
+    py::dict d;
+    d["sum_dist"] = s.sum_dist;
+    d["sum_sq_dist"] = s.sum_sq_dist;
+    d["max_sq_dist"] = s.max_sq_dist;
+    d["argmax_query"] = s.argmax_query;
+    d["argmax_data"] = s.argmax_data;
+    d["n_queries"] = s.n_queries;
+    d["n_tied"] = s.n_tied;
+    d["n_far"] = s.n_far;
+    return d;
+}
+
+template <typename T>
+pcu_b200_nn_stats one_sided_numpy(const py::array& s_in, const py::array& t_in, int leaf, int device) {
+    auto s = dense<T>(s_in);
+    auto t = dense<T>(t_in);
+    pcu_b200_workspace* ws = pool().get(device, 0);
+    apply_options(ws, leaf);
+    pcu_b200_nn_stats st{};
+    int status;
+    {
+        py::gil_scoped_release nogil;
+        if (sizeof(T) == 4)
+            status = pcu_b200_nn_stats_host_f32(ws, (const float*)s.data(), s.shape(0), (const float*)t.data(), t.shape(0), &st);
+        else
+            status = pcu_b200_nn_stats_host_f64(ws, (const double*)s.data(), s.shape(0), (const double*)t.data(), t.shape(0), &st);
+    }
+    check(status);
+    return st;
+}
+
+template <typename T>
+T metric_value(double max_sq, bool squared) {
+    const T d2 = (T)max_sq;  // exact: max_sq is the input-precision value widened
+    return squared ? d2 : (T)std::sqrt(d2);  // correctly rounded sqrt in the input precision (:84-88)
+}
+
+py::object one_sided_hausdorff_distance(const py::array& source, const py::array& target, bool return_index,
+                                        bool squared_distances, int max_points_per_leaf, int device) {
+    const Dt dt = common_dtype(source, target, "source", "target");
+    check_shapes(source, target, "source", "target");
+    const int dev = current_device_or_default(device);
+    const pcu_b200_nn_stats st = dt == Dt::f32 ? one_sided_numpy<float>(source, target, max_points_per_leaf, dev)
+                                               : one_sided_numpy<double>(source, target, max_points_per_leaf, dev);
+    const double value = dt == Dt::f32 ? (double)metric_value<float>(st.max_sq_dist, squared_distances)
+                                       : metric_value<double>(st.max_sq_dist, squared_distances);
+    if (return_index) return py::make_tuple(value, st.argmax_query, st.argmax_data);
+    return py::float_(value);
+}
+
+// Fused bidirectional sweep on numpy inputs: (chamfer value in input precision, stats x->y, stats y->x)
+py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_points_per_leaf, int device) {
+    const Dt dt = common_dtype(x_in, y_in, "x", "y");
+    check_shapes(x_in, y_in, "x", "y");
+    const int dev = current_device_or_default(device);
+    pcu_b200_workspace* ws = pool().get(dev, 0);
+    apply_options(ws, max_points_per_leaf);
+    pcu_b200_nn_stats st[2] = {};
+    int status;
+    py::object value;
+    if (dt == Dt::f32) {
+        auto x = dense<float>(x_in);
+        auto y = dense<float>(y_in);
+        float v = 0.f;
+        { py::gil_scoped_release nogil;
+          status = pcu_b200_chamfer_host_f32(ws, x.data(), x.shape(0), y.data(), y.shape(0), st, &v); }
+        check(status);
+        value = py::module_::import("numpy").attr("float32")(v);
+    } else {
+        auto x = dense<double>(x_in);
+        auto y = dense<double>(y_in);
+        double v = 0.0;
+        { py::gil_scoped_release nogil;
+          status = pcu_b200_chamfer_host_f64(ws, x.data(), x.shape(0), y.data(), y.shape(0), st, &v); }
+        check(status);
+        value = py::module_::import("numpy").attr("float64")(v);
+    }
+    return py::make_tuple(value, stats_to_dict(st[0]), stats_to_dict(st[1]));
+}
+
+// ---- raw device-pointer entry points (CUDA torch tensors) --------------------------------------
+void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int64_t m, int k, bool squared,
+                uintptr_t out_dist, uintptr_t out_idx, uintptr_t out_n_tied, int max_points_per_leaf, int device,
+                uintptr_t stream) {
+    if (k <= 0) throw py::value_error("Invalid value for k (" + std::to_string(k) + ") must be greater than 0.");
+    pcu_b200_workspace* ws = pool().get(device, stream);
+    apply_options(ws, max_points_per_leaf);
+    int status;
+    {
+        py::gil_scoped_release nogil;
+        status = is_f64 ? pcu_b200_knn_f64(ws, (const double*)query, n, (const double*)dataset, m, k, squared,
+                                           (double*)out_dist, (int64_t*)out_idx, (int64_t*)out_n_tied, (void*)stream)
+                        : pcu_b200_knn_f32(ws, (const float*)query, n, (const float*)dataset, m, k, squared,
+                                           (float*)out_dist, (int64_t*)out_idx, (int64_t*)out_n_tied, (void*)stream);
+    }
+    check(status);
+}
+
+void stats_device(bool is_f64, bool both, uintptr_t a, int64_t n, uintptr_t b, int64_t m, uintptr_t out_stats,
+                  uintptr_t out_value, int max_points_per_leaf, int device, uintptr_t stream) {
+    pcu_b200_workspace* ws = pool().get(device, stream);
+    apply_options(ws, max_points_per_leaf);
+    int status;
+    {
+        py::gil_scoped_release nogil;
+        auto* st = (pcu_b200_nn_stats*)out_stats;
+        if (both)
+            status = is_f64 ? pcu_b200_chamfer_f64(ws, (const double*)a, n, (const double*)b, m, st, (double*)out_value, (void*)stream)
+                            : pcu_b200_chamfer_f32(ws, (const float*)a, n, (const float*)b, m, st, (float*)out_value, (void*)stream);
+        else
+            status = is_f64 ? pcu_b200_nn_stats_f64(ws, (const double*)a, n, (const double*)b, m, st, (void*)stream)
+                            : pcu_b200_nn_stats_f32(ws, (const float*)a, n, (const float*)b, m, st, (void*)stream);
+    }
+    check(status);
+}
+
+// Batched Chamfer on numpy inputs: x (B, n, 3), y (B, m, 3) float32 -> ((B,) float32, fp64 sum)
+py::tuple batched_chamfer_numpy(const py::array& x_in, const py::array& y_in, int max_points_per_leaf, int device) {
+    if (!x_in.dtype().is(py::dtype::of<float>()) || !y_in.dtype().is(py::dtype::of<float>()))
+        throw py::value_error("batched_chamfer_distance: x and y must both be float32");
+    if (x_in.ndim() != 3 || y_in.ndim() != 3 || x_in.shape(2) != 3 || y_in.shape(2) != 3 || x_in.shape(0) != y_in.shape(0))
+        throw py::value_error("batched_chamfer_distance: x and y must have shape (B, n, 3) and (B, m, 3)");
+    if (x_in.shape(0) == 0 || x_in.shape(1) == 0 || y_in.shape(1) == 0)
+        throw py::value_error("Invalid input set with zero elements: x and y must have shape (B, n, 3) and (B, m, 3)");
+    auto x = dense<float>(x_in);
+    auto y = dense<float>(y_in);
+    const int64_t B = x.shape(0), n = x.shape(1), m = y.shape(1);
+    py::array_t<float> out({(py::ssize_t)B});
+    double sum = 0.0;
+    const int dev = current_device_or_default(device);
+    pcu_b200_workspace* ws = pool().get(dev, 0);
+    apply_options(ws, max_points_per_leaf);
+    int status;
+    {
+        py::gil_scoped_release nogil;
+        status = pcu_b200_batched_chamfer_host_f32(ws, x.data(), y.data(), B, n, m, out.mutable_data(),
+                                                   B <= 16384 ? &sum : nullptr);
+    }
+    check(status);
+    return py::make_tuple(out, sum);
+}
+
+void batched_chamfer_device(uintptr_t x, uintptr_t y, int64_t B, int64_t n, int64_t m, uintptr_t out_per_pair,
+                            uintptr_t out_sum, int max_points_per_leaf, int device, uintptr_t stream) {
+    pcu_b200_workspace* ws = pool().get(device, stream);
+    apply_options(ws, max_points_per_leaf);
+    int status;
+    {
+        py::gil_scoped_release nogil;
+        status = pcu_b200_batched_chamfer_f32(ws, (const float*)x, (const float*)y, B, n, m, (float*)out_per_pair,
+                                              (double*)out_sum, (void*)stream);
+    }
+    check(status);
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_pcu_internal, mod) {
+    mod.doc() = "B200-native nearest-neighbour bindings (drop-in for point_cloud_utils._pcu_internal on this path)";
+    mod.def("k_nearest_neighbors", &k_nearest_neighbors, py::arg("query_points"), py::arg("dataset_points"),
+            py::arg("k"), py::arg("squared_distances") = false, py::arg("max_points_per_leaf") = 10,
+            py::arg("num_threads") = -1, py::arg("device") = -1,
+            "Compute the k nearest neighbors (L2 distance) from each point in the query point cloud to the dataset "
+            "point cloud.  Returns (dists, corrs): (n, k) arrays, squeezed to (n,) when k == 1; corrs is int64.");
+    mod.def("one_sided_hausdorff_distance", &one_sided_hausdorff_distance, py::arg("source"), py::arg("target"),
+            py::arg("return_index") = true, py::arg("squared_distances") = false, py::arg("max_points_per_leaf") = 10,
+            py::arg("device") = -1,
+            "Compute the one sided Hausdorff distance from source to target.  Returns d or (d, i, j).");
+    mod.def("_chamfer_stats", &chamfer_stats, py::arg("x"), py::arg("y"), py::arg("max_points_per_leaf") = 10,
+            py::arg("device") = -1);
+    mod.def("_batched_chamfer", &batched_chamfer_numpy, py::arg("x"), py::arg("y"), py::arg("max_points_per_leaf") = 10,
+            py::arg("device") = -1);
+    mod.def("_batched_chamfer_device", &batched_chamfer_device);
+    mod.def("_knn_device", &knn_device);
+    mod.def("_stats_device", &stats_device);
+    mod.def("_stats_nbytes", []() { return (int)sizeof(pcu_b200_nn_stats); });
+    mod.def("_device_count", []() { return pcu_b200_device_count(); });
+    mod.def("_launch_count", []() { return (int64_t)pcu_b200_launch_count(); });
+    mod.def("_abi_version", []() { return pcu_b200_abi_version(); });
+    mod.def("_workspace_bytes", [](int device, uintptr_t stream) {
+        return (int64_t)pcu_b200_workspace_bytes(pool().get(device, stream));
+    });
+    mod.def("_set_defaults", [](float cell_occupancy, bool disable_tie_replay) {
+        defaults().occupancy = cell_occupancy;
+        defaults().disable_replay = disable_tie_replay ? 1 : 0;
+    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = false);
+    mod.def("_release_workspaces", []() { pool().clear(); });
+    // destroy workspaces before the CUDA context goes away at interpreter exit
+    py::module_::import("atexit").attr("register")(py::cpp_function([]() { pool().clear(); }));
+}

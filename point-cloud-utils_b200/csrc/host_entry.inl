@@ -1,0 +1,133 @@
+// host_entry.inl -- HOST-pointer conveniences of the C ABI: H2D, the device entry point, D2H,
+// one synchronisation at the end.  cudaMemcpyAsync takes the caller's buffers as they are: pinned
+// memory is DMA'd directly, pageable memory goes through the driver's staging.
+namespace {
+
+template <typename T>
+int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* dataset, long long m, int k, int squared,
+             T* out_dist, long long* out_idx, long long* out_n_tied) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid value for k (%d) must be greater than 0.", k);
+    PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
+    if (!out_dist || !out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& dq, T*& dd, T*& od, long long*& oi, long long*& nt) {
+        dq = cv.take<T>((size_t)3 * n);
+        dd = cv.take<T>((size_t)3 * m);
+        od = cv.take<T>((size_t)n * k);
+        oi = cv.take<long long>((size_t)n * k);
+        nt = cv.take<long long>(1);
+    };
+    T *dq, *dd, *od; long long *oi, *nt;
+    carve(measure, dq, dd, od, oi, nt);
+    PCU_TRY(ensure_io(ws, measure.off));
+    Carver cv(ws->io);
+    carve(cv, dq, dd, od, oi, nt);
+    cudaStream_t st = ws->own_stream;
+    PCU_CUDA(cudaMemcpyAsync(dq, query, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    PCU_CUDA(cudaMemcpyAsync(dd, dataset, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
+    PCU_TRY(knn_device<T>(ws, dq, n, dd, m, k, squared, od, oi, nt, st));
+    PCU_CUDA(cudaMemcpyAsync(out_dist, od, sizeof(T) * n * k, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaMemcpyAsync(out_idx, oi, sizeof(long long) * n * k, cudaMemcpyDeviceToHost, st));
+    long long tied = 0;
+    PCU_CUDA(cudaMemcpyAsync(&tied, nt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    if (out_n_tied) *out_n_tied = tied;
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
+               pcu_b200_nn_stats* out_stats, T* out_value) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    PCU_TRY(check_cloud_args<T>(a, n, b, m));
+    if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& da, T*& db, pcu_b200_nn_stats*& ds, T*& dv) {
+        da = cv.take<T>((size_t)3 * n);
+        db = cv.take<T>((size_t)3 * m);
+        ds = cv.take<pcu_b200_nn_stats>(2);
+        dv = cv.take<T>(1);
+    };
+    T *da, *db, *dv; pcu_b200_nn_stats* ds;
+    carve(measure, da, db, ds, dv);
+    PCU_TRY(ensure_io(ws, measure.off));
+    Carver cv(ws->io);
+    carve(cv, da, db, ds, dv);
+    cudaStream_t st = ws->own_stream;
+    PCU_CUDA(cudaMemcpyAsync(da, a, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    PCU_CUDA(cudaMemcpyAsync(db, b, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
+    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, ds, (both && out_value) ? dv : nullptr, st));
+    PCU_CUDA(cudaMemcpyAsync(out_stats, ds, sizeof(pcu_b200_nn_stats) * (both ? 2 : 1), cudaMemcpyDeviceToHost, st));
+    if (both && out_value) PCU_CUDA(cudaMemcpyAsync(out_value, dv, sizeof(T), cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long long batch, long long n, long long m,
+                         T* out_per_pair, double* out_sum) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (batch <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "batch must be positive (got %lld)", batch);
+    PCU_TRY(check_cloud_args<T>(x, n, y, m));
+    if (!out_per_pair) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& dx, T*& dy, T*& dv, double*& dsum) {
+        dx = cv.take<T>((size_t)3 * n * batch);
+        dy = cv.take<T>((size_t)3 * m * batch);
+        dv = cv.take<T>((size_t)batch);
+        dsum = cv.take<double>(1);
+    };
+    T *dx, *dy, *dv; double* dsum;
+    carve(measure, dx, dy, dv, dsum);
+    PCU_TRY(ensure_io(ws, measure.off));
+    Carver cv(ws->io);
+    carve(cv, dx, dy, dv, dsum);
+    cudaStream_t st = ws->own_stream;
+    PCU_CUDA(cudaMemcpyAsync(dx, x, sizeof(T) * 3 * n * batch, cudaMemcpyHostToDevice, st));
+    PCU_CUDA(cudaMemcpyAsync(dy, y, sizeof(T) * 3 * m * batch, cudaMemcpyHostToDevice, st));
+    PCU_TRY(batched_chamfer_device<T>(ws, dx, dy, batch, n, m, dv, out_sum ? dsum : nullptr, st));
+    PCU_CUDA(cudaMemcpyAsync(out_per_pair, dv, sizeof(T) * batch, cudaMemcpyDeviceToHost, st));
+    if (out_sum) PCU_CUDA(cudaMemcpyAsync(out_sum, dsum, sizeof(double), cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    return PCU_B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcu_b200_knn_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m,
+                          int k, int squared, float* out_dist, int64_t* out_idx, int64_t* out_n_tied) {
+    return knn_host<float>(ws, query, n, dataset, m, k, squared, out_dist, (long long*)out_idx, (long long*)out_n_tied);
+}
+int pcu_b200_knn_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m,
+                          int k, int squared, double* out_dist, int64_t* out_idx, int64_t* out_n_tied) {
+    return knn_host<double>(ws, query, n, dataset, m, k, squared, out_dist, (long long*)out_idx, (long long*)out_n_tied);
+}
+int pcu_b200_nn_stats_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset,
+                               int64_t m, pcu_b200_nn_stats* out_stats) {
+    return stats_host<float>(ws, query, n, dataset, m, false, out_stats, nullptr);
+}
+int pcu_b200_nn_stats_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset,
+                               int64_t m, pcu_b200_nn_stats* out_stats) {
+    return stats_host<double>(ws, query, n, dataset, m, false, out_stats, nullptr);
+}
+int pcu_b200_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const float* y, int64_t m,
+                              pcu_b200_nn_stats* out_stats, float* out_value) {
+    return stats_host<float>(ws, x, n, y, m, true, out_stats, out_value);
+}
+int pcu_b200_chamfer_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
+                              pcu_b200_nn_stats* out_stats, double* out_value) {
+    return stats_host<double>(ws, x, n, y, m, true, out_stats, out_value);
+}
+
+int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
+                                      int64_t n, int64_t m, float* out_per_pair, double* out_sum) {
+    return batched_chamfer_host<float>(ws, x, y, batch, n, m, out_per_pair, out_sum);
+}
+
+}  // extern "C"

@@ -1,0 +1,555 @@
+// pcu_b200.cu -- workspace, launch sequencing and the C ABI declared in include/pcu_b200.h.
+//
+// Host side of the B200 nearest-neighbour path.  It owns no algorithmic decisions that depend on
+// the data: grid shapes, far-query lists and tie lists are produced and consumed on the device, so
+// a device-pointer call enqueues a fixed sequence of launches and returns without synchronising.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/pcu_b200.h"
+#include "host_util.h"
+#include "common.cuh"
+#include "grid.cuh"
+#include "search.cuh"
+#include "kdreplay.cuh"
+
+using namespace pcu;
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return status;
+}
+
+#define PCU_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(e__ == cudaErrorMemoryAllocation ? PCU_B200_OUT_OF_MEMORY : PCU_B200_CUDA_ERROR, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);    \
+    } while (0)
+
+#define PCU_TRY(expr)                      \
+    do {                                   \
+        int s__ = (expr);                  \
+        if (s__ != PCU_B200_OK) return s__; \
+    } while (0)
+
+#define PCU_LAUNCH(kernel, grid, block, stream, ...)                   \
+    do {                                                               \
+        kernel<<<grid, block, 0, stream>>>(__VA_ARGS__);               \
+        g_launches.fetch_add(1, std::memory_order_relaxed);            \
+        PCU_CUDA(cudaGetLastError());                                  \
+    } while (0)
+
+// Per-field byte strides between consecutive pairs of a batch (side 0 = first cloud of each pair,
+// side 1 = second cloud; direction 0 = first -> second, direction 1 = second -> first).
+struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_partial; };
+struct SweepStrides { size_t out_dist, out_idx, partial, far_list, counters, tie_list; };
+
+template <typename U>
+__device__ __forceinline__ U* advance(U* p, size_t bytes) {
+    return p ? reinterpret_cast<U*>(reinterpret_cast<unsigned char*>(const_cast<typename std::remove_const<U>::type*>(p)) + bytes) : p;
+}
+
+// Writes the cloud / sweep descriptors of every pair of a batch.  They are generated on the device
+// from two prototypes, so a call never stages descriptors through host memory that a later call
+// could overwrite while this one is still queued.
+template <typename T>
+struct DescriptorArgs {
+    Cloud<T> cloud[2];
+    Sweep<T> sweep[2];
+    CloudStrides cs[2];
+    SweepStrides ss[2];
+    long long batch;
+    int nsweeps;
+    pcu_b200_nn_stats* stats;
+};
+
+template <typename T>
+__global__ void descriptors_kernel(const __grid_constant__ DescriptorArgs<T> a, Cloud<T>* clouds, Sweep<T>* sweeps) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.batch) return;
+    for (int s = 0; s < 2; ++s) {
+        Cloud<T> c = a.cloud[s];
+        const CloudStrides& st = a.cs[s];
+        c.raw = advance(c.raw, p * st.raw);
+        c.sorted = advance(c.sorted, p * st.sorted);
+        c.rank = advance(c.rank, p * st.rank);
+        c.cell_start = advance(c.cell_start, p * st.cell_start);
+        c.grid = advance(c.grid, p * st.grid);
+        c.wall_lo = advance(c.wall_lo, p * st.wall_lo);
+        c.wall_hi = advance(c.wall_hi, p * st.wall_hi);
+        c.bbox_partial = advance(c.bbox_partial, p * st.bbox_partial);
+        c.scan_partial = advance(c.scan_partial, p * st.scan_partial);
+        clouds[2 * p + s] = c;
+    }
+    for (int d = 0; d < a.nsweeps; ++d) {
+        Sweep<T> w = a.sweep[d];
+        const SweepStrides& st = a.ss[d];
+        w.qcloud = (int)(2 * p + d);
+        w.dcloud = (int)(2 * p + 1 - d);
+        w.out_dist = advance(w.out_dist, p * st.out_dist);
+        w.out_idx = advance(w.out_idx, p * st.out_idx);
+        w.partial = advance(w.partial, p * st.partial);
+        w.far_list = advance(w.far_list, p * st.far_list);
+        w.counters = advance(w.counters, p * st.counters);
+        w.tie_list = advance(w.tie_list, p * st.tie_list);
+        w.stats = a.stats ? a.stats + p * a.nsweeps + d : nullptr;
+        sweeps[p * a.nsweeps + d] = w;
+    }
+}
+
+}  // namespace
+
+struct pcu_b200_workspace {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    unsigned char* arena = nullptr;      // scratch of the device-pointer entry points
+    size_t arena_bytes = 0;
+    unsigned char* io = nullptr;         // device copies of host inputs / outputs (host entry points)
+    size_t io_bytes = 0;
+    pcu_b200_options opts{};
+    int sm_count = 148;
+};
+
+namespace {
+
+int ensure_arena(pcu_b200_workspace* ws, size_t bytes) {
+    if (bytes <= ws->arena_bytes) return PCU_B200_OK;
+    if (ws->arena) {
+        PCU_CUDA(cudaDeviceSynchronize());  // earlier calls may still be using the old arena
+        PCU_CUDA(cudaFree(ws->arena));
+        ws->arena = nullptr;
+        ws->arena_bytes = 0;
+    }
+    const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc(&ws->arena, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PCU_B200_OUT_OF_MEMORY, "cudaMalloc of %zu bytes of scratch failed: %s", want, cudaGetErrorString(e));
+    }
+    ws->arena_bytes = want;
+    return PCU_B200_OK;
+}
+
+int ensure_io(pcu_b200_workspace* ws, size_t bytes) {
+    if (bytes <= ws->io_bytes) return PCU_B200_OK;
+    if (ws->io) {
+        PCU_CUDA(cudaDeviceSynchronize());
+        PCU_CUDA(cudaFree(ws->io));
+        ws->io = nullptr;
+        ws->io_bytes = 0;
+    }
+    const size_t want = align_up(bytes + bytes / 8, 1 << 20);
+    cudaError_t e = cudaMalloc(&ws->io, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PCU_B200_OUT_OF_MEMORY, "cudaMalloc of %zu bytes of staging failed: %s", want, cudaGetErrorString(e));
+    }
+    ws->io_bytes = want;
+    return PCU_B200_OK;
+}
+
+int cell_cap_for(long long n, double occupancy) {
+    double c = (double)n / occupancy;
+    if (c < 1.0) c = 1.0;
+    if (c > (double)(1 << 27)) c = (double)(1 << 27);
+    return (int)c;
+}
+
+float occupancy_for(const pcu_b200_workspace* ws, int k) {
+    if (ws->opts.cell_occupancy > 0.f) return ws->opts.cell_occupancy;
+    if (k <= 1) return 2.0f;
+    return std::max(2.0f, 0.5f * (float)k);
+}
+
+// What one call works on: `batch` independent pairs (first cloud: n points, second: m points).
+template <typename T>
+struct PlanSpec {
+    long long batch = 1;
+    const T* a = nullptr;   // (batch, n, 3)
+    const T* b = nullptr;   // (batch, m, 3)
+    long long n = 0, m = 0;
+    int nsweeps = 1;        // 1: first -> second;  2: both directions
+    int k = 1;
+    int squared = 0;
+    bool want_stats = false;
+    bool want_out = false;
+    float occupancy = 2.f;
+    T* out_dist = nullptr;          // want_out (batch == 1)
+    long long* out_idx = nullptr;
+    pcu_b200_nn_stats* stats = nullptr;   // caller's device buffer, or null -> carved from the arena
+    long long replay_points = 0;
+};
+
+// Scratch layout of one call.  Every per-cloud / per-sweep buffer is an array over the batch with
+// a uniform stride, so descriptors can be generated on the device.
+template <typename T>
+struct Plan {
+    DescriptorArgs<T> args{};
+    Cloud<T>* d_clouds = nullptr;
+    Sweep<T>* d_sweeps = nullptr;
+    pcu_b200_nn_stats* d_stats = nullptr;
+    unsigned char* zero_begin = nullptr;
+    size_t zero_bytes = 0;
+    long long max_n = 0;
+    int max_cap = 0;
+    int nclouds = 0, nsweeps_total = 0;
+    size_t total = 0;
+    KdReplayBuffers<T> replay{};
+
+    template <typename U>
+    static U* take_strided(Carver& cv, size_t count_per_item, long long batch, size_t& stride_bytes) {
+        stride_bytes = align_up(count_per_item * sizeof(U));
+        return reinterpret_cast<U*>(cv.take<unsigned char>(stride_bytes * (size_t)batch));
+    }
+
+    // Carves (or, with base == nullptr, just measures) the layout.
+    void layout(unsigned char* base, const PlanSpec<T>& sp) {
+        Carver cv(base);
+        const long long B = sp.batch;
+        nclouds = (int)(2 * B);
+        nsweeps_total = (int)(B * sp.nsweeps);
+        d_clouds = cv.take<Cloud<T>>((size_t)nclouds);
+        d_sweeps = cv.take<Sweep<T>>((size_t)nsweeps_total);
+        d_stats = sp.stats ? sp.stats : (sp.want_stats ? cv.take<pcu_b200_nn_stats>((size_t)nsweeps_total) : nullptr);
+        args = DescriptorArgs<T>{};
+        args.batch = B;
+        args.nsweeps = sp.nsweeps;
+        args.stats = sp.want_stats ? d_stats : nullptr;
+        const long long sizes[2] = {sp.n, sp.m};
+        const T* raws[2] = {sp.a, sp.b};
+        max_n = std::max(sp.n, sp.m);
+        max_cap = 0;
+        // zeroed region first: cell counters and sweep counters
+        const size_t zero_from = cv.off;
+        for (int s = 0; s < 2; ++s) {
+            Cloud<T>& cl = args.cloud[s];
+            cl.raw = raws[s];
+            cl.n = sizes[s];
+            cl.cell_cap = cell_cap_for(sizes[s], sp.occupancy);
+            cl.stride = std::min(kMaxGridDim, cl.cell_cap) + 1;
+            args.cs[s].raw = (size_t)3 * sizes[s] * sizeof(T);
+            cl.cell_start = take_strided<unsigned>(cv, (size_t)cl.cell_cap + 1, B, args.cs[s].cell_start);
+            max_cap = std::max(max_cap, cl.cell_cap);
+        }
+        for (int d = 0; d < sp.nsweeps; ++d)
+            args.sweep[d].counters = take_strided<unsigned>(cv, 4, B, args.ss[d].counters);
+        zero_begin = base ? base + zero_from : nullptr;
+        zero_bytes = cv.off - zero_from;
+        for (int s = 0; s < 2; ++s) {
+            Cloud<T>& cl = args.cloud[s];
+            CloudStrides& st = args.cs[s];
+            cl.sorted = take_strided<Pt<T>>(cv, (size_t)cl.n, B, st.sorted);
+            cl.rank = take_strided<unsigned>(cv, (size_t)cl.n, B, st.rank);
+            cl.grid = take_strided<GridHeader<T>>(cv, 1, B, st.grid);
+            cl.wall_lo = take_strided<T>(cv, (size_t)3 * cl.stride, B, st.wall_lo);
+            cl.wall_hi = take_strided<T>(cv, (size_t)3 * cl.stride, B, st.wall_hi);
+            cl.bbox_partial = take_strided<T>(cv, (size_t)kBBoxBlocks * 6, B, st.bbox_partial);
+            cl.scan_partial = take_strided<unsigned>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
+                                                     st.scan_partial);
+        }
+        for (int d = 0; d < sp.nsweeps; ++d) {
+            Sweep<T>& sw = args.sweep[d];
+            SweepStrides& st = args.ss[d];
+            sw.k = sp.k;
+            sw.squared = sp.squared;
+            const long long nq = sizes[d];
+            sw.main_blocks = (int)((nq + kThreads - 1) / kThreads);
+            sw.far_list = take_strided<unsigned>(cv, (size_t)nq, B, st.far_list);
+            if (sp.want_out) {
+                sw.tie_list = take_strided<long long>(cv, (size_t)nq, B, st.tie_list);
+                sw.out_dist = sp.out_dist;   // batch == 1 on this path
+                sw.out_idx = sp.out_idx;
+            }
+            if (sp.want_stats)
+                sw.partial = take_strided<SweepPartial<T>>(cv, (size_t)2 * sw.main_blocks + 2, B, st.partial);
+        }
+        if (sp.replay_points > 0) replay.carve(cv, sp.replay_points);
+        total = cv.off;
+    }
+};
+
+template <typename T>
+int upload_descriptors(Plan<T>& plan, cudaStream_t stream) {
+    const unsigned blocks = (unsigned)((plan.args.batch + 127) / 128);
+    PCU_LAUNCH(descriptors_kernel<T>, blocks, 128, stream, plan.args, plan.d_clouds, plan.d_sweeps);
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, const PlanSpec<T>& spec) {
+    plan.layout(nullptr, spec);
+    PCU_TRY(ensure_arena(ws, plan.total));
+    plan.layout(ws->arena, spec);
+    return PCU_B200_OK;
+}
+
+// bbox -> grid -> histogram -> scan -> scatter for every cloud of the plan
+template <typename T>
+int enqueue_binning(const Plan<T>& plan, cudaStream_t stream) {
+    const int nclouds = plan.nclouds;
+    PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
+    const unsigned pts_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
+    const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
+    PCU_LAUNCH(bbox_partial_kernel<T>, dim3(kBBoxBlocks, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(grid_setup_kernel<T>, dim3(1, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(cell_count_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(scan_reduce_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(scan_partials_kernel<T>, dim3(1, nclouds), kScanThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(scan_apply_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(scatter_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int check_cloud_args(const void* a, long long n, const void* b, long long m) {
+    if (!a || !b) return fail(PCU_B200_INVALID_ARGUMENT, "null point-cloud pointer");
+    if (n <= 0 || m <= 0)
+        return fail(PCU_B200_INVALID_ARGUMENT,
+                    "Invalid input set with zero elements: both clouds must have shape (n, 3) with n > 0 "
+                    "(got %lld and %lld rows)", n, m);
+    const long long lim = sizeof(T) == 4 ? 0x7fffffffLL : (1LL << 40);
+    if (n >= lim || m >= lim) return fail(PCU_B200_INVALID_ARGUMENT, "point cloud too large (%lld, %lld rows)", n, m);
+    return PCU_B200_OK;
+}
+
+// ---- k nearest neighbours ---------------------------------------------------------------------
+template <typename T>
+int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dataset, long long m, int k, int squared,
+               T* out_dist, long long* out_idx, long long* out_n_tied, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid value for k (%d) must be greater than 0.", k);
+    PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
+    if (!out_dist || !out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    if ((double)n * (double)k >= 9e18) return fail(PCU_B200_INVALID_ARGUMENT, "n * k overflows");
+    PCU_CUDA(cudaSetDevice(ws->device));
+
+    PlanSpec<T> spec;
+    spec.a = query; spec.n = n; spec.b = dataset; spec.m = m;
+    spec.nsweeps = 1; spec.k = k; spec.squared = squared; spec.want_out = true;
+    spec.occupancy = occupancy_for(ws, k);
+    spec.out_dist = out_dist; spec.out_idx = out_idx;
+    spec.replay_points = ws->opts.disable_tie_replay ? 0 : m;
+    Plan<T> plan;
+    PCU_TRY(prepare_plan(ws, plan, spec));
+    PCU_TRY(upload_descriptors(plan, stream));
+    PCU_TRY(enqueue_binning(plan, stream));
+    const unsigned qblocks = (unsigned)((n + kThreads - 1) / kThreads);
+    if (k == 1) {
+        PCU_LAUNCH((nn1_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    } else if (k <= 32) {
+        const unsigned wblocks = (unsigned)((n * 32 + kThreads - 1) / kThreads);
+        PCU_LAUNCH(knn_warp_kernel<T>, dim3(wblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    } else {
+        PCU_LAUNCH(knn_big_kernel<T>, dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    }
+    if (!ws->opts.disable_tie_replay) {
+        const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
+        PCU_TRY((enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
+                                       plan.args.sweep[0].counters + 1, out_dist, out_idx, stream, g_launches)));
+    }
+    if (out_n_tied) {
+        PCU_LAUNCH(widen_counter_kernel, 1, 1, stream, plan.args.sweep[0].counters + 1, out_n_tied);
+    }
+    return PCU_B200_OK;
+}
+
+// ---- fused k = 1 statistics -------------------------------------------------------------------
+// nsweeps == 1: query -> dataset.  nsweeps == 2: x -> y and y -> x over the same two binned clouds.
+template <typename T>
+int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
+                 pcu_b200_nn_stats* out_stats, T* out_value, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    PCU_TRY(check_cloud_args<T>(a, n, b, m));
+    if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    const int ns = both ? 2 : 1;
+    PlanSpec<T> spec;
+    spec.a = a; spec.n = n; spec.b = b; spec.m = m;
+    spec.nsweeps = ns; spec.k = 1; spec.want_stats = true;
+    spec.occupancy = occupancy_for(ws, 1);
+    spec.stats = out_stats;
+    spec.replay_points = ws->opts.disable_tie_replay ? 0 : std::max(n, m);
+    Plan<T> plan;
+    PCU_TRY(prepare_plan(ws, plan, spec));
+    PCU_TRY(upload_descriptors(plan, stream));
+    PCU_TRY(enqueue_binning(plan, stream));
+    const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
+    PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    if (!ws->opts.disable_tie_replay) {
+        // Only the Hausdorff witness (argmax_data) can depend on tie order; replay that one query.
+        const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
+        for (int s = 0; s < ns; ++s) {
+            const T* qs = s == 0 ? a : b;
+            const T* ds = s == 0 ? b : a;
+            const long long dm = s == 0 ? m : n;
+            PCU_TRY((enqueue_witness_replay<T>(plan.replay, qs, ds, dm, leaf, plan.args.sweep[s].counters + 2,
+                                               out_stats + s, stream, g_launches)));
+        }
+    }
+    if (both && out_value) {
+        PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, out_stats, 1LL, out_value, (double*)nullptr);
+    }
+    return PCU_B200_OK;
+}
+
+// ---- batched Chamfer ---------------------------------------------------------------------------
+template <typename T>
+int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long long batch, long long n, long long m,
+                           T* out_per_pair, double* out_sum, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (batch <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "batch must be positive (got %lld)", batch);
+    PCU_TRY(check_cloud_args<T>(x, n, y, m));
+    if (!out_per_pair && !out_sum) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    // gridDim.y carries the cloud / sweep index: at most 65535, i.e. 32767 pairs per slice
+    const long long slice = 16384;
+    if (batch > slice && out_sum)
+        return fail(PCU_B200_INVALID_ARGUMENT, "out_sum is only supported for batches of at most %lld pairs", slice);
+    for (long long first = 0; first < batch; first += slice) {
+        const long long B = std::min(slice, batch - first);
+        PlanSpec<T> spec;
+        spec.batch = B;
+        spec.a = x + first * 3 * n; spec.n = n; spec.b = y + first * 3 * m; spec.m = m;
+        spec.nsweeps = 2; spec.k = 1; spec.want_stats = true;
+        spec.occupancy = occupancy_for(ws, 1);
+        Plan<T> plan;
+        PCU_TRY(prepare_plan(ws, plan, spec));
+        PCU_TRY(upload_descriptors(plan, stream));
+        PCU_TRY(enqueue_binning(plan, stream));
+        const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
+        PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,
+                   out_per_pair ? out_per_pair + first : (T*)nullptr, out_sum);
+    }
+    return PCU_B200_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int pcu_b200_abi_version(void) { return PCU_B200_ABI_VERSION; }
+const char* pcu_b200_last_error(void) { return g_error.c_str(); }
+int64_t pcu_b200_launch_count(void) { return g_launches.load(); }
+
+int pcu_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int usable = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++usable;
+    }
+    return usable;
+}
+
+int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
+    if (!out_ws) return fail(PCU_B200_INVALID_ARGUMENT, "null out_ws");
+    *out_ws = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(PCU_B200_NO_DEVICE, "no CUDA device visible: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(PCU_B200_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+    int major = 0, sms = 0;
+    PCU_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    PCU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (major != 10)
+        return fail(PCU_B200_NO_DEVICE, "device %d has compute capability %d.x; this build only carries sm_100a code",
+                    device, major);
+    pcu_b200_workspace* ws = new (std::nothrow) pcu_b200_workspace();
+    if (!ws) return fail(PCU_B200_OUT_OF_MEMORY, "out of host memory");
+    ws->device = device;
+    ws->sm_count = sms;
+    PCU_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    *out_ws = ws;
+    return PCU_B200_OK;
+}
+
+int pcu_b200_workspace_destroy(pcu_b200_workspace* ws) {
+    if (!ws) return PCU_B200_OK;
+    cudaSetDevice(ws->device);
+    cudaDeviceSynchronize();
+    if (ws->arena) cudaFree(ws->arena);
+    if (ws->io) cudaFree(ws->io);
+    if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
+    delete ws;
+    return PCU_B200_OK;
+}
+
+int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws) {
+    return ws ? (int64_t)(ws->arena_bytes + ws->io_bytes) : 0;
+}
+
+int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts) {
+    if (!ws || !opts) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
+    if (opts->max_points_per_leaf < 0) return fail(PCU_B200_INVALID_ARGUMENT, "max_points_per_leaf must be >= 0");
+    if (opts->cell_occupancy < 0.f) return fail(PCU_B200_INVALID_ARGUMENT, "cell_occupancy must be >= 0");
+    ws->opts = *opts;
+    return PCU_B200_OK;
+}
+
+int pcu_b200_knn_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m, int k,
+                     int squared, float* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream) {
+    return knn_device<float>(ws, query, n, dataset, m, k, squared, out_dist, (long long*)out_idx,
+                             (long long*)out_n_tied, (cudaStream_t)stream);
+}
+int pcu_b200_knn_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m, int k,
+                     int squared, double* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream) {
+    return knn_device<double>(ws, query, n, dataset, m, k, squared, out_dist, (long long*)out_idx,
+                              (long long*)out_n_tied, (cudaStream_t)stream);
+}
+int pcu_b200_nn_stats_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m,
+                          pcu_b200_nn_stats* out_stats, void* stream) {
+    return stats_device<float>(ws, query, n, dataset, m, false, out_stats, nullptr, (cudaStream_t)stream);
+}
+int pcu_b200_nn_stats_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m,
+                          pcu_b200_nn_stats* out_stats, void* stream) {
+    return stats_device<double>(ws, query, n, dataset, m, false, out_stats, nullptr, (cudaStream_t)stream);
+}
+int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const float* y, int64_t m,
+                         pcu_b200_nn_stats* out_stats, float* out_value, void* stream) {
+    return stats_device<float>(ws, x, n, y, m, true, out_stats, out_value, (cudaStream_t)stream);
+}
+int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
+                         pcu_b200_nn_stats* out_stats, double* out_value, void* stream) {
+    return stats_device<double>(ws, x, n, y, m, true, out_stats, out_value, (cudaStream_t)stream);
+}
+
+int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
+                                 int64_t m, float* out_per_pair, double* out_sum, void* stream) {
+    return batched_chamfer_device<float>(ws, x, y, batch, n, m, out_per_pair, out_sum, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+#include "host_entry.inl"

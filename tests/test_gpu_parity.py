@@ -1,0 +1,145 @@
+"""GPU: the CUDA path (through the pybind11 module and the C ABI) against the golden vectors the
+reference's own nanoflann path produced, and against the oracle on fresh seeded inputs.
+
+Bars: int64 indices bit-exact, distances bit-exact (same rounded arithmetic), Chamfer / Hausdorff
+scalars within 1e-6 relative (BASELINE.json)."""
+import numpy as np
+import pytest
+
+from conftest import knn_cases, knn_golden_names, load_golden, metric_golden_names
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6
+
+
+@pytest.mark.parametrize("name", knn_golden_names())
+def test_knn_matches_reference_goldens(pcu, name):
+    g = load_golden(name)
+    q, d = g["query"], g["dataset"]
+    for k, leaf, sq, dist, idx in knn_cases(g):
+        got_d, got_i = pcu.k_nearest_neighbors(q, d, k, squared_distances=sq, max_points_per_leaf=leaf)
+        assert got_i.dtype == np.int64 and got_d.dtype == q.dtype
+        assert got_i.shape == idx.shape and got_d.shape == dist.shape, (name, k)
+        assert np.array_equal(got_d, dist), (name, k, leaf, sq, "distances")
+        assert np.array_equal(got_i, idx), (name, k, leaf, sq, "indices")
+
+
+@pytest.mark.parametrize("name", metric_golden_names())
+def test_metrics_match_reference_goldens(pcu, name):
+    g = load_golden(name)
+    x, y = g["x"], g["y"]
+    for sq in (0, 1):
+        assert pcu.one_sided_hausdorff_distance(x, y, True, bool(sq)) == tuple(g["one_sided_xy_sq%d" % sq])
+        assert pcu.one_sided_hausdorff_distance(y, x, True, bool(sq)) == tuple(g["one_sided_yx_sq%d" % sq])
+        assert pcu.one_sided_hausdorff_distance(x, y, False, bool(sq)) == g["one_sided_xy_sq%d" % sq][0]
+        assert pcu.hausdorff_distance(x, y, True, bool(sq)) == tuple(g["hausdorff_sq%d" % sq])
+        assert pcu.hausdorff_distance(x, y, False, bool(sq)) == g["hausdorff_sq%d" % sq][0]
+    c = pcu.chamfer_distance(x, y)
+    assert c.dtype == x.dtype
+    assert abs(float(c) - float(g["chamfer_f64"])) <= REL * float(g["chamfer_f64"])
+    c2, cxy, cyx = pcu.chamfer_distance(x, y, return_index=True)
+    assert abs(float(c2) - float(g["chamfer_f64"])) <= REL * float(g["chamfer_f64"])
+    assert np.array_equal(cxy, g["corrs_xy"]) and np.array_equal(cyx, g["corrs_yx"])
+    for p, key in ((1, "chamfer_p1"), (np.inf, "chamfer_pinf")):
+        v = float(pcu.chamfer_distance(x, y, p_norm=p))
+        assert abs(v - float(g[key])) <= REL * float(g[key])
+
+
+def test_reference_test_suite_properties(pcu):
+    """The assertions of /root/reference/tests/test_examples.py:337-425, with seeded inputs."""
+    rng = np.random.default_rng(123)
+    for _ in range(3):
+        a, b = rng.random((1000, 3)), rng.random((500, 3))
+        k = int(rng.integers(10)) + 1
+        d, c = pcu.k_nearest_neighbors(a, b, k)
+        assert d.shape == ((1000, k) if k > 1 else (1000,)) and c.shape == d.shape
+        if k == 1:
+            d, c = d[:, None], c[:, None]
+        assert np.all(np.abs(np.linalg.norm(a[:, None, :] - b[c], axis=-1) - d) < 1e-5)
+    with pytest.raises(ValueError):
+        pcu.k_nearest_neighbors(rng.random((1000, 3)), rng.random((500, 3)), 0)
+    a, b = rng.random((100, 3)), rng.random((50, 3))
+    d1, c1 = pcu.k_nearest_neighbors(a, b, 3)
+    d2, c2 = pcu.k_nearest_neighbors(a, b, 3, squared_distances=True)
+    assert np.all(c1 == c2) and np.all(np.abs(d1 ** 2.0 - d2) < 1e-5)
+    a, b = rng.random((1000, 3)), rng.random((500, 3))
+    h_ab, ia1, ib1 = pcu.one_sided_hausdorff_distance(a, b, return_index=True)
+    h_ba, ib2, ia2 = pcu.one_sided_hausdorff_distance(b, a, return_index=True)
+    h, i1, i2 = pcu.hausdorff_distance(a, b, return_index=True)
+    assert h == max(h_ab, h_ba)
+    assert abs(h - np.linalg.norm(a[i1] - b[i2])) < 1e-7
+    assert (i1, i2) == ((ia1, ib1) if h_ab > h_ba else (ia2, ib2))
+    pcu.chamfer_distance(a[:100], b[:100])
+    c, cab, cba = pcu.chamfer_distance(a[:100], b[:100], return_index=True)
+    assert cab.shape == (100,) and cba.shape == (100,)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("k", [1, 2, 7, 16, 32, 40])
+def test_knn_against_oracle_fresh(pcu, oracle, dtype, k):
+    rng = np.random.default_rng(1000 + k)
+    q = rng.random((20000, 3)).astype(dtype)
+    d = rng.random((30000, 3)).astype(dtype)
+    got_d, got_i = pcu.k_nearest_neighbors(q, d, k)
+    ref_d, ref_i = oracle.k_nearest_neighbors(q, d, k)
+    assert np.array_equal(got_i, ref_i)
+    assert np.array_equal(got_d, ref_d)
+
+
+def test_storage_orders_and_views(pcu, oracle):
+    rng = np.random.default_rng(5)
+    q = np.asfortranarray(rng.random((3000, 3), dtype=np.float32))
+    big = rng.random((8000, 6), dtype=np.float32)
+    d = big[::2, 1:4]          # strided, non-contiguous view
+    got = pcu.k_nearest_neighbors(q, d, 3)
+    ref = oracle.k_nearest_neighbors(np.ascontiguousarray(q), np.ascontiguousarray(d), 3)
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+
+
+def test_torch_cuda_inputs_stay_on_device(pcu, oracle):
+    import torch
+    rng = np.random.default_rng(9)
+    x = rng.random((50000, 3), dtype=np.float32)
+    y = rng.random((40000, 3), dtype=np.float32)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    d, i = pcu.k_nearest_neighbors(xt, yt, 1)
+    assert d.is_cuda and i.is_cuda and i.dtype == torch.int64 and d.shape == (50000,)
+    rd, ri = oracle.k_nearest_neighbors(x, y, 1)
+    assert np.array_equal(i.cpu().numpy(), ri) and np.array_equal(d.cpu().numpy(), rd)
+    c = pcu.chamfer_distance(xt, yt)
+    assert c.is_cuda and c.dtype == torch.float32 and c.dim() == 0
+    ref = float(oracle.chamfer_distance(x, y))
+    assert abs(float(c) - ref) <= REL * ref
+    assert pcu.hausdorff_distance(xt, yt, return_index=True) == oracle.hausdorff_distance(x, y, return_index=True)
+    d16, i16 = pcu.k_nearest_neighbors(xt.double(), yt.double(), 16, squared_distances=True)
+    r16 = oracle.k_nearest_neighbors(x.astype(np.float64), y.astype(np.float64), 16, True)
+    assert np.array_equal(i16.cpu().numpy(), r16[1]) and np.array_equal(d16.cpu().numpy(), r16[0])
+
+
+def test_full_size_properties_c2_c3(pcu):
+    """BASELINE configs[1] / [2] sizes (2 x 1e6 x 3 fp32): properties that need no CPU sweep."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((1000000, 3), generator=g, device="cuda")
+    y = torch.rand((1000000, 3), generator=g, device="cuda")
+    d, i = pcu.k_nearest_neighbors(x, y, 1)
+    # (a) the returned distance is the distance to the returned index, in the reference's rounding
+    diff = x - y[i]
+    d2 = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
+    assert torch.equal(d, torch.sqrt(d2))
+    # (b) no point of a random subset of y is closer (brute force on 2048 queries)
+    sub = torch.randperm(1000000, generator=g, device="cuda")[:2048]
+    brute = torch.cdist(x[sub].double(), y.double()).min(dim=1).values
+    assert torch.all((d[sub].double() - brute).abs() <= 1e-6)
+    # (c) self-query: every point is its own nearest neighbour at distance 0
+    ds, is_ = pcu.k_nearest_neighbors(x, x, 1)
+    assert torch.all(ds == 0) and torch.equal(x[is_], x)
+    # (d) fused Chamfer equals the mean of the per-point distances from the KNN path
+    c = pcu.chamfer_distance(x, y)
+    d_yx, _ = pcu.k_nearest_neighbors(y, x, 1)
+    ref = d.double().mean() + d_yx.double().mean()
+    assert abs(float(c) - float(ref)) <= REL * float(ref)
+    # (e) Hausdorff is the max of those distances, witnessed by its index pair
+    h, hi, hj = pcu.hausdorff_distance(x, y, return_index=True)
+    assert h == max(float(d.max()), float(d_yx.max()))
+    assert abs(h - float(torch.linalg.vector_norm(x[hi] - y[hj]))) <= 1e-6
