@@ -69,6 +69,10 @@ typedef struct pcu_b200_nn_stats {
     int64_t n_queries;    /* n                                                                    */
     int64_t n_tied;       /* queries whose nearest neighbour was decided by tie order             */
     int64_t n_far;        /* queries that needed the ring-expansion slow path (diagnostic)        */
+    int64_t witness_tied; /* 1: argmax_query had several equally near neighbours, so argmax_data  */
+                          /* is the lowest such index, not necessarily the reference's pick; the  */
+                          /* host entry points resolve this themselves, device callers use        */
+                          /* pcu_b200_resolve_witness_* (value, sums and argmax_query are final)   */
 } pcu_b200_nn_stats;
 
 /* Tunables; zero-initialise and override what you need.  0 always means "library default". */
@@ -99,6 +103,8 @@ int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_option
  * out_idx  : (n, k) row-major int64 indices into dataset
  * out_n_tied (may be NULL): device int64 that receives the number of queries that went through
  *            the tie replay.
+ * Unless disable_tie_replay is set, this call synchronises `stream` once (it reads the number of
+ * flagged queries back to decide whether the kd-tree replay has to run at all).
  * Replaces shortest_distances_nanoflann (src/point_cloud_distance.cpp:21-99).                    */
 int pcu_b200_knn_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m, int k,
                      int squared, float* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream);
@@ -113,6 +119,15 @@ int pcu_b200_nn_stats_f32(pcu_b200_workspace* ws, const float* query, int64_t n,
                           pcu_b200_nn_stats* out_stats, void* stream);
 int pcu_b200_nn_stats_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m,
                           pcu_b200_nn_stats* out_stats, void* stream);
+
+/* Re-answers stats->argmax_query with the reference's tie order (kd-tree replay built with
+ * max_points_per_leaf) and stores the result in stats->argmax_data; clears witness_tied.
+ * `stats` is a DEVICE pointer to one record produced by the calls above for (query, dataset).
+ * Synchronises the stream (the replay builds the tree level by level).                           */
+int pcu_b200_resolve_witness_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset,
+                                 int64_t m, pcu_b200_nn_stats* stats, void* stream);
+int pcu_b200_resolve_witness_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset,
+                                 int64_t m, pcu_b200_nn_stats* stats, void* stream);
 
 /* ---- fused bidirectional Chamfer (+ Hausdorff), DEVICE pointers ----------------------------
  * out_stats : device pointer to TWO pcu_b200_nn_stats: [0] = x -> y, [1] = y -> x.
@@ -148,6 +163,18 @@ int pcu_b200_chamfer_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n
                               pcu_b200_nn_stats* out_stats, double* out_value);
 int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
                                       int64_t n, int64_t m, float* out_per_pair, double* out_sum);
+
+/* ---- diagnostics ----------------------------------------------------------------------------
+ * Builds the kd-tree replica used by the tie replay for HOST points and copies it out, so tests can
+ * compare it node for node with the reference's tree.  order: (m) slot -> point index (nanoflann's
+ * vAcc); per node (capacity node_cap, at most 2 m - 1 are used): split dimension (-1 = leaf),
+ * divlow, divhigh, slot range [first, last), children.  Returns the node count through out_nodes.  */
+int pcu_b200_debug_kd_tree_f32(pcu_b200_workspace* ws, const float* points, int64_t m, int max_points_per_leaf,
+                               int32_t* order, int64_t node_cap, int32_t* feat, float* div_lo, float* div_hi,
+                               int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes);
+int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int64_t m, int max_points_per_leaf,
+                               int32_t* order, int64_t node_cap, int32_t* feat, double* div_lo, double* div_hi,
+                               int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes);
 
 #ifdef __cplusplus
 }

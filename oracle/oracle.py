@@ -120,9 +120,9 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
     rc = fn(*args, dists.ctypes.data, corrs.ctypes.data)
     if rc != 0:
         raise RuntimeError("oracle call failed (rc=%d)" % rc)
-    if k == 1:  # npe::move squeezes size-1 dims (tests/test_examples.py:363-368)
-        return dists[:, 0], corrs[:, 0]
-    return dists, corrs
+    # npe::move hands the Eigen matrix to numpy and squeezes every size-1 dimension ((n, 1) -> (n,) is
+    # pinned by tests/test_examples.py:363-368; numpyeigen itself is not in the reference tree)
+    return dists.squeeze(), corrs.squeeze()
 
 
 def one_sided_hausdorff_distance(source, target, return_index=True, squared_distances=False, max_points_per_leaf=10,

@@ -39,8 +39,7 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
            "batched_chamfer_distance", "device_count", "launch_count"]
 
-_STATS_FIELDS = ("sum_dist", "sum_sq_dist", "max_sq_dist", "argmax_query", "argmax_data", "n_queries", "n_tied",
-                 "n_far")
+_STATS_WORDS = 9   # sizeof(pcu_b200_nn_stats) / 8
 
 
 def device_count():
@@ -99,16 +98,28 @@ def _stats_from_tensor(buf, which):
     host = buf.cpu()
     f = host.view(_torch().float64)
     i = host.view(_torch().int64)
-    o = 8 * which
+    o = _STATS_WORDS * which
     return {"sum_dist": float(f[o]), "sum_sq_dist": float(f[o + 1]), "max_sq_dist": float(f[o + 2]),
             "argmax_query": int(i[o + 3]), "argmax_data": int(i[o + 4]), "n_queries": int(i[o + 5]),
-            "n_tied": int(i[o + 6]), "n_far": int(i[o + 7])}
+            "n_tied": int(i[o + 6]), "n_far": int(i[o + 7]), "witness_tied": int(i[o + 8])}
+
+
+def _resolved_stats(buf, which, q, d, leaf):
+    """Stats record `which` of `buf`; when its Hausdorff witness hinges on tie order, have the device replay it."""
+    st = _stats_from_tensor(buf, which)
+    if st["witness_tied"]:
+        torch = _torch()
+        _pcu_internal._resolve_witness_device(q.dtype == torch.float64, q.data_ptr(), q.shape[0], d.data_ptr(),
+                                              d.shape[0], buf.data_ptr() + 8 * _STATS_WORDS * which, int(leaf),
+                                              q.device.index or 0, _stream_of(q))
+        st = _stats_from_tensor(buf, which)
+    return st
 
 
 def _stats_device(a, b, both, leaf):
     torch = _torch()
-    assert _pcu_internal._stats_nbytes() == 64
-    buf = torch.empty(16, dtype=torch.int64, device=a.device)
+    assert _pcu_internal._stats_nbytes() == 8 * _STATS_WORDS
+    buf = torch.empty(2 * _STATS_WORDS, dtype=torch.int64, device=a.device)
     val = torch.empty((), dtype=a.dtype, device=a.device)
     _pcu_internal._stats_device(a.dtype == torch.float64, both, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0],
                                 buf.data_ptr(), val.data_ptr() if both else 0, int(leaf), a.device.index or 0,
@@ -194,7 +205,7 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
             return _pcu_internal.one_sided_hausdorff_distance(s.numpy(), t.numpy(), bool(return_index),
                                                               bool(squared_distances), int(max_points_per_leaf))
         buf, _ = _stats_device(s, t, False, max_points_per_leaf)
-        st = _stats_from_tensor(buf, 0)
+        st = _resolved_stats(buf, 0, s, t, max_points_per_leaf)
         value = _metric_value(st["max_sq_dist"], squared_distances,
                               _np.float32 if s.dtype == _torch().float32 else _np.float64)
         if return_index:
@@ -212,7 +223,7 @@ def _both_stats(x, y, max_points_per_leaf):
         xs, ys = _check_tensor_pair(x, y, "x", "y")
         if xs.is_cuda:
             buf, val = _stats_device(xs, ys, True, max_points_per_leaf)
-            return ("cuda", xs.dtype, val, buf)
+            return ("cuda", xs.dtype, val, (buf, xs, ys))
         x, y = xs.numpy(), ys.numpy()
     val, sxy, syx = _pcu_internal._chamfer_stats(_np.asarray(x), _np.asarray(y), int(max_points_per_leaf))
     return ("host", _np.asarray(x).dtype.type, val, (sxy, syx))
@@ -241,7 +252,9 @@ def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_po
     """
     where, dtype, _, st = _both_stats(x, y, max_points_per_leaf)
     if where == "cuda":
-        sxy, syx = _stats_from_tensor(st, 0), _stats_from_tensor(st, 1)
+        buf, xs, ys = st
+        sxy = _resolved_stats(buf, 0, xs, ys, max_points_per_leaf)
+        syx = _resolved_stats(buf, 1, ys, xs, max_points_per_leaf)
         np_t = _np.float32 if dtype == _torch().float32 else _np.float64
     else:
         sxy, syx = st

@@ -175,6 +175,7 @@ py::dict stats_to_dict(const pcu_b200_nn_stats& s) {
     d["n_queries"] = s.n_queries;
     d["n_tied"] = s.n_tied;
     d["n_far"] = s.n_far;
+    d["witness_tied"] = s.witness_tied;
     return d;
 }
 
@@ -321,6 +322,56 @@ void batched_chamfer_device(uintptr_t x, uintptr_t y, int64_t B, int64_t n, int6
     check(status);
 }
 
+template <typename T>
+py::dict debug_kd_tree_t(const py::array& pts_in, int leaf, int device) {
+    auto pts = dense<T>(pts_in);
+    const int64_t m = pts.shape(0);
+    const int64_t cap = 2 * m + 2;
+    py::array_t<int32_t> order(m), feat(cap), first(cap), last(cap), kid0(cap), kid1(cap);
+    py::array_t<T> lo(cap), hi(cap);
+    int64_t nn = 0;
+    pcu_b200_workspace* ws = pool().get(device, 0);
+    int status;
+    if (sizeof(T) == 4)
+        status = pcu_b200_debug_kd_tree_f32(ws, (const float*)pts.data(), m, leaf, order.mutable_data(), cap,
+                                            feat.mutable_data(), (float*)lo.mutable_data(), (float*)hi.mutable_data(),
+                                            first.mutable_data(), last.mutable_data(), kid0.mutable_data(),
+                                            kid1.mutable_data(), &nn);
+    else
+        status = pcu_b200_debug_kd_tree_f64(ws, (const double*)pts.data(), m, leaf, order.mutable_data(), cap,
+                                            feat.mutable_data(), (double*)lo.mutable_data(), (double*)hi.mutable_data(),
+                                            first.mutable_data(), last.mutable_data(), kid0.mutable_data(),
+                                            kid1.mutable_data(), &nn);
+    check(status);
+    py::dict d;
+    d["order"] = order; d["feat"] = feat; d["div_lo"] = lo; d["div_hi"] = hi; d["first"] = first; d["last"] = last;
+    d["kid0"] = kid0; d["kid1"] = kid1; d["n_nodes"] = nn;
+    return d;
+}
+
+py::dict debug_kd_tree(const py::array& pts, int leaf, int device) {
+    if (pts.ndim() != 2 || pts.shape(1) != 3 || pts.shape(0) == 0) throw py::value_error("points must be (m, 3)");
+    const int dev = current_device_or_default(device);
+    if (pts.dtype().is(py::dtype::of<float>())) return debug_kd_tree_t<float>(pts, leaf, dev);
+    if (pts.dtype().is(py::dtype::of<double>())) return debug_kd_tree_t<double>(pts, leaf, dev);
+    throw py::value_error("points must be float32 or float64");
+}
+
+void resolve_witness_device(bool is_f64, uintptr_t q, int64_t n, uintptr_t d, int64_t m, uintptr_t stats,
+                            int max_points_per_leaf, int device, uintptr_t stream) {
+    pcu_b200_workspace* ws = pool().get(device, stream);
+    apply_options(ws, max_points_per_leaf);
+    int status;
+    {
+        py::gil_scoped_release nogil;
+        status = is_f64 ? pcu_b200_resolve_witness_f64(ws, (const double*)q, n, (const double*)d, m,
+                                                       (pcu_b200_nn_stats*)stats, (void*)stream)
+                        : pcu_b200_resolve_witness_f32(ws, (const float*)q, n, (const float*)d, m,
+                                                       (pcu_b200_nn_stats*)stats, (void*)stream);
+    }
+    check(status);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_pcu_internal, mod) {
@@ -341,6 +392,9 @@ PYBIND11_MODULE(_pcu_internal, mod) {
     mod.def("_batched_chamfer_device", &batched_chamfer_device);
     mod.def("_knn_device", &knn_device);
     mod.def("_stats_device", &stats_device);
+    mod.def("_resolve_witness_device", &resolve_witness_device);
+    mod.def("_debug_kd_tree", &debug_kd_tree, py::arg("points"), py::arg("max_points_per_leaf") = 10,
+            py::arg("device") = -1);
     mod.def("_stats_nbytes", []() { return (int)sizeof(pcu_b200_nn_stats); });
     mod.def("_device_count", []() { return pcu_b200_device_count(); });
     mod.def("_launch_count", []() { return (int64_t)pcu_b200_launch_count(); });

@@ -63,6 +63,17 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     PCU_CUDA(cudaMemcpyAsync(out_stats, ds, sizeof(pcu_b200_nn_stats) * (both ? 2 : 1), cudaMemcpyDeviceToHost, st));
     if (both && out_value) PCU_CUDA(cudaMemcpyAsync(out_value, dv, sizeof(T), cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
+    // Hausdorff witnesses whose neighbour was decided by tie order: replay with the reference's tree
+    if (!ws->opts.disable_tie_replay) {
+        for (int s = 0; s < (both ? 2 : 1); ++s) {
+            if (!out_stats[s].witness_tied) continue;
+            const T* qs = s == 0 ? da : db;
+            const T* dsrc = s == 0 ? db : da;
+            PCU_TRY(resolve_witness_device<T>(ws, qs, s == 0 ? n : m, dsrc, s == 0 ? m : n, ds + s, st));
+            PCU_CUDA(cudaMemcpyAsync(out_stats + s, ds + s, sizeof(pcu_b200_nn_stats), cudaMemcpyDeviceToHost, st));
+            PCU_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     return PCU_B200_OK;
 }
 
@@ -96,6 +107,40 @@ int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long lo
     return PCU_B200_OK;
 }
 
+template <typename T>
+int debug_kd_tree(pcu_b200_workspace* ws, const T* points, long long m, int leaf, int32_t* order, long long node_cap,
+                  int32_t* feat, T* div_lo, T* div_hi, int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1,
+                  int64_t* out_nodes) {
+    if (!ws || !points || m <= 0 || leaf <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "bad argument");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_CUDA(cudaDeviceSynchronize());
+    KdReplayBuffers<T> rb;
+    T* dpts;
+    Carver measure(nullptr);
+    rb.carve(measure, m);
+    dpts = measure.take<T>((size_t)3 * m);
+    PCU_TRY(ensure_arena(ws, measure.off));
+    Carver cv(ws->arena);
+    rb.carve(cv, m);
+    dpts = cv.take<T>((size_t)3 * m);
+    cudaStream_t st = ws->own_stream;
+    PCU_CUDA(cudaMemcpyAsync(dpts, points, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
+    const int rs = build_kd_replica<T>(rb, dpts, m, leaf, st, g_launches);
+    if (rs != PCU_B200_OK) return fail(rs, "kd replica build failed: %s", cudaGetErrorString(cudaGetLastError()));
+    KdCounters hc;
+    PCU_CUDA(cudaMemcpyAsync(&hc, rb.counters, sizeof hc, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaMemcpyAsync(order, rb.order, sizeof(int) * m, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    std::vector<KdNode<T>> nodes((size_t)hc.n_nodes);
+    PCU_CUDA(cudaMemcpy(nodes.data(), rb.nodes, sizeof(KdNode<T>) * nodes.size(), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < hc.n_nodes && i < node_cap; ++i) {
+        feat[i] = nodes[i].feat; div_lo[i] = nodes[i].div_lo; div_hi[i] = nodes[i].div_hi;
+        first[i] = nodes[i].first; last[i] = nodes[i].last; kid0[i] = nodes[i].kid0; kid1[i] = nodes[i].kid1;
+    }
+    *out_nodes = hc.n_nodes;
+    return PCU_B200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -125,6 +170,18 @@ int pcu_b200_chamfer_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n
     return stats_host<double>(ws, x, n, y, m, true, out_stats, out_value);
 }
 
+int pcu_b200_debug_kd_tree_f32(pcu_b200_workspace* ws, const float* points, int64_t m, int max_points_per_leaf,
+                               int32_t* order, int64_t node_cap, int32_t* feat, float* div_lo, float* div_hi,
+                               int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes) {
+    return debug_kd_tree<float>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
+                                kid0, kid1, out_nodes);
+}
+int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int64_t m, int max_points_per_leaf,
+                               int32_t* order, int64_t node_cap, int32_t* feat, double* div_lo, double* div_hi,
+                               int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes) {
+    return debug_kd_tree<double>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
+                                 kid0, kid1, out_nodes);
+}
 int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
                                       int64_t n, int64_t m, float* out_per_pair, double* out_sum) {
     return batched_chamfer_host<float>(ws, x, y, batch, n, m, out_per_pair, out_sum);

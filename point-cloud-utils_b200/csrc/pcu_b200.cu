@@ -365,8 +365,9 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     }
     if (!ws->opts.disable_tie_replay) {
         const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
-        PCU_TRY((enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
-                                       plan.args.sweep[0].counters + 1, out_dist, out_idx, stream, g_launches)));
+        const int rs = enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
+                                             plan.args.sweep[0].counters + 1, out_dist, out_idx, stream, g_launches);
+        if (rs != PCU_B200_OK) return fail(rs, "tie replay failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (out_n_tied) {
         PCU_LAUNCH(widen_counter_kernel, 1, 1, stream, plan.args.sweep[0].counters + 1, out_n_tied);
@@ -389,7 +390,6 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     spec.nsweeps = ns; spec.k = 1; spec.want_stats = true;
     spec.occupancy = occupancy_for(ws, 1);
     spec.stats = out_stats;
-    spec.replay_points = ws->opts.disable_tie_replay ? 0 : std::max(n, m);
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec));
     PCU_TRY(upload_descriptors(plan, stream));
@@ -398,20 +398,30 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-    if (!ws->opts.disable_tie_replay) {
-        // Only the Hausdorff witness (argmax_data) can depend on tie order; replay that one query.
-        const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
-        for (int s = 0; s < ns; ++s) {
-            const T* qs = s == 0 ? a : b;
-            const T* ds = s == 0 ? b : a;
-            const long long dm = s == 0 ? m : n;
-            PCU_TRY((enqueue_witness_replay<T>(plan.replay, qs, ds, dm, leaf, plan.args.sweep[s].counters + 2,
-                                               out_stats + s, stream, g_launches)));
-        }
-    }
     if (both && out_value) {
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, out_stats, 1LL, out_value, (double*)nullptr);
     }
+    return PCU_B200_OK;
+}
+
+// ---- Hausdorff witness under ties ---------------------------------------------------------------
+template <typename T>
+int resolve_witness_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dataset, long long m,
+                           pcu_b200_nn_stats* stats, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
+    if (!stats) return fail(PCU_B200_INVALID_ARGUMENT, "null stats pointer");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_CUDA(cudaStreamSynchronize(stream));   // the arena is about to be re-carved
+    KdReplayBuffers<T> rb;
+    Carver measure(nullptr);
+    rb.carve(measure, m);
+    PCU_TRY(ensure_arena(ws, measure.off));
+    Carver cv(ws->arena);
+    rb.carve(cv, m);
+    const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
+    const int rs = enqueue_witness_replay<T>(rb, query, dataset, m, leaf, stats, stream, g_launches);
+    if (rs != PCU_B200_OK) return fail(rs, "witness replay failed: %s", cudaGetErrorString(cudaGetLastError()));
     return PCU_B200_OK;
 }
 
@@ -535,6 +545,14 @@ int pcu_b200_nn_stats_f32(pcu_b200_workspace* ws, const float* query, int64_t n,
 int pcu_b200_nn_stats_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset, int64_t m,
                           pcu_b200_nn_stats* out_stats, void* stream) {
     return stats_device<double>(ws, query, n, dataset, m, false, out_stats, nullptr, (cudaStream_t)stream);
+}
+int pcu_b200_resolve_witness_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset,
+                                 int64_t m, pcu_b200_nn_stats* stats, void* stream) {
+    return resolve_witness_device<float>(ws, query, n, dataset, m, stats, (cudaStream_t)stream);
+}
+int pcu_b200_resolve_witness_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset,
+                                 int64_t m, pcu_b200_nn_stats* stats, void* stream) {
+    return resolve_witness_device<double>(ws, query, n, dataset, m, stats, (cudaStream_t)stream);
 }
 int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const float* y, int64_t m,
                          pcu_b200_nn_stats* out_stats, float* out_value, void* stream) {

@@ -327,8 +327,7 @@ __global__ void __launch_bounds__(kThreads) stats_finalize_kernel(const Cloud<T>
         s.n_queries = n;
         s.n_tied = result.n_tied;
         s.n_far = n_far;
-        // tie_at_max is surfaced through counters[2] so the host can replay that single query
-        sw.counters[2] = result.tie_at_max;
+        s.witness_tied = result.tie_at_max ? 1 : 0;
         *sw.stats = s;
     }
 }

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(pcu):
 
 
 def test_stats_struct_layout(pcu):
-    assert pcu._pcu_internal._stats_nbytes() == 64
+    assert pcu._pcu_internal._stats_nbytes() == 72
 
 
 def test_no_cpu_fallback_without_gpu(pcu):

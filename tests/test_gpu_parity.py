@@ -143,3 +143,40 @@ def test_full_size_properties_c2_c3(pcu):
     h, hi, hj = pcu.hausdorff_distance(x, y, return_index=True)
     assert h == max(float(d.max()), float(d_yx.max()))
     assert abs(h - float(torch.linalg.vector_norm(x[hi] - y[hj]))) <= 1e-6
+
+
+def _walk_equal(a, b, na, nb, path=""):
+    """Recursively compare two kd-trees given as dicts of arrays (node numbering may differ)."""
+    assert a["feat"][na] == b["feat"][nb], ("split dim", path)
+    assert a["first"][na] == b["first"][nb] and a["last"][na] == b["last"][nb], ("range", path)
+    if a["feat"][na] < 0:
+        return 1
+    assert a["div_lo"][na] == b["div_lo"][nb] and a["div_hi"][na] == b["div_hi"][nb], ("planes", path)
+    return 1 + _walk_equal(a, b, a["kid0"][na], b["kid0"][nb], path + "L") + \
+        _walk_equal(a, b, a["kid1"][na], b["kid1"][nb], path + "R")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_kd_replica_equals_reference_tree(pcu, oracle, dtype):
+    """The GPU replica of the reference's kd-tree (used for tie replay): same permutation (vAcc), same
+    split planes, same leaves as the oracle's build, which is pinned to nanoflann's."""
+    import sys
+    sys.setrecursionlimit(10000)
+    rng = np.random.default_rng(77)
+    base = rng.random((3000, 3)).astype(dtype)
+    clouds = {
+        "uniform": rng.random((20000, 3)).astype(dtype),
+        "duplicates": np.concatenate([base, base, base[:500]]),
+        "lattice": np.stack(np.meshgrid(*[np.arange(12)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(dtype),
+        "planar": np.concatenate([rng.random((4000, 2)), np.full((4000, 1), 0.25)], axis=1).astype(dtype),
+        "identical": np.full((500, 3), 0.5, dtype),
+        "clustered": np.concatenate([rng.normal(0.2, 0.01, (3000, 3)), rng.normal(0.8, 0.03, (3000, 3))]).astype(dtype),
+        "tiny": rng.random((7, 3)).astype(dtype),
+    }
+    for name, pts in clouds.items():
+        for leaf in (10, 1, 3):
+            got = pcu._pcu_internal._debug_kd_tree(pts, leaf)
+            ref = oracle.kd_tree(pts, leaf)
+            assert np.array_equal(np.asarray(got["order"], dtype=np.int64), ref["order"]), (name, leaf, "order")
+            n_ref = _walk_equal(got, ref, 0, 0)
+            assert n_ref == len(ref["feat"]) == got["n_nodes"], (name, leaf)
