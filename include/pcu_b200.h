@@ -95,8 +95,14 @@ int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws);
 int pcu_b200_workspace_destroy(pcu_b200_workspace* ws);
 /* Bytes of device scratch currently held. */
 int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws);
-/* Average kernel time per algorithm stage of the LAST call when profiling is enabled (diagnostic). */
 int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts);
+/* Per-stage device timing (diagnostic; bench.py's roofline pass).  When enabled, every device entry
+ * point records CUDA events on the launching stream between its stages; after that stream has been
+ * synchronised, last_profile() returns the milliseconds of the LAST call's 8 stages (descriptors,
+ * bbox+grid, histogram, scan, scatter, search, search_far, finalize) and their count (0 if none). */
+int pcu_b200_workspace_set_profiling(pcu_b200_workspace* ws, int enabled);
+int pcu_b200_workspace_last_profile(pcu_b200_workspace* ws, float* out_ms, int capacity);
+const char* pcu_b200_profile_stage_name(int stage);
 
 /* ---- k nearest neighbours, DEVICE pointers -------------------------------------------------
  * out_dist : (n, k) row-major, input precision; sqrt(d2) unless squared != 0

@@ -402,6 +402,16 @@ PYBIND11_MODULE(_pcu_internal, mod) {
     mod.def("_workspace_bytes", [](int device, uintptr_t stream) {
         return (int64_t)pcu_b200_workspace_bytes(pool().get(device, stream));
     });
+    mod.def("_set_profiling", [](int device, uintptr_t stream, bool on) {
+        check(pcu_b200_workspace_set_profiling(pool().get(device, stream), on ? 1 : 0));
+    });
+    mod.def("_last_profile", [](int device, uintptr_t stream) {
+        float ms[8];
+        const int n = pcu_b200_workspace_last_profile(pool().get(device, stream), ms, 8);
+        py::dict d;
+        for (int i = 0; i < n; ++i) d[py::str(pcu_b200_profile_stage_name(i))] = ms[i];
+        return d;
+    });
     mod.def("_set_defaults", [](float cell_occupancy, bool disable_tie_replay) {
         defaults().occupancy = cell_occupancy;
         defaults().disable_replay = disable_tie_replay ? 1 : 0;

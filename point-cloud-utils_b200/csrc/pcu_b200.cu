@@ -128,7 +128,13 @@ struct pcu_b200_workspace {
     size_t io_bytes = 0;
     pcu_b200_options opts{};
     int sm_count = 148;
+    // optional per-stage timing (bench.py's roofline pass): events recorded on the launching stream
+    bool profiling = false;
+    cudaEvent_t marks[9] = {};
+    int marks_used = 0;
 };
+
+#define PCU_STAGE_NAMES "descriptors", "bbox+grid", "histogram", "scan", "scatter", "search", "search_far", "finalize"
 
 namespace {
 
@@ -166,6 +172,12 @@ int ensure_io(pcu_b200_workspace* ws, size_t bytes) {
     }
     ws->io_bytes = want;
     return PCU_B200_OK;
+}
+
+void mark(pcu_b200_workspace* ws, int index, cudaStream_t stream) {
+    if (!ws->profiling) return;
+    cudaEventRecord(ws->marks[index], stream);
+    ws->marks_used = index + 1;
 }
 
 int cell_cap_for(long long n, double occupancy) {
@@ -305,18 +317,22 @@ int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, const PlanSpec<T>& spec)
 
 // bbox -> grid -> histogram -> scan -> scatter for every cloud of the plan
 template <typename T>
-int enqueue_binning(const Plan<T>& plan, cudaStream_t stream) {
+int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream) {
     const int nclouds = plan.nclouds;
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
     const unsigned pts_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
     PCU_LAUNCH(bbox_partial_kernel<T>, dim3(kBBoxBlocks, nclouds), kThreads, stream, plan.d_clouds);
     PCU_LAUNCH(grid_setup_kernel<T>, dim3(1, nclouds), kThreads, stream, plan.d_clouds);
+    mark(ws, 2, stream);
     PCU_LAUNCH(cell_count_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    mark(ws, 3, stream);
     PCU_LAUNCH(scan_reduce_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
     PCU_LAUNCH(scan_partials_kernel<T>, dim3(1, nclouds), kScanThreads, stream, plan.d_clouds);
     PCU_LAUNCH(scan_apply_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
+    mark(ws, 4, stream);
     PCU_LAUNCH(scatter_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    mark(ws, 5, stream);
     return PCU_B200_OK;
 }
 
@@ -351,17 +367,25 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     spec.replay_points = ws->opts.disable_tie_replay ? 0 : m;
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec));
+    mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
-    PCU_TRY(enqueue_binning(plan, stream));
+    mark(ws, 1, stream);
+    PCU_TRY(enqueue_binning(ws, plan, stream));
     const unsigned qblocks = (unsigned)((n + kThreads - 1) / kThreads);
     if (k == 1) {
         PCU_LAUNCH((nn1_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        mark(ws, 6, stream);
         PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        mark(ws, 7, stream);
     } else if (k <= 32) {
         const unsigned wblocks = (unsigned)((n * 32 + kThreads - 1) / kThreads);
         PCU_LAUNCH(knn_warp_kernel<T>, dim3(wblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        mark(ws, 6, stream);
+        mark(ws, 7, stream);
     } else {
         PCU_LAUNCH(knn_big_kernel<T>, dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        mark(ws, 6, stream);
+        mark(ws, 7, stream);
     }
     if (!ws->opts.disable_tie_replay) {
         const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
@@ -372,6 +396,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     if (out_n_tied) {
         PCU_LAUNCH(widen_counter_kernel, 1, 1, stream, plan.args.sweep[0].counters + 1, out_n_tied);
     }
+    mark(ws, 8, stream);
     return PCU_B200_OK;
 }
 
@@ -392,15 +417,20 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     spec.stats = out_stats;
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec));
+    mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
-    PCU_TRY(enqueue_binning(plan, stream));
+    mark(ws, 1, stream);
+    PCU_TRY(enqueue_binning(ws, plan, stream));
     const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
     PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    mark(ws, 6, stream);
     PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    mark(ws, 7, stream);
     PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     if (both && out_value) {
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, out_stats, 1LL, out_value, (double*)nullptr);
     }
+    mark(ws, 8, stream);
     return PCU_B200_OK;
 }
 
@@ -447,14 +477,19 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         spec.occupancy = occupancy_for(ws, 1);
         Plan<T> plan;
         PCU_TRY(prepare_plan(ws, plan, spec));
+        mark(ws, 0, stream);
         PCU_TRY(upload_descriptors(plan, stream));
-        PCU_TRY(enqueue_binning(plan, stream));
+        mark(ws, 1, stream);
+        PCU_TRY(enqueue_binning(ws, plan, stream));
         const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
         PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        mark(ws, 6, stream);
         PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        mark(ws, 7, stream);
         PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,
                    out_per_pair ? out_per_pair + first : (T*)nullptr, out_sum);
+        mark(ws, 8, stream);
     }
     return PCU_B200_OK;
 }
@@ -512,12 +547,41 @@ int pcu_b200_workspace_destroy(pcu_b200_workspace* ws) {
     if (ws->arena) cudaFree(ws->arena);
     if (ws->io) cudaFree(ws->io);
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
+    for (auto& e : ws->marks) if (e) cudaEventDestroy(e);
     delete ws;
     return PCU_B200_OK;
 }
 
 int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws) {
     return ws ? (int64_t)(ws->arena_bytes + ws->io_bytes) : 0;
+}
+
+int pcu_b200_workspace_set_profiling(pcu_b200_workspace* ws, int enabled) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    PCU_CUDA(cudaSetDevice(ws->device));
+    if (enabled && !ws->marks[0])
+        for (auto& e : ws->marks) PCU_CUDA(cudaEventCreate(&e));
+    ws->profiling = enabled != 0;
+    ws->marks_used = 0;
+    return PCU_B200_OK;
+}
+
+int pcu_b200_workspace_last_profile(pcu_b200_workspace* ws, float* out_ms, int capacity) {
+    if (!ws || !out_ms) return -1;
+    if (!ws->profiling || ws->marks_used < 9) return 0;
+    if (cudaEventSynchronize(ws->marks[8]) != cudaSuccess) { cudaGetLastError(); return -1; }
+    int n = 0;
+    for (; n < 8 && n < capacity; ++n) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ws->marks[n], ws->marks[n + 1]) != cudaSuccess) { cudaGetLastError(); return -1; }
+        out_ms[n] = ms;
+    }
+    return n;
+}
+
+const char* pcu_b200_profile_stage_name(int stage) {
+    static const char* names[] = {PCU_STAGE_NAMES};
+    return stage >= 0 && stage < 8 ? names[stage] : "";
 }
 
 int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts) {
