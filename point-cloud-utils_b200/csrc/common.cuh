@@ -146,13 +146,16 @@ struct Cloud {
     GridHeader<T>* grid;
     T* wall_lo;             // 3 * stride
     T* wall_hi;             // 3 * stride
-    T* bbox_partial;        // kBBoxBlocks * 6
+    T* bbox_partial;        // bbox_blocks * 6
     unsigned* scan_partial; // per-scan-block totals
     int cell_cap;           // upper bound on ncells (host-known)
     int stride;             // wall table stride (host-known)
+    int bbox_blocks;        // partial bounding boxes of this cloud (host-known, <= kMaxBBoxBlocks)
+    int pad;
 };
 
-constexpr int kBBoxBlocks = 128;        // partial bounding boxes per cloud
+constexpr int kMaxBBoxBlocks = 1024;    // partial bounding boxes per cloud, upper bound
+constexpr int kBBoxPerThread = 8;       // scalars each thread folds per pass
 constexpr int kScanItems = 8;           // items per thread in the scan
 constexpr int kScanThreads = 512;
 constexpr int kScanTile = kScanItems * kScanThreads;

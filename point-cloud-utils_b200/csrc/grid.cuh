@@ -13,26 +13,40 @@
 namespace pcu {
 
 // ---------------------------------------------------------------------------------------------
-// 1. partial bounding boxes: grid (kBBoxBlocks, nclouds)
+// 1. partial bounding boxes: grid (max bbox_blocks, nclouds)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const Cloud<T>* __restrict__ clouds) {
     using R = Real<T>;
     const Cloud<T> c = clouds[blockIdx.y];
+    if ((int)blockIdx.x >= c.bbox_blocks) return;
     T lo[3] = {R::inf(), R::inf(), R::inf()};
     T hi[3] = {-R::inf(), -R::inf(), -R::inf()};
-    // flat, fully coalesced walk over the 3n scalars; the axis of element e is e % 3
+    // Flat, fully coalesced walk over the 3n scalars.  Each thread folds kBBoxPerThread scalars per
+    // pass, spaced 3 * blockDim apart so that all of them belong to the same axis; the loads of a
+    // pass are independent, which keeps several requests in flight per thread.
     const long long total = 3 * c.n;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int axis = (int)(e % 3);
-    const int axis_step = (int)(step % 3);
-    for (; e < total; e += step) {
-        const T v = __ldg(c.raw + e);
+    const long long pass = (long long)c.bbox_blocks * blockDim.x * 3 * kBBoxPerThread;
+    T vlo = R::inf(), vhi = -R::inf();
+    for (long long base = ((long long)blockIdx.x * kBBoxPerThread) * (3 * blockDim.x) + threadIdx.x; base < total; base += pass) {
+        T v[kBBoxPerThread];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-            if (a == axis) { lo[a] = R::vmin(lo[a], v); hi[a] = R::vmax(hi[a], v); }
-        axis += axis_step;
-        if (axis >= 3) axis -= 3;
+        for (int k = 0; k < kBBoxPerThread; ++k) {
+            const long long e = base + (long long)k * 3 * blockDim.x;
+            v[k] = e < total ? __ldg(c.raw + e) : R::inf();
+        }
+#pragma unroll
+        for (int k = 0; k < kBBoxPerThread; ++k) {
+            const long long e = base + (long long)k * 3 * blockDim.x;
+            vlo = R::vmin(vlo, v[k]);
+            if (e < total) vhi = R::vmax(vhi, v[k]);
+        }
+    }
+    // every index this thread touched is threadIdx.x plus a multiple of 3
+    const int my_axis = (int)(threadIdx.x % 3);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = a == my_axis ? vlo : R::inf();
+        hi[a] = a == my_axis ? vhi : -R::inf();
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -64,51 +78,88 @@ __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const Cloud<T>* __
     using bits_t = typename R::bits_t;
     const Cloud<T> c = clouds[blockIdx.y];
     __shared__ T box[6];
+    __shared__ T red[kThreads / 32][6];
     __shared__ GridHeader<T> hdr;
-    if (threadIdx.x < 6) {
-        T v = c.bbox_partial[threadIdx.x];
-        for (int i = 1; i < kBBoxBlocks; ++i) {
-            const T u = c.bbox_partial[i * 6 + threadIdx.x];
-            v = threadIdx.x < 3 ? R::vmin(v, u) : R::vmax(v, u);
+    __shared__ double s_ext[3], s_lo, s_hi;
+    __shared__ int s_first;
+    {   // fold the partial boxes: thread t takes partials t, t + blockDim, ...
+        T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
+        for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = R::vmin(lo[a], c.bbox_partial[i * 6 + a]);
+                hi[a] = R::vmax(hi[a], c.bbox_partial[i * 6 + 3 + a]);
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            T v = red[0][threadIdx.x];
+            for (int i = 1; i < kThreads / 32; ++i)
+                v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
+            box[threadIdx.x] = v;
         }
-        box[threadIdx.x] = v;
+        __syncthreads();
+    }
+    const int maxdim = c.stride - 1;
+    if (threadIdx.x == 0) {
+        double emax = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            double e = (double)box[3 + a] - (double)box[a];
+            if (!(e > 0.0)) e = 0.0;        // also swallows NaN
+            if (!(e < 1e300)) e = 1e300;    // +inf input: keep the arithmetic finite
+            s_ext[a] = e;
+            emax = fmax(emax, e);
+        }
+        s_lo = emax / (double)maxdim;       // finest admissible cell (no axis exceeds maxdim cells)
+        s_hi = emax;                        // a single cell
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const int maxdim = c.stride - 1;
-        double ext[3], emax = 0.0;
-        for (int a = 0; a < 3; ++a) {
-            ext[a] = (double)box[3 + a] - (double)box[a];
-            if (!(ext[a] > 0.0)) ext[a] = 0.0;      // also swallows NaN
-            if (!(ext[a] < 1e300)) ext[a] = 1e300;  // +inf input: keep the arithmetic finite
-            emax = fmax(emax, ext[a]);
-        }
-        double h = 1.0;
-        if (emax > 0.0) {
-            auto cells_at = [&](double hh) {
-                double p = 1.0;
-                for (int a = 0; a < 3; ++a) {
-                    double d = ceil(ext[a] / hh);
-                    d = fmin(fmax(d, 1.0), (double)maxdim);
-                    p *= d;
-                }
-                return p;
-            };
-            double lo_h = emax / (double)maxdim, hi_h = emax;   // cells_at(hi_h) == 1
-            const double cap = (double)c.cell_cap;
-            if (cells_at(lo_h) <= cap) {
-                h = lo_h;
-            } else {
-                for (int it = 0; it < 64; ++it) {
-                    const double mid = 0.5 * (lo_h + hi_h);
-                    if (cells_at(mid) <= cap) hi_h = mid; else lo_h = mid;
-                }
-                h = hi_h;
+    const double ext0 = s_ext[0], ext1 = s_ext[1], ext2 = s_ext[2];
+    const double emax = s_hi;
+    const double cap = (double)c.cell_cap;
+    auto cells_at = [&](double hh) {
+        const double d0 = fmin(fmax(ceil(ext0 / hh), 1.0), (double)maxdim);
+        const double d1 = fmin(fmax(ceil(ext1 / hh), 1.0), (double)maxdim);
+        const double d2 = fmin(fmax(ceil(ext2 / hh), 1.0), (double)maxdim);
+        return d0 * d1 * d2;
+    };
+    // Smallest h with cells_at(h) <= cap (cells_at is non-increasing in h): three rounds of a
+    // blockDim-ary search over a geometric ladder between s_lo and s_hi.
+    if (emax > 0.0) {
+        for (int round = 0; round < 3; ++round) {
+            const double lo_h = s_lo, hi_h = s_hi;
+            __syncthreads();
+            if (threadIdx.x == 0) s_first = blockDim.x - 1;
+            __syncthreads();
+            const double frac = (double)(threadIdx.x + 1) / (double)blockDim.x;
+            const double cand = threadIdx.x + 1 == blockDim.x ? hi_h : lo_h * pow(hi_h / lo_h, frac);
+            if (cells_at(cand) <= cap) atomicMin(&s_first, (int)threadIdx.x);
+            __syncthreads();
+            const int first = s_first;
+            __syncthreads();
+            if ((int)threadIdx.x == first) {
+                s_hi = cand;
+                if (first > 0) s_lo = lo_h * pow(hi_h / lo_h, (double)first / (double)blockDim.x);
             }
+            __syncthreads();
         }
+    }
+    if (threadIdx.x == 0) {
+        double h = emax > 0.0 ? s_hi : 1.0;
+        if (emax > 0.0 && cells_at(s_lo) <= cap) h = s_lo;
         long long nc = 1;
         for (int a = 0; a < 3; ++a) {
-            double d = emax > 0.0 ? ceil(ext[a] / h) : 1.0;
+            double d = emax > 0.0 ? ceil(s_ext[a] / h) : 1.0;
             d = fmin(fmax(d, 1.0), (double)maxdim);
             hdr.dim[a] = (int)d;
             nc *= (long long)d;

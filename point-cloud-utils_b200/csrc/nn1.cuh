@@ -1,0 +1,269 @@
+// nn1.cuh -- the k = 1 sweep (per-point outputs and / or fused Chamfer-Hausdorff statistics).
+//
+// This is the hot kernel of the path: it replaces the reference's per-query kd-tree descent
+// (external/nanoflann/nanoflann.hpp:1545-1624) for every query of both directions of a Chamfer /
+// Hausdorff call, and fuses the reductions the reference does afterwards on the CPU
+// (src/point_cloud_distance.cpp:221-225, point_cloud_utils/__init__.py:112-113), so no per-point
+// distance buffer is ever written for the scalar metrics.
+#pragma once
+#include "search.cuh"
+
+namespace pcu {
+
+// Per-thread table of the 9 rows (fixed y, z; three x-adjacent cells = one contiguous run of the
+// sorted dataset) of a query's 3 x 3 x 3 neighbourhood, nearest rows first.  Indexed [row][thread]
+// so that lanes hit distinct banks whatever row each lane is currently on.
+template <typename T>
+struct RowTable {
+    unsigned begin[9][kThreads];
+    unsigned end[9][kThreads];
+    T bound[9][kThreads];
+};
+
+// Main pass: one thread per (cell-sorted) query.
+//   phase A (uniform): look up the 9 runs and the wall bound of each row;
+//   phase B (flattened): ONE loop in which a lane either evaluates its next candidate or steps to its
+//     next row that is not pruned by its bound.  Lanes therefore stay busy until their own total
+//     work is done, instead of idling in nine separate loops of different lengths.
+// grid (ceil(max_n / kThreads), nsweeps).
+template <typename T, bool kOut, bool kStats>
+__global__ void __launch_bounds__(kThreads) nn1_kernel(const Cloud<T>* __restrict__ clouds,
+                                                       const Sweep<T>* __restrict__ sweeps) {
+    using R = Real<T>;
+    const Sweep<T> sw = sweeps[blockIdx.y];
+    const Cloud<T> qc = clouds[sw.qcloud];
+    const Cloud<T> dc = clouds[sw.dcloud];
+    if ((long long)blockIdx.x * blockDim.x >= qc.n) return;   // blocks beyond this sweep's queries
+    __shared__ GridHeader<T> g;
+    __shared__ RowTable<T> rows;
+    if (threadIdx.x == 0) g = *dc.grid;
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + tid;
+    const bool active = t < qc.n;
+    Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
+    bool settled = false;
+    long long row = -1;
+    if (active) {
+        const Pt<T> q = load_pt<T>(qc.sorted + t);
+        row = (long long)q.i;
+        const int st = g.stride;
+        const T* lo_x = dc.wall_lo;           const T* hi_x = dc.wall_hi;
+        const T* lo_y = dc.wall_lo + st;      const T* hi_y = dc.wall_hi + st;
+        const T* lo_z = dc.wall_lo + 2 * st;  const T* hi_z = dc.wall_hi + 2 * st;
+        const int cx = cell_of<T>(q.x, g.origin[0], g.inv_h, g.dim[0]);
+        const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
+        const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
+        const int xa = max(cx - 1, 0), xb = min(cx + 1, g.dim[0] - 1);
+        // gaps to the walls of the query's own cell along y and z
+        const T gy[3] = {(T)0, sq_gap<T>(q.y, __ldg(lo_y + cy)), sq_gap<T>(q.y, __ldg(hi_y + cy + 1))};
+        const T gz[3] = {(T)0, sq_gap<T>(q.z, __ldg(lo_z + cz)), sq_gap<T>(q.z, __ldg(hi_z + cz + 1))};
+        // (dy, dz) as indices into {0: same, 1: minus one, 2: plus one}; nearest rows first
+        const int order_y[9] = {0, 1, 2, 0, 0, 1, 2, 1, 2};
+        const int order_z[9] = {0, 0, 0, 1, 2, 1, 1, 2, 2};
+#pragma unroll
+        for (int s = 0; s < 9; ++s) {
+            const int oy = order_y[s], oz = order_z[s];
+            const int y = cy + (oy == 1 ? -1 : (oy == 2 ? 1 : 0));
+            const int z = cz + (oz == 1 ? -1 : (oz == 2 ? 1 : 0));
+            unsigned a = 0, b = 0;
+            if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+                const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+                a = __ldg(dc.cell_start + base + xa);
+                b = __ldg(dc.cell_start + base + xb + 1);
+            }
+            rows.begin[s][tid] = a;
+            rows.end[s][tid] = b;
+            rows.bound[s][tid] = R::add(gy[oy], gz[oz]);
+        }
+        int r = 0;
+        unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
+        for (;;) {
+            if (j < e) {
+                const Pt<T> p = load_pt<T>(dc.sorted + j);
+                ++j;
+                offer1<T>(best, dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z), p.i);
+            } else {
+                if (++r >= 9) break;
+                // a row whose bound exceeds the current best only holds strictly farther points
+                if (!(rows.bound[r][tid] > best.d)) { j = rows.begin[r][tid]; e = rows.end[r][tid]; }
+            }
+        }
+        const int ya = max(cy - 1, 0), yb = min(cy + 1, g.dim[1] - 1);
+        const int za = max(cz - 1, 0), zb = min(cz + 1, g.dim[2] - 1);
+        T lb = sq_gap<T>(q.x, __ldg(lo_x + xa));
+        lb = R::vmin(lb, sq_gap<T>(q.x, __ldg(hi_x + xb + 1)));
+        lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(lo_y + ya)));
+        lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(hi_y + yb + 1)));
+        lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(lo_z + za)));
+        lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(hi_z + zb + 1)));
+        settled = best.d < lb;
+        if (!settled) sw.far_list[atomicAdd(sw.counters, 1u)] = (unsigned)t;
+    }
+    double sum = 0.0, sumsq = 0.0;
+    unsigned ties = 0;
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
+    finish_query1<T, kOut, kStats>(sw, active && settled, best, row, sum, sumsq, mc, ties);
+    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + blockIdx.x);
+}
+
+// Merges the running best of two lanes (after each lane has scanned disjoint cells).
+template <typename T>
+__device__ __forceinline__ void merge_best(Best1<T>& a, const Best1<T>& b) {
+    if (b.d < a.d) a = b;
+    else if (b.d == a.d) {
+        a.tie = a.tie || b.tie || (b.i != a.i);
+        a.i = b.i < a.i ? b.i : a.i;
+    }
+}
+
+// Slow pass for the queries the one-ring pass could not settle (empty neighbourhoods, queries
+// outside the dataset's box): one WARP per such query; each ring of cells is split over the lanes
+// (one (y, z) row per lane and step), the lanes' results are merged, and the ring loop stops as soon
+// as the wall bound closes.  grid (sw.far_blocks, nsweeps), warp-stride loop over the far list.
+template <typename T, bool kOut, bool kStats>
+__global__ void __launch_bounds__(kThreads) nn1_far_kernel(const Cloud<T>* __restrict__ clouds,
+                                                           const Sweep<T>* __restrict__ sweeps) {
+    using R = Real<T>;
+    const Sweep<T> sw = sweeps[blockIdx.y];
+    const unsigned n_far = sw.counters[0];
+    const Cloud<T> qc = clouds[sw.qcloud];
+    const Cloud<T> dc = clouds[sw.dcloud];
+    const int lane = threadIdx.x & 31;
+    const unsigned warps_total = gridDim.x * (kThreads / 32);
+    double sum = 0.0, sumsq = 0.0;
+    unsigned ties = 0;
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
+    if (n_far > 0) {
+        const GridHeader<T> g = *dc.grid;
+        const int st = g.stride;
+        const T* lo_x = dc.wall_lo;           const T* hi_x = dc.wall_hi;
+        const T* lo_y = dc.wall_lo + st;      const T* hi_y = dc.wall_hi + st;
+        const T* lo_z = dc.wall_lo + 2 * st;  const T* hi_z = dc.wall_hi + 2 * st;
+        for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total) {
+            const Pt<T> q = load_pt<T>(qc.sorted + sw.far_list[f]);
+            const int cx = cell_of<T>(q.x, g.origin[0], g.inv_h, g.dim[0]);
+            const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
+            const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
+            Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
+            for (int r = 0;; ++r) {
+                const int xa = max(cx - r, 0), xb = min(cx + r, g.dim[0] - 1);
+                const int ya = max(cy - r, 0), yb = min(cy + r, g.dim[1] - 1);
+                const int za = max(cz - r, 0), zb = min(cz + r, g.dim[2] - 1);
+                const int ny = yb - ya + 1, nrows = ny * (zb - za + 1);
+                for (int idx = lane; idx < nrows; idx += 32) {
+                    const int z = za + idx / ny, y = ya + idx % ny;
+                    const T bz = z < cz ? sq_gap<T>(q.z, lo_z[z + 1]) : (z > cz ? sq_gap<T>(q.z, hi_z[z]) : (T)0);
+                    const T by = y < cy ? sq_gap<T>(q.y, lo_y[y + 1]) : (y > cy ? sq_gap<T>(q.y, hi_y[y]) : (T)0);
+                    const T byz = R::add(by, bz);
+                    if (byz > best.d) continue;
+                    const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+                    const bool shell_row = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+                    if (shell_row || r == 0) {
+                        scan_run1<T>(dc.sorted, dc.cell_start[base + xa], dc.cell_start[base + xb + 1], q.x, q.y, q.z, best);
+                    } else {
+                        if (cx - r >= 0 && !(R::add(R::add(sq_gap<T>(q.x, lo_x[cx - r + 1]), by), bz) > best.d))
+                            scan_run1<T>(dc.sorted, dc.cell_start[base + cx - r], dc.cell_start[base + cx - r + 1],
+                                         q.x, q.y, q.z, best);
+                        if (cx + r <= g.dim[0] - 1 && !(R::add(R::add(sq_gap<T>(q.x, hi_x[cx + r]), by), bz) > best.d))
+                            scan_run1<T>(dc.sorted, dc.cell_start[base + cx + r], dc.cell_start[base + cx + r + 1],
+                                         q.x, q.y, q.z, best);
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    Best1<T> other;
+                    other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+                    other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                    other.tie = __shfl_xor_sync(0xffffffffu, (int)best.tie, o) != 0;
+                    merge_best<T>(best, other);
+                }
+                T lb = sq_gap<T>(q.x, lo_x[xa]);
+                lb = R::vmin(lb, sq_gap<T>(q.x, hi_x[xb + 1]));
+                lb = R::vmin(lb, sq_gap<T>(q.y, lo_y[ya]));
+                lb = R::vmin(lb, sq_gap<T>(q.y, hi_y[yb + 1]));
+                lb = R::vmin(lb, sq_gap<T>(q.z, lo_z[za]));
+                lb = R::vmin(lb, sq_gap<T>(q.z, hi_z[zb + 1]));
+                if (best.d < lb) break;
+                if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) break;
+            }
+            finish_query1<T, kOut, kStats>(sw, lane == 0, best, (long long)q.i, sum, sumsq, mc, ties);
+        }
+    }
+    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + blockIdx.x);
+}
+
+// Combines the per-block partials of one sweep into its pcu_b200_nn_stats.  grid (1, nsweeps).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) stats_finalize_kernel(const Cloud<T>* __restrict__ clouds,
+                                                                  const Sweep<T>* __restrict__ sweeps) {
+    const Sweep<T> sw = sweeps[blockIdx.y];
+    const long long n = clouds[sw.qcloud].n;
+    const int main_used = (int)((n + kThreads - 1) / kThreads);
+    const int total = main_used + sw.far_blocks;
+    double sum = 0.0, sumsq = 0.0;
+    unsigned ties = 0;
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
+    constexpr int kBatch = 4;   // independent loads in flight per thread
+    for (int s0 = threadIdx.x; s0 < total; s0 += blockDim.x * kBatch) {
+        SweepPartial<T> p[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int s = s0 + u * blockDim.x;
+            if (s < total) p[u] = sw.partial[s < main_used ? s : sw.main_blocks + (s - main_used)];
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int s = s0 + u * blockDim.x;
+            if (s < total) {
+                sum += p[u].sum; sumsq += p[u].sumsq; ties += p[u].n_tied;
+                MaxCand<T> c; c.d2 = p[u].max_d2; c.q = p[u].arg_q; c.d = p[u].arg_d; c.tie = p[u].tie_at_max;
+                take_max<T>(mc, c);
+            }
+        }
+    }
+    __shared__ SweepPartial<T> result;
+    block_reduce_stats<T>(sum, sumsq, mc, ties, &result);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        pcu_b200_nn_stats s;
+        s.sum_dist = result.sum;
+        s.sum_sq_dist = result.sumsq;
+        s.max_sq_dist = (double)result.max_d2;
+        s.argmax_query = result.arg_q;
+        s.argmax_data = result.arg_d;
+        s.n_queries = n;
+        s.n_tied = result.n_tied;
+        s.n_far = sw.counters[0];
+        s.witness_tied = result.tie_at_max ? 1 : 0;
+        *sw.stats = s;
+    }
+}
+
+// chamfer = mean_x |x - NN_y(x)| + mean_y |y - NN_x(y)|  (point_cloud_utils/__init__.py:112-115)
+// stats: 2 per pair ([2p] = x->y, [2p+1] = y->x).  One block; pairs strided over its threads.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) chamfer_value_kernel(const pcu_b200_nn_stats* __restrict__ stats,
+                                                                 long long npairs, T* __restrict__ out_value,
+                                                                 double* __restrict__ out_sum) {
+    double acc = 0.0;
+    for (long long p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const pcu_b200_nn_stats a = stats[2 * p], b = stats[2 * p + 1];
+        const double v = a.sum_dist / (double)a.n_queries + b.sum_dist / (double)b.n_queries;
+        const T vt = (T)v;
+        if (out_value) out_value[p] = vt;
+        acc += (double)vt;
+    }
+    if (out_sum == nullptr) return;
+    __shared__ double s[kThreads];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_sum = s[0];
+}
+
+}  // namespace pcu

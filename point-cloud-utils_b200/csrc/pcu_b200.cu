@@ -19,6 +19,8 @@
 #include "common.cuh"
 #include "grid.cuh"
 #include "search.cuh"
+#include "nn1.cuh"
+#include "topk.cuh"
 #include "kdreplay.cuh"
 
 using namespace pcu;
@@ -224,6 +226,8 @@ struct Plan {
     size_t zero_bytes = 0;
     long long max_n = 0;
     int max_cap = 0;
+    int max_bbox_blocks = 1;
+    int far_blocks = 1;
     int nclouds = 0, nsweeps_total = 0;
     size_t total = 0;
     KdReplayBuffers<T> replay{};
@@ -251,6 +255,9 @@ struct Plan {
         const T* raws[2] = {sp.a, sp.b};
         max_n = std::max(sp.n, sp.m);
         max_cap = 0;
+        max_bbox_blocks = 1;
+        // far pass: a fixed number of CTAs per sweep (warp-stride loop over the far list)
+        far_blocks = (int)std::max<long long>(4, 592 / std::max<long long>(1, B * sp.nsweeps));
         // zeroed region first: cell counters and sweep counters
         const size_t zero_from = cv.off;
         for (int s = 0; s < 2; ++s) {
@@ -259,6 +266,8 @@ struct Plan {
             cl.n = sizes[s];
             cl.cell_cap = cell_cap_for(sizes[s], sp.occupancy);
             cl.stride = std::min(kMaxGridDim, cl.cell_cap) + 1;
+            cl.bbox_blocks = (int)std::min<long long>(kMaxBBoxBlocks, std::max<long long>(1, (3 * sizes[s] + 2 * kThreads * kBBoxPerThread - 1) / (2 * kThreads * kBBoxPerThread)));
+            max_bbox_blocks = std::max(max_bbox_blocks, cl.bbox_blocks);
             args.cs[s].raw = (size_t)3 * sizes[s] * sizeof(T);
             cl.cell_start = take_strided<unsigned>(cv, (size_t)cl.cell_cap + 1, B, args.cs[s].cell_start);
             max_cap = std::max(max_cap, cl.cell_cap);
@@ -275,7 +284,7 @@ struct Plan {
             cl.grid = take_strided<GridHeader<T>>(cv, 1, B, st.grid);
             cl.wall_lo = take_strided<T>(cv, (size_t)3 * cl.stride, B, st.wall_lo);
             cl.wall_hi = take_strided<T>(cv, (size_t)3 * cl.stride, B, st.wall_hi);
-            cl.bbox_partial = take_strided<T>(cv, (size_t)kBBoxBlocks * 6, B, st.bbox_partial);
+            cl.bbox_partial = take_strided<T>(cv, (size_t)cl.bbox_blocks * 6, B, st.bbox_partial);
             cl.scan_partial = take_strided<unsigned>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
                                                      st.scan_partial);
         }
@@ -286,6 +295,7 @@ struct Plan {
             sw.squared = sp.squared;
             const long long nq = sizes[d];
             sw.main_blocks = (int)((nq + kThreads - 1) / kThreads);
+            sw.far_blocks = far_blocks;
             sw.far_list = take_strided<unsigned>(cv, (size_t)nq, B, st.far_list);
             if (sp.want_out) {
                 sw.tie_list = take_strided<long long>(cv, (size_t)nq, B, st.tie_list);
@@ -293,7 +303,7 @@ struct Plan {
                 sw.out_idx = sp.out_idx;
             }
             if (sp.want_stats)
-                sw.partial = take_strided<SweepPartial<T>>(cv, (size_t)2 * sw.main_blocks + 2, B, st.partial);
+                sw.partial = take_strided<SweepPartial<T>>(cv, (size_t)sw.main_blocks + far_blocks, B, st.partial);
         }
         if (sp.replay_points > 0) replay.carve(cv, sp.replay_points);
         total = cv.off;
@@ -322,7 +332,7 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
     const unsigned pts_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
-    PCU_LAUNCH(bbox_partial_kernel<T>, dim3(kBBoxBlocks, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(bbox_partial_kernel<T>, dim3(plan.max_bbox_blocks, nclouds), kThreads, stream, plan.d_clouds);
     PCU_LAUNCH(grid_setup_kernel<T>, dim3(1, nclouds), kThreads, stream, plan.d_clouds);
     mark(ws, 2, stream);
     PCU_LAUNCH(cell_count_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
@@ -375,7 +385,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     if (k == 1) {
         PCU_LAUNCH((nn1_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
-        PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
     } else if (k <= 32) {
         const unsigned wblocks = (unsigned)((n * 32 + kThreads - 1) / kThreads);
@@ -424,7 +434,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
     PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     mark(ws, 6, stream);
-    PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     mark(ws, 7, stream);
     PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     if (both && out_value) {
@@ -484,7 +494,7 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
         PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
-        PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
         PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,
