@@ -55,31 +55,31 @@ def shard_bounds(batch, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def distributed_batched_chamfer_sum(x_shard, y_shard, group=None, max_points_per_leaf=10):
-    """Every rank passes ITS shard of pairs; returns the fp64 sum of the Chamfer distances of all
-    pairs of all ranks (a 0-dim tensor on the shard's device).  One all-reduce of one scalar."""
+def reduce_sum(local, group=None):
+    """All-reduce (sum) of one fp64 scalar per rank: the only exchange of the sharded batched path."""
     torch = _torch()
     import torch.distributed as dist
-    _, local = batched_chamfer(x_shard, y_shard, max_points_per_leaf, return_sum=True)
     if not isinstance(local, torch.Tensor):
         local = torch.tensor(float(local), dtype=torch.float64)
-    local = local.reshape(1).clone()
+    local = local.to(torch.float64).reshape(1).clone()
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(local, op=dist.ReduceOp.SUM, group=group)
     return local.reshape(())
 
 
-def distributed_batched_chamfer(x_shard, y_shard, batch, group=None, max_points_per_leaf=10):
-    """Every rank passes its shard (see shard_bounds); returns the (batch,) per-pair values on every
-    rank.  One all-gather of at most ceil(batch / world) floats per rank."""
+def gather_values(vals, batch, group=None):
+    """All-gather of the per-pair values of every rank's shard (see shard_bounds) into the (batch,) vector."""
     torch = _torch()
     import torch.distributed as dist
-    vals = batched_chamfer(x_shard, y_shard, max_points_per_leaf)
     if not isinstance(vals, torch.Tensor):
         vals = torch.from_numpy(_np.asarray(vals))
     if not (dist.is_available() and dist.is_initialized()):
         return vals
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_bounds(batch, world, rank)
+    if vals.numel() != hi - lo:
+        raise ValueError("rank %d owns pairs [%d, %d) but passed %d values" % (rank, lo, hi, vals.numel()))
     width = (int(batch) + world - 1) // world
     padded = torch.zeros(width, dtype=vals.dtype, device=vals.device)
     padded[: vals.numel()] = vals
@@ -87,6 +87,19 @@ def distributed_batched_chamfer(x_shard, y_shard, batch, group=None, max_points_
     dist.all_gather(gathered, padded, group=group)
     parts = []
     for r in range(world):
-        lo, hi = shard_bounds(batch, world, r)
-        parts.append(gathered[r][: hi - lo])
+        rlo, rhi = shard_bounds(batch, world, r)
+        parts.append(gathered[r][: rhi - rlo])
     return torch.cat(parts)
+
+
+def distributed_batched_chamfer_sum(x_shard, y_shard, group=None, max_points_per_leaf=10):
+    """Every rank passes ITS shard of pairs; returns the fp64 sum of the Chamfer distances of all
+    pairs of all ranks (a 0-dim tensor on the shard's device).  One all-reduce of one scalar."""
+    _, local = batched_chamfer(x_shard, y_shard, max_points_per_leaf, return_sum=True)
+    return reduce_sum(local, group)
+
+
+def distributed_batched_chamfer(x_shard, y_shard, batch, group=None, max_points_per_leaf=10):
+    """Every rank passes its shard (see shard_bounds); returns the (batch,) per-pair values on every
+    rank.  One all-gather of at most ceil(batch / world) floats per rank."""
+    return gather_values(batched_chamfer(x_shard, y_shard, max_points_per_leaf), batch, group)
