@@ -81,9 +81,15 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const Cloud<T>* __restric
         unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
         for (;;) {
             if (j < e) {
-                const Pt<T> p = load_pt<T>(dc.sorted + j);
-                ++j;
-                offer1<T>(best, dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z), p.i);
+                // two candidates per step: both loads are issued before either distance is needed
+                const bool two = j + 1 < e;
+                const Pt<T> p0 = load_pt<T>(dc.sorted + j);
+                const Pt<T> p1 = load_pt<T>(dc.sorted + (two ? j + 1 : j));
+                j += 2;
+                const T d0 = dist2<T>(q.x, q.y, q.z, p0.x, p0.y, p0.z);
+                const T d1 = dist2<T>(q.x, q.y, q.z, p1.x, p1.y, p1.z);
+                offer1_select<T>(best, d0, p0.i, true);
+                offer1_select<T>(best, d1, p1.i, two);
             } else {
                 if (++r >= 9) break;
                 // a row whose bound exceeds the current best only holds strictly farther points

@@ -388,9 +388,13 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
     } else if (k <= 32) {
-        const unsigned wblocks = (unsigned)((n * 32 + kThreads - 1) / kThreads);
-        PCU_LAUNCH(knn_warp_kernel<T>, dim3(wblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        // thread-per-query lists in registers (capacity = next power of two), warp pass for the rest
+        if (k <= 4)       PCU_LAUNCH((knn_thread_kernel<T, 4>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        else if (k <= 8)  PCU_LAUNCH((knn_thread_kernel<T, 8>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        else if (k <= 16) PCU_LAUNCH((knn_thread_kernel<T, 16>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        else              PCU_LAUNCH((knn_thread_kernel<T, 32>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
+        PCU_LAUNCH((knn_warp_kernel<T, true>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
     } else {
         PCU_LAUNCH(knn_big_kernel<T>, dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);

@@ -63,6 +63,17 @@ __device__ __forceinline__ void offer1(Best1<T>& b, T d, typename Real<T>::index
     }
 }
 
+// Same update as offer1 written with selects (no divergent branch inside the hot loop).
+template <typename T>
+__device__ __forceinline__ void offer1_select(Best1<T>& b, T d, typename Real<T>::index_t i, bool valid) {
+    const bool lt = valid && d < b.d;
+    const bool eq = valid && d == b.d;
+    const typename Real<T>::index_t lower = i < b.i ? i : b.i;
+    b.i = lt ? i : (eq ? lower : b.i);
+    b.tie = !lt && (eq || b.tie);
+    b.d = lt ? d : b.d;
+}
+
 template <typename T>
 __device__ __forceinline__ void scan_run1(const Pt<T>* __restrict__ pts, unsigned a, unsigned b, T qx, T qy, T qz,
                                           Best1<T>& best) {
@@ -137,6 +148,41 @@ __device__ __forceinline__ void take_max(MaxCand<T>& a, const MaxCand<T>& b) {
     if (b.d2 > a.d2 || (b.d2 == a.d2 && b.q < a.q)) a = b;
 }
 
+// Warp-wide take_max; every lane returns the winner.
+template <typename T>
+__device__ __forceinline__ MaxCand<T> warp_take_max(MaxCand<T> mc) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MaxCand<T> other;
+        other.d2 = __shfl_xor_sync(0xffffffffu, mc.d2, o);
+        other.q = __shfl_xor_sync(0xffffffffu, mc.q, o);
+        other.d = __shfl_xor_sync(0xffffffffu, mc.d, o);
+        other.tie = __shfl_xor_sync(0xffffffffu, mc.tie, o);
+        take_max<T>(mc, other);
+    }
+    return mc;
+}
+// fp32: distances are >= 0, so their bit patterns order like the values and the hardware integer
+// reductions (REDUX) do the work: max of the distance bits, then min row among the lanes holding it.
+template <>
+__device__ __forceinline__ MaxCand<float> warp_take_max<float>(MaxCand<float> mc) {
+    const bool real = mc.d2 >= 0.f;   // the neutral element has d2 = -1
+    const unsigned bits = real ? __float_as_uint(mc.d2) : 0u;
+    const unsigned top = __reduce_max_sync(0xffffffffu, bits);
+    const bool holds = real && bits == top;
+    const unsigned row = holds ? (unsigned)mc.q : 0xffffffffu;
+    const unsigned first = __reduce_min_sync(0xffffffffu, row);
+    const unsigned who = __ballot_sync(0xffffffffu, holds && row == first);
+    if (who == 0u) return mc;         // nobody holds a real candidate: all lanes are neutral
+    const int src = __ffs(who) - 1;
+    MaxCand<float> out;
+    out.d2 = __shfl_sync(0xffffffffu, mc.d2, src);
+    out.q = (long long)first;
+    out.d = __shfl_sync(0xffffffffu, mc.d, src);
+    out.tie = __shfl_sync(0xffffffffu, mc.tie, src);
+    return out;
+}
+
 template <typename T>
 __device__ __forceinline__ void block_reduce_stats(double sum, double sumsq, MaxCand<T> mc, unsigned ties,
                                                    SweepPartial<T>* out) {
@@ -147,14 +193,9 @@ __device__ __forceinline__ void block_reduce_stats(double sum, double sumsq, Max
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
-        ties += __shfl_xor_sync(0xffffffffu, ties, o);
-        MaxCand<T> other;
-        other.d2 = __shfl_xor_sync(0xffffffffu, mc.d2, o);
-        other.q = __shfl_xor_sync(0xffffffffu, mc.q, o);
-        other.d = __shfl_xor_sync(0xffffffffu, mc.d, o);
-        other.tie = __shfl_xor_sync(0xffffffffu, mc.tie, o);
-        take_max<T>(mc, other);
     }
+    ties = __reduce_add_sync(0xffffffffu, ties);
+    mc = warp_take_max<T>(mc);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) { s_sum[w] = sum; s_sq[w] = sumsq; s_mc[w] = mc; s_t[w] = ties; }
     __syncthreads();

@@ -4,6 +4,7 @@
 // :1545-1624 in the reference).  Shares the ring walk and its exactness argument with search.cuh.
 #pragma once
 #include "search.cuh"
+#include "nn1.cuh"
 
 namespace pcu {
 
@@ -14,18 +15,11 @@ namespace pcu {
 // distances are reported in tie_list and re-answered by the kd-tree replay.
 // grid (ceil(max_n * 32 / kThreads), nsweeps).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) knn_warp_kernel(const Cloud<T>* __restrict__ clouds,
-                                                            const Sweep<T>* __restrict__ sweeps) {
+__device__ __forceinline__ void knn_warp_one(const Sweep<T>& sw, const Cloud<T>& qc, const Cloud<T>& dc,
+                                             const GridHeader<T>& g, long long t, int lane) {
     using R = Real<T>;
     using index_t = typename R::index_t;
-    const Sweep<T> sw = sweeps[blockIdx.y];
-    const Cloud<T> qc = clouds[sw.qcloud];
-    const Cloud<T> dc = clouds[sw.dcloud];
-    const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= qc.n) return;   // warp-uniform
-    const int lane = threadIdx.x & 31;
     const int k = sw.k;
-    const GridHeader<T> g = *dc.grid;
     const Pt<T> q = load_pt<T>(qc.sorted + t);
 
     T dl = R::inf();
@@ -91,6 +85,30 @@ __global__ void __launch_bounds__(kThreads) knn_warp_kernel(const Cloud<T>* __re
     if (any && lane == 0) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
 }
 
+// kFar == false: warp w answers sorted query w.            grid (ceil(max_n * 32 / kThreads), nsweeps)
+// kFar == true : warp-stride loop over the far list left by knn_thread_kernel.   grid (far_blocks, nsweeps)
+template <typename T, bool kFar>
+__global__ void __launch_bounds__(kThreads) knn_warp_kernel(const Cloud<T>* __restrict__ clouds,
+                                                            const Sweep<T>* __restrict__ sweeps) {
+    const Sweep<T> sw = sweeps[blockIdx.y];
+    const Cloud<T> qc = clouds[sw.qcloud];
+    const Cloud<T> dc = clouds[sw.dcloud];
+    const int lane = threadIdx.x & 31;
+    if (kFar) {
+        const unsigned n_far = sw.counters[0];
+        if (n_far == 0) return;
+        const GridHeader<T> g = *dc.grid;
+        const unsigned warps_total = gridDim.x * (kThreads / 32);
+        for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total)
+            knn_warp_one<T>(sw, qc, dc, g, (long long)sw.far_list[f], lane);
+    } else {
+        const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (t >= qc.n) return;   // warp-uniform
+        const GridHeader<T> g = *dc.grid;
+        knn_warp_one<T>(sw, qc, dc, g, t, lane);
+    }
+}
+
 // k > 32: one thread per query, the (distance, index)-sorted list lives in the caller's output rows
 // (squared distances while searching).  Generic and slow; large k is not a hot configuration.
 // grid (ceil(max_n / kThreads), nsweeps).
@@ -136,6 +154,150 @@ __global__ void __launch_bounds__(kThreads) knn_big_kernel(const Cloud<T>* __res
     for (int s = 0; s + 1 < have; ++s) tie = tie || (ld[s] == ld[s + 1]);
     if (!sw.squared) for (int s = 0; s < have; ++s) ld[s] = R::root(ld[s]);
     for (int s = have; s < k; ++s) { ld[s] = (T)-1; li[s] = -1; }
+    if (tie) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2 <= k <= 32, main pass: ONE THREAD per query with its (distance, index)-sorted list held in
+// registers.  An insertion is a fully unrolled compare/select chain (~6 instructions per slot), and
+// because 32 queries share every issued instruction, the cost per query is a small fraction of the
+// warp-per-query scheme above, which remains the slow pass for the queries this kernel cannot settle
+// within the 3 x 3 x 3 neighbourhood.
+//
+// Slots: K = capacity (power of two >= k).  The K - k surplus slots are filled with a key that is
+// smaller than every real key, so they sit at the front of the ascending list for ever and the k-th
+// best is always slot K - 1 -- a compile-time register, no dynamic indexing.
+template <typename T> struct ListKey;
+template <> struct ListKey<float> {
+    unsigned long long v;   // (distance bits << 32) | index : distances are >= +0, bits order like values
+    static __device__ __forceinline__ ListKey make(float d, int i) {
+        ListKey k; k.v = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i; return k;
+    }
+    static __device__ __forceinline__ ListKey dead() { ListKey k; k.v = 0ull; return k; }
+    static __device__ __forceinline__ ListKey empty() { ListKey k; k.v = ~0ull; return k; }
+    __device__ __forceinline__ bool less(const ListKey& o) const { return v < o.v; }
+    __device__ __forceinline__ float dist() const { return __uint_as_float((unsigned)(v >> 32)); }
+    __device__ __forceinline__ long long index() const { return (long long)(int)(unsigned)v; }
+    __device__ __forceinline__ bool is_empty() const { return v == ~0ull; }
+};
+template <> struct ListKey<double> {
+    double d; long long i;
+    static __device__ __forceinline__ ListKey make(double d, long long i) { ListKey k; k.d = d; k.i = i; return k; }
+    static __device__ __forceinline__ ListKey dead() { ListKey k; k.d = -1.0; k.i = -1; return k; }
+    static __device__ __forceinline__ ListKey empty() {
+        ListKey k; k.d = __longlong_as_double(0x7ff0000000000000LL); k.i = 0x7fffffffffffffffLL; return k;
+    }
+    __device__ __forceinline__ bool less(const ListKey& o) const { return d < o.d || (d == o.d && i < o.i); }
+    __device__ __forceinline__ double dist() const { return d; }
+    __device__ __forceinline__ long long index() const { return i; }
+    __device__ __forceinline__ bool is_empty() const { return i == 0x7fffffffffffffffLL; }
+};
+
+template <typename T, int K>
+__device__ __forceinline__ void list_insert(ListKey<T> (&a)[K], const ListKey<T>& key) {
+    bool lt[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) lt[s] = key.less(a[s]);
+#pragma unroll
+    for (int s = K - 1; s >= 1; --s) a[s] = lt[s - 1] ? a[s - 1] : (lt[s] ? key : a[s]);
+    a[0] = lt[0] ? key : a[0];
+}
+
+// grid (ceil(max_n / kThreads), nsweeps)
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads) knn_thread_kernel(const Cloud<T>* __restrict__ clouds,
+                                                              const Sweep<T>* __restrict__ sweeps) {
+    using R = Real<T>;
+    const Sweep<T> sw = sweeps[blockIdx.y];
+    const Cloud<T> qc = clouds[sw.qcloud];
+    const Cloud<T> dc = clouds[sw.dcloud];
+    if ((long long)blockIdx.x * blockDim.x >= qc.n) return;
+    __shared__ GridHeader<T> g;
+    __shared__ RowTable<T> rows;
+    if (threadIdx.x == 0) g = *dc.grid;
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + tid;
+    if (t >= qc.n) return;
+    const int k = sw.k;
+    const Pt<T> q = load_pt<T>(qc.sorted + t);
+    const int st = g.stride;
+    const T* lo_x = dc.wall_lo;           const T* hi_x = dc.wall_hi;
+    const T* lo_y = dc.wall_lo + st;      const T* hi_y = dc.wall_hi + st;
+    const T* lo_z = dc.wall_lo + 2 * st;  const T* hi_z = dc.wall_hi + 2 * st;
+    const int cx = cell_of<T>(q.x, g.origin[0], g.inv_h, g.dim[0]);
+    const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
+    const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
+    const int xa = max(cx - 1, 0), xb = min(cx + 1, g.dim[0] - 1);
+    const T gy[3] = {(T)0, sq_gap<T>(q.y, __ldg(lo_y + cy)), sq_gap<T>(q.y, __ldg(hi_y + cy + 1))};
+    const T gz[3] = {(T)0, sq_gap<T>(q.z, __ldg(lo_z + cz)), sq_gap<T>(q.z, __ldg(hi_z + cz + 1))};
+    const int order_y[9] = {0, 1, 2, 0, 0, 1, 2, 1, 2};
+    const int order_z[9] = {0, 0, 0, 1, 2, 1, 1, 2, 2};
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+        const int oy = order_y[s], oz = order_z[s];
+        const int y = cy + (oy == 1 ? -1 : (oy == 2 ? 1 : 0));
+        const int z = cz + (oz == 1 ? -1 : (oz == 2 ? 1 : 0));
+        unsigned a = 0, b = 0;
+        if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+            const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+            a = __ldg(dc.cell_start + base + xa);
+            b = __ldg(dc.cell_start + base + xb + 1);
+        }
+        rows.begin[s][tid] = a;
+        rows.end[s][tid] = b;
+        rows.bound[s][tid] = R::add(gy[oy], gz[oz]);
+    }
+    ListKey<T> list[K];
+#pragma unroll
+    for (int s = 0; s < K; ++s) list[s] = s < K - k ? ListKey<T>::dead() : ListKey<T>::empty();
+    T rej = R::inf();   // smallest distance turned away or pushed out: equal to the k-th => order-dependent answer
+    int r = 0;
+    unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
+    for (;;) {
+        if (j < e) {
+            const Pt<T> p = load_pt<T>(dc.sorted + j);
+            ++j;
+            const T d = dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z);
+            const ListKey<T> key = ListKey<T>::make(d, p.i);
+            if (key.less(list[K - 1])) {
+                if (!list[K - 1].is_empty()) rej = R::vmin(rej, list[K - 1].dist());
+                list_insert<T, K>(list, key);
+            } else {
+                rej = R::vmin(rej, d);
+            }
+        } else {
+            if (++r >= 9) break;
+            // skip a row only if all of it is strictly farther than the current k-th distance
+            if (!(rows.bound[r][tid] > list[K - 1].dist())) { j = rows.begin[r][tid]; e = rows.end[r][tid]; }
+        }
+    }
+    const int ya = max(cy - 1, 0), yb = min(cy + 1, g.dim[1] - 1);
+    const int za = max(cz - 1, 0), zb = min(cz + 1, g.dim[2] - 1);
+    T lb = sq_gap<T>(q.x, __ldg(lo_x + xa));
+    lb = R::vmin(lb, sq_gap<T>(q.x, __ldg(hi_x + xb + 1)));
+    lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(lo_y + ya)));
+    lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(hi_y + yb + 1)));
+    lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(lo_z + za)));
+    lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(hi_z + zb + 1)));
+    const T worst = list[K - 1].dist();
+    const bool full = !list[K - 1].is_empty();
+    if (!(full && worst < lb)) {   // not provably complete within one ring: hand over to the warp pass
+        sw.far_list[atomicAdd(sw.counters, 1u)] = (unsigned)t;
+        return;
+    }
+    const long long row = (long long)q.i;
+    bool tie = rej == worst;
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+        if (s >= K - k) {
+            const int c = s - (K - k);
+            const T d = list[s].dist();
+            sw.out_idx[row * k + c] = list[s].index();
+            sw.out_dist[row * k + c] = sw.squared ? d : R::root(d);
+            if (s + 1 < K) tie = tie || (d == list[s + 1].dist());
+        }
+    }
     if (tie) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
 }
 
