@@ -15,6 +15,7 @@ namespace pcu {
 
 constexpr int kMaxGridDim = 2048;   // cells per axis, upper bound
 constexpr int kThreads = 256;       // default CTA size of the streaming kernels
+constexpr int kMaxLevels = 12;      // 2^11 = kMaxGridDim, plus one
 
 template <typename T> struct Real;
 
@@ -127,6 +128,14 @@ struct GridHeader {
     int pad;
 };
 
+// Shape of the occupancy pyramid over a grid (kept apart from GridHeader, which every block of the
+// streaming kernels copies to shared memory).
+struct PyramidShape {
+    int levels;                       // level l (1..levels) halves the resolution l times; the top is 1x1x1
+    int lvl_dim[kMaxLevels + 1][3];   // [0] = the grid's own dim
+    int lvl_off[kMaxLevels + 1];      // offset of level l inside Cloud::pyramid (level 0 is cell_start itself)
+};
+
 template <typename T>
 __device__ __forceinline__ int cell_of(T p, T origin, T inv_h, int dim) {
     using R = Real<T>;
@@ -148,6 +157,8 @@ struct Cloud {
     T* wall_hi;             // 3 * stride
     T* bbox_partial;        // bbox_blocks * 6
     unsigned* scan_partial; // per-scan-block totals
+    unsigned* pyramid;      // cell_cap + 64: point counts of the coarser levels (built only when needed)
+    PyramidShape* shape;    // written by grid_setup
     int cell_cap;           // upper bound on ncells (host-known)
     int stride;             // wall table stride (host-known)
     int bbox_blocks;        // partial bounding boxes of this cloud (host-known, <= kMaxBBoxBlocks)

@@ -173,6 +173,19 @@ __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const Cloud<T>* __
         hdr.inv_h = (T)(1.0 / h);
         hdr.stride = c.stride;
         hdr.pad = 0;
+        // shape of the occupancy pyramid (filled by pyramid_build_kernel only if some query needs it)
+        PyramidShape ps;
+        int lv = 0, off = 0;
+        ps.lvl_dim[0][0] = hdr.dim[0]; ps.lvl_dim[0][1] = hdr.dim[1]; ps.lvl_dim[0][2] = hdr.dim[2];
+        ps.lvl_off[0] = 0;
+        while ((ps.lvl_dim[lv][0] > 1 || ps.lvl_dim[lv][1] > 1 || ps.lvl_dim[lv][2] > 1) && lv < kMaxLevels) {
+            for (int a = 0; a < 3; ++a) ps.lvl_dim[lv + 1][a] = (ps.lvl_dim[lv][a] + 1) / 2;
+            ps.lvl_off[lv + 1] = off;
+            off += ps.lvl_dim[lv + 1][0] * ps.lvl_dim[lv + 1][1] * ps.lvl_dim[lv + 1][2];
+            ++lv;
+        }
+        ps.levels = lv;
+        *c.shape = ps;
         *c.grid = hdr;
     }
     __syncthreads();

@@ -124,6 +124,8 @@ __device__ __forceinline__ void merge_best(Best1<T>& a, const Best1<T>& b) {
     }
 }
 
+constexpr int kMaxRing = 2;   // rings the far pass walks before handing a query to the pyramid descent
+
 // Slow pass for the queries the one-ring pass could not settle (empty neighbourhoods, queries
 // outside the dataset's box): one WARP per such query; each ring of cells is split over the lanes
 // (one (y, z) row per lane and step), the lanes' results are merged, and the ring loop stops as soon
@@ -153,7 +155,8 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const Cloud<T>* __res
             const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
             const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
             Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
-            for (int r = 0;; ++r) {
+            bool settled = false;
+            for (int r = 0; r <= kMaxRing; ++r) {
                 const int xa = max(cx - r, 0), xb = min(cx + r, g.dim[0] - 1);
                 const int ya = max(cy - r, 0), yb = min(cy + r, g.dim[1] - 1);
                 const int za = max(cz - r, 0), zb = min(cz + r, g.dim[2] - 1);
@@ -191,10 +194,15 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const Cloud<T>* __res
                 lb = R::vmin(lb, sq_gap<T>(q.y, hi_y[yb + 1]));
                 lb = R::vmin(lb, sq_gap<T>(q.z, lo_z[za]));
                 lb = R::vmin(lb, sq_gap<T>(q.z, hi_z[zb + 1]));
-                if (best.d < lb) break;
-                if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) break;
+                if (best.d < lb) { settled = true; break; }
+                if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) {
+                    settled = true;   // the whole grid has been examined
+                    break;
+                }
             }
-            finish_query1<T, kOut, kStats>(sw, lane == 0, best, (long long)q.i, sum, sumsq, mc, ties);
+            // rings grow cubically with the distance to the data: beyond kMaxRing the occupancy pyramid takes over
+            if (!settled && lane == 0) sw.vfar_list[atomicAdd(sw.counters + 2, 1u)] = sw.far_list[f];
+            finish_query1<T, kOut, kStats>(sw, settled && lane == 0, best, (long long)q.i, sum, sumsq, mc, ties);
         }
     }
     if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + blockIdx.x);
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) stats_finalize_kernel(const Cloud<T>
     const Sweep<T> sw = sweeps[blockIdx.y];
     const long long n = clouds[sw.qcloud].n;
     const int main_used = (int)((n + kThreads - 1) / kThreads);
-    const int total = main_used + sw.far_blocks;
+    const int total = main_used + 2 * sw.far_blocks;   // main | far pass | pyramid pass
     double sum = 0.0, sumsq = 0.0;
     unsigned ties = 0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;

@@ -21,6 +21,7 @@
 #include "search.cuh"
 #include "nn1.cuh"
 #include "topk.cuh"
+#include "pyramid.cuh"
 #include "kdreplay.cuh"
 
 using namespace pcu;
@@ -63,8 +64,8 @@ int fail(int status, const char* fmt, ...) {
 
 // Per-field byte strides between consecutive pairs of a batch (side 0 = first cloud of each pair,
 // side 1 = second cloud; direction 0 = first -> second, direction 1 = second -> first).
-struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_partial; };
-struct SweepStrides { size_t out_dist, out_idx, partial, far_list, counters, tie_list; };
+struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_partial, pyramid, shape; };
+struct SweepStrides { size_t out_dist, out_idx, partial, far_list, vfar_list, counters, tie_list; };
 
 template <typename U>
 __device__ __forceinline__ U* advance(U* p, size_t bytes) {
@@ -101,6 +102,8 @@ __global__ void descriptors_kernel(const __grid_constant__ DescriptorArgs<T> a, 
         c.wall_hi = advance(c.wall_hi, p * st.wall_hi);
         c.bbox_partial = advance(c.bbox_partial, p * st.bbox_partial);
         c.scan_partial = advance(c.scan_partial, p * st.scan_partial);
+        c.pyramid = advance(c.pyramid, p * st.pyramid);
+        c.shape = advance(c.shape, p * st.shape);
         clouds[2 * p + s] = c;
     }
     for (int d = 0; d < a.nsweeps; ++d) {
@@ -112,6 +115,7 @@ __global__ void descriptors_kernel(const __grid_constant__ DescriptorArgs<T> a, 
         w.out_idx = advance(w.out_idx, p * st.out_idx);
         w.partial = advance(w.partial, p * st.partial);
         w.far_list = advance(w.far_list, p * st.far_list);
+        w.vfar_list = advance(w.vfar_list, p * st.vfar_list);
         w.counters = advance(w.counters, p * st.counters);
         w.tie_list = advance(w.tie_list, p * st.tie_list);
         w.stats = a.stats ? a.stats + p * a.nsweeps + d : nullptr;
@@ -287,6 +291,8 @@ struct Plan {
             cl.bbox_partial = take_strided<T>(cv, (size_t)cl.bbox_blocks * 6, B, st.bbox_partial);
             cl.scan_partial = take_strided<unsigned>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
                                                      st.scan_partial);
+            cl.pyramid = take_strided<unsigned>(cv, (size_t)cl.cell_cap + 64, B, st.pyramid);
+            cl.shape = take_strided<PyramidShape>(cv, 1, B, st.shape);
         }
         for (int d = 0; d < sp.nsweeps; ++d) {
             Sweep<T>& sw = args.sweep[d];
@@ -297,13 +303,14 @@ struct Plan {
             sw.main_blocks = (int)((nq + kThreads - 1) / kThreads);
             sw.far_blocks = far_blocks;
             sw.far_list = take_strided<unsigned>(cv, (size_t)nq, B, st.far_list);
+            sw.vfar_list = take_strided<unsigned>(cv, (size_t)nq, B, st.vfar_list);
             if (sp.want_out) {
                 sw.tie_list = take_strided<long long>(cv, (size_t)nq, B, st.tie_list);
                 sw.out_dist = sp.out_dist;   // batch == 1 on this path
                 sw.out_idx = sp.out_idx;
             }
             if (sp.want_stats)
-                sw.partial = take_strided<SweepPartial<T>>(cv, (size_t)sw.main_blocks + far_blocks, B, st.partial);
+                sw.partial = take_strided<SweepPartial<T>>(cv, (size_t)sw.main_blocks + 2 * far_blocks, B, st.partial);
         }
         if (sp.replay_points > 0) replay.carve(cv, sp.replay_points);
         total = cv.off;
@@ -386,6 +393,8 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         PCU_LAUNCH((nn1_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
         PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, 1), kPyramidThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((nn1_vfar_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
     } else if (k <= 32) {
         // thread-per-query lists in registers (capacity = next power of two), warp pass for the rest
@@ -439,6 +448,8 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     mark(ws, 6, stream);
     PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, ns), kPyramidThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH((nn1_vfar_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     mark(ws, 7, stream);
     PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     if (both && out_value) {
@@ -499,6 +510,8 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
         PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, plan.nsweeps_total), kPyramidThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((nn1_vfar_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
         PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,

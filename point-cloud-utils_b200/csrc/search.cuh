@@ -39,7 +39,8 @@ struct Sweep {
     long long* out_idx;          // (n, k) or null
     SweepPartial<T>* partial;    // main_blocks + far blocks slots, or null
     unsigned* far_list;          // sorted-order positions of queries the one-ring pass could not settle
-    unsigned* counters;          // [0] far queries, [1] tied queries
+    unsigned* vfar_list;         // ... and of those the ring walk gave up on (answered by the pyramid descent)
+    unsigned* counters;          // [0] far queries, [1] tied queries, [2] very far queries
     long long* tie_list;         // caller-order rows whose answer depends on tie order
     pcu_b200_nn_stats* stats;    // or null
 };

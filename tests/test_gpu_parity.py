@@ -180,3 +180,27 @@ def test_kd_replica_equals_reference_tree(pcu, oracle, dtype):
             assert np.array_equal(np.asarray(got["order"], dtype=np.int64), ref["order"]), (name, leaf, "order")
             n_ref = _walk_equal(got, ref, 0, 0)
             assert n_ref == len(ref["feat"]) == got["n_nodes"], (name, leaf)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_far_apart_and_clustered_clouds(pcu, oracle, dtype):
+    """Queries far from every dataset point (disjoint boxes, tight clusters in a large void): the ring
+    walk hands over to the occupancy-pyramid descent; results must not change."""
+    rng = np.random.default_rng(31)
+    x = rng.random((20000, 3)).astype(dtype)
+    y = (rng.random((30000, 3)) * np.array([1.0, 2.0, 0.5]) + np.array([40.0, -25.0, 3.0])).astype(dtype)
+    blobs = np.concatenate([rng.normal(c, 0.002, (5000, 3)) for c in ((0.1, 0.1, 0.1), (0.9, 0.2, 0.7), (0.5, 0.95, 0.3))])
+    blobs = blobs.astype(dtype)
+    for q, d in ((x, y), (y, x), (x, blobs), (blobs, x)):
+        got_d, got_i = pcu.k_nearest_neighbors(q, d, 1)
+        ref_d, ref_i = oracle.k_nearest_neighbors(q, d, 1)
+        assert np.array_equal(got_i, ref_i) and np.array_equal(got_d, ref_d)
+    for a, b in ((x, y), (x, blobs)):
+        ref = float(oracle.chamfer_distance(a, b))
+        assert abs(float(pcu.chamfer_distance(a, b)) - ref) <= REL * ref
+        assert pcu.hausdorff_distance(a, b, return_index=True) == oracle.hausdorff_distance(a, b, return_index=True)
+    st = pcu._pcu_internal._chamfer_stats(x, y)
+    assert st[1]["n_far"] == len(x) and st[2]["n_far"] == len(y)      # every query took the slow path ...
+    got = pcu.k_nearest_neighbors(x[:2000], blobs, 5)                 # ... and k > 1 still agrees
+    ref = oracle.k_nearest_neighbors(x[:2000], blobs, 5)
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
