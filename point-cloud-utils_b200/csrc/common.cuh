@@ -156,7 +156,8 @@ struct Cloud {
     T* wall_lo;             // 3 * stride
     T* wall_hi;             // 3 * stride
     T* bbox_partial;        // bbox_blocks * 6
-    unsigned* scan_partial; // per-scan-block totals
+    unsigned long long* scan_state;  // per scan tile: status | value (decoupled look-back), zeroed per call
+    unsigned* scan_ticket;           // tile ticket, zeroed per call
     unsigned* pyramid;      // cell_cap + 64: point counts of the coarser levels (built only when needed)
     PyramidShape* shape;    // written by grid_setup
     int cell_cap;           // upper bound on ncells (host-known)

@@ -12,6 +12,8 @@
 
 namespace pcu {
 
+constexpr int kBinPerThread = 1;   // points per thread in the histogram / scatter kernels
+
 // ---------------------------------------------------------------------------------------------
 // 1. partial bounding boxes: grid (max bbox_blocks, nclouds)
 template <typename T>
@@ -230,15 +232,29 @@ __global__ void __launch_bounds__(kThreads) cell_count_kernel(const Cloud<T>* __
     __shared__ GridHeader<T> g;
     if (threadIdx.x == 0) g = *c.grid;
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
-    const T x = __ldg(c.raw + 3 * i), y = __ldg(c.raw + 3 * i + 1), z = __ldg(c.raw + 3 * i + 2);
-    const int lin = linear_cell<T>(g, x, y, z);
-    c.rank[i] = atomicAdd(c.cell_start + lin, 1u);
+    // kBinPerThread points per thread, blockDim apart: the loads and the atomics of one thread are
+    // independent, so several of each are in flight
+    const long long base = (long long)blockIdx.x * (blockDim.x * kBinPerThread) + threadIdx.x;
+    if (base >= c.n) return;
+    int lin[kBinPerThread];
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) {
+        const long long i = base + (long long)k * blockDim.x;
+        lin[k] = -1;
+        if (i < c.n) {
+            const T x = __ldg(c.raw + 3 * i), y = __ldg(c.raw + 3 * i + 1), z = __ldg(c.raw + 3 * i + 2);
+            lin[k] = linear_cell<T>(g, x, y, z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) {
+        const long long i = base + (long long)k * blockDim.x;
+        if (lin[k] >= 0) c.rank[i] = atomicAdd(c.cell_start + lin[k], 1u);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4. exclusive scan of cell_start[0 .. cell_cap] (three phases, in place)
+// 4. exclusive scan of cell_start[0 .. cell_cap], in place
 __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* total) {
     // kScanThreads threads; returns the exclusive prefix of v, *total = block sum
     __shared__ unsigned warp_sum[kScanThreads / 32];
@@ -267,46 +283,21 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
     return before + inc - v;
 }
 
+// Single-pass scan with decoupled look-back: every CTA draws a tile ticket, scans its tile, publishes
+// the tile total, and resolves its carry by walking back over the published states of the tiles
+// before it.  state word = status (bits 63:62; 1 = tile total, 2 = inclusive prefix) | value (low 32).
+// Ticket and states must be zero on entry (they live in the call's zeroed region).
+// grid (tiles, nclouds)
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const Cloud<T>* __restrict__ clouds) {
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const Cloud<T>* __restrict__ clouds) {
     const Cloud<T> c = clouds[blockIdx.y];
     const long long count = (long long)c.cell_cap + 1;
-    const long long base = (long long)blockIdx.x * kScanTile;
+    __shared__ unsigned s_tile, s_carry;
+    if (threadIdx.x == 0) s_tile = atomicAdd(c.scan_ticket, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const long long base = (long long)tile * kScanTile;
     if (base >= count) return;
-    unsigned s = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        const long long i = base + (long long)k * kScanThreads + threadIdx.x;
-        if (i < count) s += c.cell_start[i];
-    }
-    unsigned total;
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) c.scan_partial[blockIdx.x] = total;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(const Cloud<T>* __restrict__ clouds) {
-    const Cloud<T> c = clouds[blockIdx.y];
-    const long long count = (long long)c.cell_cap + 1;
-    const int nb = (int)((count + kScanTile - 1) / kScanTile);
-    unsigned carry = 0;
-    for (int base = 0; base < nb; base += kScanThreads) {
-        const int i = base + threadIdx.x;
-        const unsigned v = i < nb ? c.scan_partial[i] : 0u;
-        unsigned total;
-        const unsigned ex = block_exclusive_scan(v, &total);
-        if (i < nb) c.scan_partial[i] = carry + ex;
-        carry += total;
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const Cloud<T>* __restrict__ clouds) {
-    const Cloud<T> c = clouds[blockIdx.y];
-    const long long count = (long long)c.cell_cap + 1;
-    const long long base = (long long)blockIdx.x * kScanTile;
-    if (base >= count) return;
-    // each thread owns kScanItems consecutive entries
     unsigned v[kScanItems];
     unsigned s = 0;
     const long long first = base + (long long)threadIdx.x * kScanItems;
@@ -316,7 +307,30 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const Cloud<T>
         s += v[k];
     }
     unsigned total;
-    unsigned run = block_exclusive_scan(s, &total) + c.scan_partial[blockIdx.x];
+    const unsigned ex = block_exclusive_scan(s, &total);
+    if (threadIdx.x < 32) {
+        // warp-wide look-back: lane l inspects tile (tile - 1 - l), 32 predecessors per step
+        volatile unsigned long long* state = c.scan_state;
+        const int lane = threadIdx.x;
+        if (lane == 0) state[tile] = ((tile == 0 ? 2ull : 1ull) << 62) | total;
+        unsigned carry = 0;
+        if (tile > 0) {
+            for (long long p = (long long)tile - 1;; p -= 32) {
+                const long long mine = p - lane;
+                unsigned long long w = 2ull << 62;            // lanes before tile 0 act as a zero prefix
+                if (mine >= 0) do { w = state[mine]; } while ((w >> 62) == 0);
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+                const int stop = has_prefix ? __ffs(has_prefix) - 1 : 31;   // nearest predecessor holding a prefix
+                const unsigned part = lane <= stop ? (unsigned)w : 0u;
+                carry += __reduce_add_sync(0xffffffffu, part);
+                if (has_prefix) break;
+            }
+            if (lane == 0) state[tile] = (2ull << 62) | (unsigned long long)(carry + total);
+        }
+        if (lane == 0) s_carry = carry;
+    }
+    __syncthreads();
+    unsigned run = ex + s_carry;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         if ((first + k) < count) c.cell_start[first + k] = run;
@@ -332,12 +346,23 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const Cloud<T>* __res
     __shared__ GridHeader<T> g;
     if (threadIdx.x == 0) g = *c.grid;
     __syncthreads();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
-    const T x = __ldg(c.raw + 3 * i), y = __ldg(c.raw + 3 * i + 1), z = __ldg(c.raw + 3 * i + 2);
-    const int lin = linear_cell<T>(g, x, y, z);
-    const unsigned pos = c.cell_start[lin] + c.rank[i];
-    store_pt<T>(c.sorted + pos, x, y, z, i);
+    const long long base = (long long)blockIdx.x * (blockDim.x * kBinPerThread) + threadIdx.x;
+    if (base >= c.n) return;
+    T x[kBinPerThread], y[kBinPerThread], z[kBinPerThread];
+    unsigned pos[kBinPerThread];
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) {
+        const long long i = base + (long long)k * blockDim.x;
+        if (i < c.n) {
+            x[k] = __ldg(c.raw + 3 * i); y[k] = __ldg(c.raw + 3 * i + 1); z[k] = __ldg(c.raw + 3 * i + 2);
+            pos[k] = c.cell_start[linear_cell<T>(g, x[k], y[k], z[k])] + c.rank[i];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kBinPerThread; ++k) {
+        const long long i = base + (long long)k * blockDim.x;
+        if (i < c.n) store_pt<T>(c.sorted + pos[k], x[k], y[k], z[k], i);
+    }
 }
 
 }  // namespace pcu

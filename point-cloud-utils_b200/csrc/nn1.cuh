@@ -10,6 +10,8 @@
 
 namespace pcu {
 
+constexpr int kMaxRing = 2;   // rings the in-kernel slow path walks before a query goes to the pyramid descent
+
 // Per-thread table of the 9 rows (fixed y, z; three x-adjacent cells = one contiguous run of the
 // sorted dataset) of a query's 3 x 3 x 3 neighbourhood, nearest rows first.  Indexed [row][thread]
 // so that lanes hit distinct banks whatever row each lane is currently on.
@@ -20,11 +22,80 @@ struct RowTable {
     T bound[9][kThreads];
 };
 
+// Merges the running best of two lanes (after each lane has scanned disjoint cells).
+template <typename T>
+__device__ __forceinline__ void merge_best(Best1<T>& a, const Best1<T>& b) {
+    if (b.d < a.d) a = b;
+    else if (b.d == a.d) {
+        a.tie = a.tie || b.tie || (b.i != a.i);
+        a.i = b.i < a.i ? b.i : a.i;
+    }
+}
+
+// Warp-cooperative ring walk for ONE query: each ring of cells is split over the lanes (one (y, z)
+// row per lane and step), the lanes' results are merged, and the walk stops as soon as the wall bound
+// closes (returns true) or kMaxRing rings have been examined (returns false unless the whole grid was
+// covered).  All lanes return the same best.
+template <typename T>
+__device__ __forceinline__ bool warp_ring_search(const GridHeader<T>& g, const Cloud<T>& dc, const Pt<T>& q, int lane,
+                                                 Best1<T>& best) {
+    using R = Real<T>;
+    const int st = g.stride;
+    const T* lo_x = dc.wall_lo;           const T* hi_x = dc.wall_hi;
+    const T* lo_y = dc.wall_lo + st;      const T* hi_y = dc.wall_hi + st;
+    const T* lo_z = dc.wall_lo + 2 * st;  const T* hi_z = dc.wall_hi + 2 * st;
+    const int cx = cell_of<T>(q.x, g.origin[0], g.inv_h, g.dim[0]);
+    const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
+    const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
+    best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
+    for (int r = 0; r <= kMaxRing; ++r) {
+        const int xa = max(cx - r, 0), xb = min(cx + r, g.dim[0] - 1);
+        const int ya = max(cy - r, 0), yb = min(cy + r, g.dim[1] - 1);
+        const int za = max(cz - r, 0), zb = min(cz + r, g.dim[2] - 1);
+        const int ny = yb - ya + 1, nrows = ny * (zb - za + 1);
+        for (int idx = lane; idx < nrows; idx += 32) {
+            const int z = za + idx / ny, y = ya + idx % ny;
+            const T bz = z < cz ? sq_gap<T>(q.z, lo_z[z + 1]) : (z > cz ? sq_gap<T>(q.z, hi_z[z]) : (T)0);
+            const T by = y < cy ? sq_gap<T>(q.y, lo_y[y + 1]) : (y > cy ? sq_gap<T>(q.y, hi_y[y]) : (T)0);
+            if (R::add(by, bz) > best.d) continue;
+            const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+            const bool shell_row = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
+            if (shell_row || r == 0) {
+                scan_run1<T>(dc.sorted, dc.cell_start[base + xa], dc.cell_start[base + xb + 1], q.x, q.y, q.z, best);
+            } else {
+                if (cx - r >= 0 && !(R::add(R::add(sq_gap<T>(q.x, lo_x[cx - r + 1]), by), bz) > best.d))
+                    scan_run1<T>(dc.sorted, dc.cell_start[base + cx - r], dc.cell_start[base + cx - r + 1], q.x, q.y, q.z, best);
+                if (cx + r <= g.dim[0] - 1 && !(R::add(R::add(sq_gap<T>(q.x, hi_x[cx + r]), by), bz) > best.d))
+                    scan_run1<T>(dc.sorted, dc.cell_start[base + cx + r], dc.cell_start[base + cx + r + 1], q.x, q.y, q.z, best);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Best1<T> other;
+            other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+            other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+            other.tie = __shfl_xor_sync(0xffffffffu, (int)best.tie, o) != 0;
+            merge_best<T>(best, other);
+        }
+        T lb = sq_gap<T>(q.x, lo_x[xa]);
+        lb = R::vmin(lb, sq_gap<T>(q.x, hi_x[xb + 1]));
+        lb = R::vmin(lb, sq_gap<T>(q.y, lo_y[ya]));
+        lb = R::vmin(lb, sq_gap<T>(q.y, hi_y[yb + 1]));
+        lb = R::vmin(lb, sq_gap<T>(q.z, lo_z[za]));
+        lb = R::vmin(lb, sq_gap<T>(q.z, hi_z[zb + 1]));
+        if (best.d < lb) return true;
+        if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) return true;
+    }
+    return false;
+}
+
 // Main pass: one thread per (cell-sorted) query.
 //   phase A (uniform): look up the 9 runs and the wall bound of each row;
-//   phase B (flattened): ONE loop in which a lane either evaluates its next candidate or steps to its
-//     next row that is not pruned by its bound.  Lanes therefore stay busy until their own total
-//     work is done, instead of idling in nine separate loops of different lengths.
+//   phase B (flattened): ONE loop in which a lane either evaluates its next two candidates or steps to
+//     its next row that is not pruned by its bound;
+//   queries the 3 x 3 x 3 neighbourhood cannot settle (empty surroundings) go to the far list
+//   (nn1_far_kernel below; doing them here, one warp each, cost more in registers and idle warps
+//   than the extra launch -- measured).
 // grid (ceil(max_n / kThreads), nsweeps).
 template <typename T, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_kernel(const Cloud<T>* __restrict__ clouds,
@@ -114,26 +185,16 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const Cloud<T>* __restric
     if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + blockIdx.x);
 }
 
-// Merges the running best of two lanes (after each lane has scanned disjoint cells).
-template <typename T>
-__device__ __forceinline__ void merge_best(Best1<T>& a, const Best1<T>& b) {
-    if (b.d < a.d) a = b;
-    else if (b.d == a.d) {
-        a.tie = a.tie || b.tie || (b.i != a.i);
-        a.i = b.i < a.i ? b.i : a.i;
-    }
-}
+template <typename T> __device__ void build_pyramid(const Cloud<T>& dc);   // pyramid.cuh
 
-constexpr int kMaxRing = 2;   // rings the far pass walks before handing a query to the pyramid descent
-
-// Slow pass for the queries the one-ring pass could not settle (empty neighbourhoods, queries
-// outside the dataset's box): one WARP per such query; each ring of cells is split over the lanes
-// (one (y, z) row per lane and step), the lanes' results are merged, and the ring loop stops as soon
-// as the wall bound closes.  grid (sw.far_blocks, nsweeps), warp-stride loop over the far list.
+// Slow pass for the queries the 3 x 3 x 3 neighbourhood could not settle (empty surroundings): one
+// WARP per query (warp_ring_search); what even kMaxRing rings cannot settle goes to the very-far list.
+// The CTA that finishes last builds the dataset's occupancy pyramid if that list is not empty, so the
+// pyramid pass that follows needs no launch of its own for it.
+// grid (sw.far_blocks, nsweeps), warp-stride loop over the far list.
 template <typename T, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const Cloud<T>* __restrict__ clouds,
                                                            const Sweep<T>* __restrict__ sweeps) {
-    using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const unsigned n_far = sw.counters[0];
     const Cloud<T> qc = clouds[sw.qcloud];
@@ -145,77 +206,33 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const Cloud<T>* __res
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
     if (n_far > 0) {
         const GridHeader<T> g = *dc.grid;
-        const int st = g.stride;
-        const T* lo_x = dc.wall_lo;           const T* hi_x = dc.wall_hi;
-        const T* lo_y = dc.wall_lo + st;      const T* hi_y = dc.wall_hi + st;
-        const T* lo_z = dc.wall_lo + 2 * st;  const T* hi_z = dc.wall_hi + 2 * st;
         for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total) {
-            const Pt<T> q = load_pt<T>(qc.sorted + sw.far_list[f]);
-            const int cx = cell_of<T>(q.x, g.origin[0], g.inv_h, g.dim[0]);
-            const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
-            const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
-            Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
-            bool settled = false;
-            for (int r = 0; r <= kMaxRing; ++r) {
-                const int xa = max(cx - r, 0), xb = min(cx + r, g.dim[0] - 1);
-                const int ya = max(cy - r, 0), yb = min(cy + r, g.dim[1] - 1);
-                const int za = max(cz - r, 0), zb = min(cz + r, g.dim[2] - 1);
-                const int ny = yb - ya + 1, nrows = ny * (zb - za + 1);
-                for (int idx = lane; idx < nrows; idx += 32) {
-                    const int z = za + idx / ny, y = ya + idx % ny;
-                    const T bz = z < cz ? sq_gap<T>(q.z, lo_z[z + 1]) : (z > cz ? sq_gap<T>(q.z, hi_z[z]) : (T)0);
-                    const T by = y < cy ? sq_gap<T>(q.y, lo_y[y + 1]) : (y > cy ? sq_gap<T>(q.y, hi_y[y]) : (T)0);
-                    const T byz = R::add(by, bz);
-                    if (byz > best.d) continue;
-                    const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-                    const bool shell_row = (z == cz - r) || (z == cz + r) || (y == cy - r) || (y == cy + r);
-                    if (shell_row || r == 0) {
-                        scan_run1<T>(dc.sorted, dc.cell_start[base + xa], dc.cell_start[base + xb + 1], q.x, q.y, q.z, best);
-                    } else {
-                        if (cx - r >= 0 && !(R::add(R::add(sq_gap<T>(q.x, lo_x[cx - r + 1]), by), bz) > best.d))
-                            scan_run1<T>(dc.sorted, dc.cell_start[base + cx - r], dc.cell_start[base + cx - r + 1],
-                                         q.x, q.y, q.z, best);
-                        if (cx + r <= g.dim[0] - 1 && !(R::add(R::add(sq_gap<T>(q.x, hi_x[cx + r]), by), bz) > best.d))
-                            scan_run1<T>(dc.sorted, dc.cell_start[base + cx + r], dc.cell_start[base + cx + r + 1],
-                                         q.x, q.y, q.z, best);
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    Best1<T> other;
-                    other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
-                    other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-                    other.tie = __shfl_xor_sync(0xffffffffu, (int)best.tie, o) != 0;
-                    merge_best<T>(best, other);
-                }
-                T lb = sq_gap<T>(q.x, lo_x[xa]);
-                lb = R::vmin(lb, sq_gap<T>(q.x, hi_x[xb + 1]));
-                lb = R::vmin(lb, sq_gap<T>(q.y, lo_y[ya]));
-                lb = R::vmin(lb, sq_gap<T>(q.y, hi_y[yb + 1]));
-                lb = R::vmin(lb, sq_gap<T>(q.z, lo_z[za]));
-                lb = R::vmin(lb, sq_gap<T>(q.z, hi_z[zb + 1]));
-                if (best.d < lb) { settled = true; break; }
-                if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) {
-                    settled = true;   // the whole grid has been examined
-                    break;
-                }
-            }
-            // rings grow cubically with the distance to the data: beyond kMaxRing the occupancy pyramid takes over
-            if (!settled && lane == 0) sw.vfar_list[atomicAdd(sw.counters + 2, 1u)] = sw.far_list[f];
-            finish_query1<T, kOut, kStats>(sw, settled && lane == 0, best, (long long)q.i, sum, sumsq, mc, ties);
+            const unsigned qt = sw.far_list[f];
+            const Pt<T> q = load_pt<T>(qc.sorted + qt);
+            Best1<T> best;
+            const bool ok = warp_ring_search<T>(g, dc, q, lane, best);
+            if (!ok && lane == 0) sw.vfar_list[atomicAdd(sw.counters + 2, 1u)] = qt;
+            finish_query1<T, kOut, kStats>(sw, ok && lane == 0, best, (long long)q.i, sum, sumsq, mc, ties);
         }
     }
     if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + blockIdx.x);
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(sw.counters + 5, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (*(volatile unsigned*)(sw.counters + 2) > 0) build_pyramid<T>(dc);
+    }
 }
 
-// Combines the per-block partials of one sweep into its pcu_b200_nn_stats.  grid (1, nsweeps).
+// Combines the per-block partials of one sweep into its pcu_b200_nn_stats (called by ONE CTA).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) stats_finalize_kernel(const Cloud<T>* __restrict__ clouds,
-                                                                  const Sweep<T>* __restrict__ sweeps) {
-    const Sweep<T> sw = sweeps[blockIdx.y];
-    const long long n = clouds[sw.qcloud].n;
+__device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, long long n) {
     const int main_used = (int)((n + kThreads - 1) / kThreads);
-    const int total = main_used + 2 * sw.far_blocks;   // main | far pass | pyramid pass
+    const int total = main_used + 2 * sw.far_blocks;   // main pass | far pass | pyramid pass
     double sum = 0.0, sumsq = 0.0;
     unsigned ties = 0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
@@ -225,7 +242,13 @@ __global__ void __launch_bounds__(kThreads) stats_finalize_kernel(const Cloud<T>
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int s = s0 + u * blockDim.x;
-            if (s < total) p[u] = sw.partial[s < main_used ? s : sw.main_blocks + (s - main_used)];
+            if (s < total) {
+                // written by other CTAs (some of them in this very launch): read around L1
+                const SweepPartial<T>* src = sw.partial + (s < main_used ? s : sw.main_blocks + (s - main_used));
+                p[u].sum = __ldcg(&src->sum); p[u].sumsq = __ldcg(&src->sumsq); p[u].max_d2 = __ldcg(&src->max_d2);
+                p[u].arg_q = __ldcg(&src->arg_q); p[u].arg_d = __ldcg(&src->arg_d);
+                p[u].n_tied = __ldcg(&src->n_tied); p[u].tie_at_max = __ldcg(&src->tie_at_max);
+            }
         }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
@@ -249,23 +272,27 @@ __global__ void __launch_bounds__(kThreads) stats_finalize_kernel(const Cloud<T>
         s.argmax_data = result.arg_d;
         s.n_queries = n;
         s.n_tied = result.n_tied;
-        s.n_far = sw.counters[0];
+        s.n_far = (long long)sw.counters[0];   // includes the very far ones (counters[2])
         s.witness_tied = result.tie_at_max ? 1 : 0;
         *sw.stats = s;
     }
 }
 
 // chamfer = mean_x |x - NN_y(x)| + mean_y |y - NN_x(y)|  (point_cloud_utils/__init__.py:112-115)
+template <typename T>
+__device__ __forceinline__ T chamfer_of(const pcu_b200_nn_stats& a, const pcu_b200_nn_stats& b) {
+    return (T)(a.sum_dist / (double)a.n_queries + b.sum_dist / (double)b.n_queries);
+}
+
 // stats: 2 per pair ([2p] = x->y, [2p+1] = y->x).  One block; pairs strided over its threads.
+// Used by the batched entry point (per-pair values and their fp64 sum).
 template <typename T>
 __global__ void __launch_bounds__(kThreads) chamfer_value_kernel(const pcu_b200_nn_stats* __restrict__ stats,
                                                                  long long npairs, T* __restrict__ out_value,
                                                                  double* __restrict__ out_sum) {
     double acc = 0.0;
     for (long long p = threadIdx.x; p < npairs; p += blockDim.x) {
-        const pcu_b200_nn_stats a = stats[2 * p], b = stats[2 * p + 1];
-        const double v = a.sum_dist / (double)a.n_queries + b.sum_dist / (double)b.n_queries;
-        const T vt = (T)v;
+        const T vt = chamfer_of<T>(stats[2 * p], stats[2 * p + 1]);
         if (out_value) out_value[p] = vt;
         acc += (double)vt;
     }

@@ -64,7 +64,7 @@ int fail(int status, const char* fmt, ...) {
 
 // Per-field byte strides between consecutive pairs of a batch (side 0 = first cloud of each pair,
 // side 1 = second cloud; direction 0 = first -> second, direction 1 = second -> first).
-struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_partial, pyramid, shape; };
+struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_state, scan_ticket, pyramid, shape; };
 struct SweepStrides { size_t out_dist, out_idx, partial, far_list, vfar_list, counters, tie_list; };
 
 template <typename U>
@@ -84,6 +84,7 @@ struct DescriptorArgs {
     long long batch;
     int nsweeps;
     pcu_b200_nn_stats* stats;
+    T* value_out;   // per-pair Chamfer values (bidirectional calls), or null
 };
 
 template <typename T>
@@ -101,7 +102,8 @@ __global__ void descriptors_kernel(const __grid_constant__ DescriptorArgs<T> a, 
         c.wall_lo = advance(c.wall_lo, p * st.wall_lo);
         c.wall_hi = advance(c.wall_hi, p * st.wall_hi);
         c.bbox_partial = advance(c.bbox_partial, p * st.bbox_partial);
-        c.scan_partial = advance(c.scan_partial, p * st.scan_partial);
+        c.scan_state = advance(c.scan_state, p * st.scan_state);
+        c.scan_ticket = advance(c.scan_ticket, p * st.scan_ticket);
         c.pyramid = advance(c.pyramid, p * st.pyramid);
         c.shape = advance(c.shape, p * st.shape);
         clouds[2 * p + s] = c;
@@ -119,6 +121,9 @@ __global__ void descriptors_kernel(const __grid_constant__ DescriptorArgs<T> a, 
         w.counters = advance(w.counters, p * st.counters);
         w.tie_list = advance(w.tie_list, p * st.tie_list);
         w.stats = a.stats ? a.stats + p * a.nsweeps + d : nullptr;
+        w.pair_stats = a.stats ? a.stats + p * a.nsweeps : nullptr;
+        w.pair_ticket = advance(a.sweep[0].counters, p * a.ss[0].counters) + 4;
+        w.value_out = (a.nsweeps == 2 && a.value_out) ? a.value_out + p : nullptr;
         sweeps[p * a.nsweeps + d] = w;
     }
 }
@@ -215,6 +220,7 @@ struct PlanSpec {
     T* out_dist = nullptr;          // want_out (batch == 1)
     long long* out_idx = nullptr;
     pcu_b200_nn_stats* stats = nullptr;   // caller's device buffer, or null -> carved from the arena
+    T* value_out = nullptr;               // per-pair Chamfer values (nsweeps == 2), or null
     long long replay_points = 0;
 };
 
@@ -255,13 +261,14 @@ struct Plan {
         args.batch = B;
         args.nsweeps = sp.nsweeps;
         args.stats = sp.want_stats ? d_stats : nullptr;
+        args.value_out = sp.value_out;
         const long long sizes[2] = {sp.n, sp.m};
         const T* raws[2] = {sp.a, sp.b};
         max_n = std::max(sp.n, sp.m);
         max_cap = 0;
         max_bbox_blocks = 1;
         // far pass: a fixed number of CTAs per sweep (warp-stride loop over the far list)
-        far_blocks = (int)std::max<long long>(4, 592 / std::max<long long>(1, B * sp.nsweeps));
+        far_blocks = (int)std::max<long long>(4, 296 / std::max<long long>(1, B * sp.nsweeps));
         // zeroed region first: cell counters and sweep counters
         const size_t zero_from = cv.off;
         for (int s = 0; s < 2; ++s) {
@@ -274,10 +281,13 @@ struct Plan {
             max_bbox_blocks = std::max(max_bbox_blocks, cl.bbox_blocks);
             args.cs[s].raw = (size_t)3 * sizes[s] * sizeof(T);
             cl.cell_start = take_strided<unsigned>(cv, (size_t)cl.cell_cap + 1, B, args.cs[s].cell_start);
+            cl.scan_state = take_strided<unsigned long long>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
+                                                             args.cs[s].scan_state);
+            cl.scan_ticket = take_strided<unsigned>(cv, 1, B, args.cs[s].scan_ticket);
             max_cap = std::max(max_cap, cl.cell_cap);
         }
         for (int d = 0; d < sp.nsweeps; ++d)
-            args.sweep[d].counters = take_strided<unsigned>(cv, 4, B, args.ss[d].counters);
+            args.sweep[d].counters = take_strided<unsigned>(cv, 8, B, args.ss[d].counters);
         zero_begin = base ? base + zero_from : nullptr;
         zero_bytes = cv.off - zero_from;
         for (int s = 0; s < 2; ++s) {
@@ -289,8 +299,6 @@ struct Plan {
             cl.wall_lo = take_strided<T>(cv, (size_t)3 * cl.stride, B, st.wall_lo);
             cl.wall_hi = take_strided<T>(cv, (size_t)3 * cl.stride, B, st.wall_hi);
             cl.bbox_partial = take_strided<T>(cv, (size_t)cl.bbox_blocks * 6, B, st.bbox_partial);
-            cl.scan_partial = take_strided<unsigned>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
-                                                     st.scan_partial);
             cl.pyramid = take_strided<unsigned>(cv, (size_t)cl.cell_cap + 64, B, st.pyramid);
             cl.shape = take_strided<PyramidShape>(cv, 1, B, st.shape);
         }
@@ -342,13 +350,12 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     PCU_LAUNCH(bbox_partial_kernel<T>, dim3(plan.max_bbox_blocks, nclouds), kThreads, stream, plan.d_clouds);
     PCU_LAUNCH(grid_setup_kernel<T>, dim3(1, nclouds), kThreads, stream, plan.d_clouds);
     mark(ws, 2, stream);
-    PCU_LAUNCH(cell_count_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads * kBinPerThread - 1) / (kThreads * kBinPerThread));
+    PCU_LAUNCH(cell_count_kernel<T>, dim3(bin_blocks, nclouds), kThreads, stream, plan.d_clouds);
     mark(ws, 3, stream);
-    PCU_LAUNCH(scan_reduce_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
-    PCU_LAUNCH(scan_partials_kernel<T>, dim3(1, nclouds), kScanThreads, stream, plan.d_clouds);
-    PCU_LAUNCH(scan_apply_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(scan_lookback_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
     mark(ws, 4, stream);
-    PCU_LAUNCH(scatter_kernel<T>, dim3(pts_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH(scatter_kernel<T>, dim3(bin_blocks, nclouds), kThreads, stream, plan.d_clouds);
     mark(ws, 5, stream);
     return PCU_B200_OK;
 }
@@ -393,7 +400,6 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         PCU_LAUNCH((nn1_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
         PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, 1), kPyramidThreads, stream, plan.d_clouds, plan.d_sweeps);
         PCU_LAUNCH((nn1_vfar_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
     } else if (k <= 32) {
@@ -438,6 +444,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     spec.nsweeps = ns; spec.k = 1; spec.want_stats = true;
     spec.occupancy = occupancy_for(ws, 1);
     spec.stats = out_stats;
+    spec.value_out = both ? out_value : nullptr;
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec));
     mark(ws, 0, stream);
@@ -448,13 +455,8 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     mark(ws, 6, stream);
     PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-    PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, ns), kPyramidThreads, stream, plan.d_clouds, plan.d_sweeps);
     PCU_LAUNCH((nn1_vfar_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
     mark(ws, 7, stream);
-    PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-    if (both && out_value) {
-        PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, out_stats, 1LL, out_value, (double*)nullptr);
-    }
     mark(ws, 8, stream);
     return PCU_B200_OK;
 }
@@ -510,10 +512,8 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
         PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, plan.nsweeps_total), kPyramidThreads, stream, plan.d_clouds, plan.d_sweeps);
         PCU_LAUNCH((nn1_vfar_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
-        PCU_LAUNCH(stats_finalize_kernel<T>, dim3(1, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,
                    out_per_pair ? out_per_pair + first : (T*)nullptr, out_sum);
         mark(ws, 8, stream);

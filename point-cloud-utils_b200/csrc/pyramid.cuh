@@ -9,22 +9,17 @@
 // the grid size.  Exactness is the same wall argument as everywhere else: a node is skipped only when
 // the lower bound of the reference-rounded distance to its cell box is STRICTLY above the current best.
 //
-// The pyramid is built by one CTA per sweep, and only when that sweep has such queries (the kernel
-// exits at once otherwise): uniform random clouds never pay for it.
+// The pyramid is built by the last CTA of the far pass (nn1.cuh), and only when that sweep has such
+// queries: uniform random clouds never pay for it.
 #pragma once
 #include "search.cuh"
+#include "nn1.cuh"
 
 namespace pcu {
 
-constexpr int kPyramidThreads = 1024;
-
-// grid (1, nsweeps)
+// Fills the levels of the dataset's occupancy pyramid; executed by ONE CTA (the far pass's last one).
 template <typename T>
-__global__ void __launch_bounds__(kPyramidThreads) pyramid_build_kernel(const Cloud<T>* __restrict__ clouds,
-                                                                        const Sweep<T>* __restrict__ sweeps) {
-    const Sweep<T> sw = sweeps[blockIdx.y];
-    if (sw.counters[2] == 0) return;             // nobody needs it
-    const Cloud<T> dc = clouds[sw.dcloud];
+__device__ void build_pyramid(const Cloud<T>& dc) {
     __shared__ PyramidShape ps;
     for (int w = threadIdx.x; w < (int)(sizeof(PyramidShape) / sizeof(int)); w += blockDim.x)
         reinterpret_cast<int*>(&ps)[w] = reinterpret_cast<const int*>(dc.shape)[w];
@@ -44,10 +39,11 @@ __global__ void __launch_bounds__(kPyramidThreads) pyramid_build_kernel(const Cl
                     const int row = (zz * cy + yy) * cx;
                     const int x0 = 2 * x, x1 = min(2 * x + 2, cx);
                     if (l == 1) total += dc.cell_start[row + x1] - dc.cell_start[row + x0];   // x-adjacent cells are contiguous
-                    else for (int xx = x0; xx < x1; ++xx) total += below[row + xx];
+                    else for (int xx = x0; xx < x1; ++xx) total += __ldcg(below + row + xx);
                 }
             out[node] = total;
         }
+        __threadfence();
         __syncthreads();
     }
 }
@@ -129,7 +125,33 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const Cloud<T>* __re
             finish_query1<T, kOut, kStats>(sw, true, best, (long long)q.i, sum, sumsq, mc, ties);
         }
     }
-    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + sw.far_blocks + blockIdx.x);
+    if (kStats) {
+        block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + sw.far_blocks + blockIdx.x);
+        // The CTA that finishes last folds all partials of this sweep (main pass + this pass) into the
+        // caller's statistics record; for a bidirectional call the sweep that finishes second also
+        // writes the Chamfer value.  No separate finalize launch.
+        __shared__ bool s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(sw.counters + 3, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            finalize_sweep<T>(sw, qc.n);
+            if (sw.value_out != nullptr && threadIdx.x == 0) {
+                __threadfence();
+                if (atomicAdd(sw.pair_ticket, 1u) == 1u) {
+                    __threadfence();
+                    const volatile pcu_b200_nn_stats* ps = sw.pair_stats;
+                    pcu_b200_nn_stats a, b;
+                    a.sum_dist = ps[0].sum_dist; a.n_queries = ps[0].n_queries;
+                    b.sum_dist = ps[1].sum_dist; b.n_queries = ps[1].n_queries;
+                    *sw.value_out = chamfer_of<T>(a, b);
+                }
+            }
+        }
+    }
 }
 
 }  // namespace pcu

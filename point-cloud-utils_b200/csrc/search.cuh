@@ -34,15 +34,20 @@ struct Sweep {
     int k;
     int squared;
     int main_blocks;             // partial slots [0, main_blocks) are written by the main kernel
-    int far_blocks;              // partial slots [main_blocks, main_blocks + far_blocks) by the far kernel
+    int far_blocks;              // partial slots [main_blocks, main_blocks + far_blocks) by the pyramid pass
     T* out_dist;                 // (n, k) or null
     long long* out_idx;          // (n, k) or null
     SweepPartial<T>* partial;    // main_blocks + far blocks slots, or null
     unsigned* far_list;          // sorted-order positions of queries the one-ring pass could not settle
     unsigned* vfar_list;         // ... and of those the ring walk gave up on (answered by the pyramid descent)
-    unsigned* counters;          // [0] far queries, [1] tied queries, [2] very far queries
+    unsigned* counters;          // [0] far queries, [1] tied, [2] very far, [3] finished CTAs of the last pass, [4] pair ticket
     long long* tie_list;         // caller-order rows whose answer depends on tie order
     pcu_b200_nn_stats* stats;    // or null
+    // bidirectional calls: where the pair's Chamfer value goes (null: not wanted), the pair's two
+    // statistics records and a zeroed ticket shared by the two sweeps of the pair
+    T* value_out;
+    pcu_b200_nn_stats* pair_stats;
+    unsigned* pair_ticket;
 };
 
 template <typename T>

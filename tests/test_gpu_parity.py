@@ -204,3 +204,20 @@ def test_far_apart_and_clustered_clouds(pcu, oracle, dtype):
     got = pcu.k_nearest_neighbors(x[:2000], blobs, 5)                 # ... and k > 1 still agrees
     ref = oracle.k_nearest_neighbors(x[:2000], blobs, 5)
     assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+
+
+@pytest.mark.parametrize("k", [1, 16])
+def test_million_point_clouds_against_oracle(pcu, oracle, k):
+    """BASELINE configs[1] / [3] shapes at 1e6 x 1e6 fp32: every index and distance against the oracle
+    (the host CPU finishes this in seconds with its OpenMP sweep)."""
+    rng = np.random.default_rng(2024 + k)
+    q = rng.random((1000000, 3), dtype=np.float32)
+    d = rng.random((1000000, 3), dtype=np.float32)
+    got_d, got_i = pcu.k_nearest_neighbors(q, d, k)
+    ref_d, ref_i = oracle.k_nearest_neighbors(q, d, k)
+    assert np.array_equal(got_i, ref_i)
+    assert np.array_equal(got_d, ref_d)
+    if k == 1:
+        ref = float(oracle.chamfer_distance(q, d))
+        assert abs(float(pcu.chamfer_distance(q, d)) - ref) <= REL * ref
+        assert pcu.hausdorff_distance(q, d, return_index=True) == oracle.hausdorff_distance(q, d, return_index=True)
