@@ -109,8 +109,8 @@ const char* pcu_b200_profile_stage_name(int stage);
  * out_idx  : (n, k) row-major int64 indices into dataset
  * out_n_tied (may be NULL): device int64 that receives the number of queries that went through
  *            the tie replay.
- * Unless disable_tie_replay is set, this call synchronises `stream` once (it reads the number of
- * flagged queries back to decide whether the kd-tree replay has to run at all).
+ * The call never synchronises: the kd-tree replay is one cooperative launch gated, on the device, on
+ * the number of flagged queries (it returns at once when that number is zero).
  * Replaces shortest_distances_nanoflann (src/point_cloud_distance.cpp:21-99).                    */
 int pcu_b200_knn_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m, int k,
                      int squared, float* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream);
@@ -129,7 +129,7 @@ int pcu_b200_nn_stats_f64(pcu_b200_workspace* ws, const double* query, int64_t n
 /* Re-answers stats->argmax_query with the reference's tie order (kd-tree replay built with
  * max_points_per_leaf) and stores the result in stats->argmax_data; clears witness_tied.
  * `stats` is a DEVICE pointer to one record produced by the calls above for (query, dataset).
- * Synchronises the stream (the replay builds the tree level by level).                           */
+ * Synchronises the stream once (the workspace scratch is re-carved for the replay).              */
 int pcu_b200_resolve_witness_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset,
                                  int64_t m, pcu_b200_nn_stats* stats, void* stream);
 int pcu_b200_resolve_witness_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const double* dataset,

@@ -125,7 +125,7 @@ int debug_kd_tree(pcu_b200_workspace* ws, const T* points, long long m, int leaf
     dpts = cv.take<T>((size_t)3 * m);
     cudaStream_t st = ws->own_stream;
     PCU_CUDA(cudaMemcpyAsync(dpts, points, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
-    const int rs = build_kd_replica<T>(rb, dpts, m, leaf, st, g_launches);
+    const int rs = build_kd_replica<T>(rb, dpts, m, leaf, nullptr, st, g_launches);
     if (rs != PCU_B200_OK) return fail(rs, "kd replica build failed: %s", cudaGetErrorString(cudaGetLastError()));
     KdCounters hc;
     PCU_CUDA(cudaMemcpyAsync(&hc, rb.counters, sizeof hc, cudaMemcpyDeviceToHost, st));

@@ -12,20 +12,27 @@
 //             (nanoflann.hpp:1001-1059, :1061-1110, :1121-1162).  planeSplit's two-pointer exchange
 //             is deterministic -- the j-th misplaced element from the left trades places with the
 //             j-th misplaced element from the right -- so it is reproduced with prefix sums.
+//             ONE cooperative launch builds the whole tree: the phases of a level are separated by
+//             grid-wide barriers, the level loop runs on the device, and the kernel returns at once
+//             when its gate (the number of flagged queries) is zero -- no host synchronisation.
 //   search  : findNeighbors / searchLevel / KNNResultSet (nanoflann.hpp:1394-1418, :1545-1624,
 //             :157-230) with an explicit stack; one thread per flagged query.
 //
-// The build costs a few hundred small launches and is only run when at least one query is
-// flagged (uniform random clouds: none for k = 1, a handful per million queries for k = 16).
+// The build only does work when at least one query is flagged (uniform random clouds: none for
+// k = 1, a handful per million queries for k = 16).
 #pragma once
 #include <atomic>
 #include <cfloat>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "grid.cuh"
 #include "host_util.h"
 #include "../../include/pcu_b200.h"
 
 namespace pcu {
+
+constexpr int kKdItems = 8;                       // slots per thread and scan tile
+constexpr int kKdTile = kThreads * kKdItems;      // slots per scan tile
 
 template <typename T>
 struct KdNode {
@@ -46,6 +53,8 @@ struct KdCounters {
     int level_begin;    // first node id of the current level
     int level_end;      // one past the last node id of the current level
     int n_split;        // nodes of the current level that were split
+    int done;           // set when a level split nothing
+    int levels;         // levels processed (diagnostic)
 };
 
 template <typename T>
@@ -68,7 +77,7 @@ struct KdReplayBuffers {
         order = cv.take<int>((size_t)points);
         node_of = cv.take<int>((size_t)points);
         prefix = cv.take<unsigned>((size_t)points + 1);
-        scan_partial = cv.take<unsigned>(((size_t)points + 1 + kScanTile - 1) / kScanTile + 1);
+        scan_partial = cv.take<unsigned>(((size_t)points + 1 + kKdTile - 1) / kKdTile + 1);
         left_pos = cv.take<int>((size_t)points);
         right_pos = cv.take<int>((size_t)points);
         nodes = cv.take<KdNode<T>>((size_t)2 * points + 2);
@@ -81,28 +90,40 @@ struct KdReplayBuffers {
 
 __global__ void widen_counter_kernel(const unsigned* src, long long* dst) { *dst = (long long)*src; }
 
-// ---- build kernels -------------------------------------------------------------------------------
-template <typename T>
-__global__ void kd_init_kernel(KdReplayBuffers<T> b, int m) {
-    using R = Real<T>;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < m) { b.order[s] = s; b.node_of[s] = 0; }
-    if (s == 0) {
-        KdNode<T> nd{};
-        nd.feat = -2; nd.first = 0; nd.last = m; nd.kid0 = nd.kid1 = -1; nd.parent = -1; nd.side = 0;
-        for (int d = 0; d < 3; ++d) { nd.tight_lo[d] = ordered<T>(R::inf()); nd.tight_hi[d] = ordered<T>(-R::inf()); }
-        b.nodes[0] = nd;
-        KdCounters c; c.n_nodes = 1; c.level_begin = 0; c.level_end = 1; c.n_split = 0;
-        *b.counters = c;
+// ---- build -----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned kd_block_exclusive_scan(unsigned v, unsigned* total) {
+    // kThreads threads; returns the exclusive prefix of v, *total = block sum
+    __shared__ unsigned warp_sum[kThreads / 32];
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (l >= o) inc += u;
     }
+    if (l == 31) warp_sum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned s = l < kThreads / 32 ? warp_sum[l] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, s, o);
+            if (l >= o) s += u;
+        }
+        if (l < kThreads / 32) warp_sum[l] = s;
+    }
+    __syncthreads();
+    const unsigned before = w ? warp_sum[w - 1] : 0u;
+    *total = warp_sum[kThreads / 32 - 1];
+    __syncthreads();
+    return before + inc - v;
 }
 
-// tight bounding box of every node of the current level (element-parallel, atomics on the ordered
-// integer image; a warp whose lanes all sit in the same node reduces first)
+// tight bounding box contribution of slot s to its node (atomics on the ordered integer image; a warp
+// whose lanes all sit in the same node reduces first).  Called by whole warps.
 template <typename T>
-__global__ void kd_tight_box_kernel(KdReplayBuffers<T> b, const T* __restrict__ pts, int m) {
+__device__ __forceinline__ void kd_tight_box_slot(const KdReplayBuffers<T>& b, const T* __restrict__ pts, int s, int m) {
     using bits_t = typename Real<T>::bits_t;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int node = s < m ? b.node_of[s] : -1;
     bits_t v[3] = {0, 0, 0};
     if (node >= 0) {
@@ -129,110 +150,65 @@ __global__ void kd_tight_box_kernel(KdReplayBuffers<T> b, const T* __restrict__ 
     }
 }
 
-// leaf-or-split decision + split plane of every node of the current level (node-parallel);
-// also hands this node's tight extent along the parent's split axis up to the parent
-// (divlow / divhigh, nanoflann.hpp:1047-1048).
+// leaf-or-split decision + split plane of one node; also hands this node's tight extent along the
+// parent's split axis up to the parent (divlow / divhigh, nanoflann.hpp:1047-1048).
 template <typename T>
-__global__ void kd_decide_kernel(KdReplayBuffers<T> b, int leaf_cap) {
+__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap) {
     using R = Real<T>;
-    const KdCounters c = *b.counters;
-    for (int id = c.level_begin + blockIdx.x * blockDim.x + threadIdx.x; id < c.level_end; id += gridDim.x * blockDim.x) {
-        KdNode<T>& nd = b.nodes[id];
-        T tlo[3], thi[3];
-        for (int d = 0; d < 3; ++d) { tlo[d] = unordered<T>(nd.tight_lo[d]); thi[d] = unordered<T>(nd.tight_hi[d]); }
-        if (nd.parent >= 0) {
-            KdNode<T>& par = b.nodes[nd.parent];
-            if (nd.side == 0) par.div_lo = thi[par.feat]; else par.div_hi = tlo[par.feat];
-        } else {
-            for (int d = 0; d < 3; ++d) { nd.loose_lo[d] = tlo[d]; nd.loose_hi[d] = thi[d]; }  // root: computeBoundingBox
-        }
-        const int count = nd.last - nd.first;
-        if (count <= leaf_cap) { nd.feat = -1; continue; }
-        // middleSplit_ (nanoflann.hpp:1061-1096)
-        const T eps = (T)0.00001;
-        T widest = R::sub(nd.loose_hi[0], nd.loose_lo[0]);
-        for (int d = 1; d < 3; ++d) {
-            const T w = R::sub(nd.loose_hi[d], nd.loose_lo[d]);
-            if (w > widest) widest = w;
-        }
-        const T gate = R::mul(R::sub((T)1, eps), widest);
-        T best_spread = (T)-1;
-        int feat = 0;
-        for (int d = 0; d < 3; ++d) {
-            const T w = R::sub(nd.loose_hi[d], nd.loose_lo[d]);
-            if (w > gate) {
-                const T spread = R::sub(thi[d], tlo[d]);
-                if (spread > best_spread) { feat = d; best_spread = spread; }
-            }
-        }
-        const T mid = R::mul(R::add(nd.loose_lo[feat], nd.loose_hi[feat]), (T)0.5);
-        T cut;
-        if (mid < tlo[feat]) cut = tlo[feat];
-        else if (mid > thi[feat]) cut = thi[feat];
-        else cut = mid;
-        nd.feat = feat;
-        nd.cut = cut;
+    KdNode<T>& nd = b.nodes[id];
+    T tlo[3], thi[3];
+    for (int d = 0; d < 3; ++d) { tlo[d] = unordered<T>(nd.tight_lo[d]); thi[d] = unordered<T>(nd.tight_hi[d]); }
+    if (nd.parent >= 0) {
+        KdNode<T>& par = b.nodes[nd.parent];
+        if (nd.side == 0) par.div_lo = thi[par.feat]; else par.div_hi = tlo[par.feat];
+    } else {
+        for (int d = 0; d < 3; ++d) { nd.loose_lo[d] = tlo[d]; nd.loose_hi[d] = thi[d]; }  // root: computeBoundingBox
     }
+    const int count = nd.last - nd.first;
+    if (count <= leaf_cap) { nd.feat = -1; return; }
+    // middleSplit_ (nanoflann.hpp:1061-1096)
+    const T eps = (T)0.00001;
+    T widest = R::sub(nd.loose_hi[0], nd.loose_lo[0]);
+    for (int d = 1; d < 3; ++d) {
+        const T w = R::sub(nd.loose_hi[d], nd.loose_lo[d]);
+        if (w > widest) widest = w;
+    }
+    const T gate = R::mul(R::sub((T)1, eps), widest);
+    T best_spread = (T)-1;
+    int feat = 0;
+    for (int d = 0; d < 3; ++d) {
+        const T w = R::sub(nd.loose_hi[d], nd.loose_lo[d]);
+        if (w > gate) {
+            const T spread = R::sub(thi[d], tlo[d]);
+            if (spread > best_spread) { feat = d; best_spread = spread; }
+        }
+    }
+    const T mid = R::mul(R::add(nd.loose_lo[feat], nd.loose_hi[feat]), (T)0.5);
+    T cut;
+    if (mid < tlo[feat]) cut = tlo[feat];
+    else if (mid > thi[feat]) cut = thi[feat];
+    else cut = mid;
+    nd.feat = feat;
+    nd.cut = cut;
 }
 
 // sweep 1: flag = (value < cut); sweep 2: flag = (value <= cut) on the part right of n_less.
 template <typename T, int kSweep>
-__global__ void kd_flag_kernel(KdReplayBuffers<T> b, const T* __restrict__ pts, int m) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > m) return;
-    unsigned f = 0;
-    if (s < m) {
-        const int node = b.node_of[s];
-        if (node >= 0) {
-            const KdNode<T>& nd = b.nodes[node];
-            if (nd.feat >= 0) {
-                const T v = pts[3 * (long long)b.order[s] + nd.feat];
-                if (kSweep == 1) f = v < nd.cut ? 1u : 0u;
-                else f = (s >= nd.first + nd.n_less && v <= nd.cut) ? 1u : 0u;
-            }
-        }
-    }
-    b.prefix[s] = f;   // entry m is the sentinel that becomes the grand total
+__device__ __forceinline__ unsigned kd_flag(const KdReplayBuffers<T>& b, const T* __restrict__ pts, int s, int m) {
+    if (s >= m) return 0u;    // entry m is the sentinel that carries the grand total
+    const int node = b.node_of[s];
+    if (node < 0) return 0u;
+    const KdNode<T>& nd = b.nodes[node];
+    if (nd.feat < 0) return 0u;
+    const T v = pts[3 * (long long)b.order[s] + nd.feat];
+    if (kSweep == 1) return v < nd.cut ? 1u : 0u;
+    return (s >= nd.first + nd.n_less && v <= nd.cut) ? 1u : 0u;
 }
 
-// exclusive scan of prefix[0 .. m] (three phases, same scheme as grid.cuh)
+// exclusive prefix of the flags at slot s: in-tile prefix + offset of the tile
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads) kd_scan_reduce_kernel(KdReplayBuffers<T> b, int count) {
-    const long long base = (long long)blockIdx.x * kScanTile;
-    unsigned s = 0;
-    for (int k = 0; k < kScanItems; ++k) {
-        const long long i = base + (long long)k * kScanThreads + threadIdx.x;
-        if (i < count) s += b.prefix[i];
-    }
-    unsigned total;
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) b.scan_partial[blockIdx.x] = total;
-}
-template <typename T>
-__global__ void __launch_bounds__(kScanThreads) kd_scan_partials_kernel(KdReplayBuffers<T> b, int nb) {
-    unsigned carry = 0;
-    for (int base = 0; base < nb; base += kScanThreads) {
-        const int i = base + threadIdx.x;
-        const unsigned v = i < nb ? b.scan_partial[i] : 0u;
-        unsigned total;
-        const unsigned ex = block_exclusive_scan(v, &total);
-        if (i < nb) b.scan_partial[i] = carry + ex;
-        carry += total;
-    }
-}
-template <typename T>
-__global__ void __launch_bounds__(kScanThreads) kd_scan_apply_kernel(KdReplayBuffers<T> b, int count) {
-    const long long base = (long long)blockIdx.x * kScanTile;
-    unsigned v[kScanItems];
-    unsigned s = 0;
-    const long long first = base + (long long)threadIdx.x * kScanItems;
-    for (int k = 0; k < kScanItems; ++k) { v[k] = (first + k) < count ? b.prefix[first + k] : 0u; s += v[k]; }
-    unsigned total;
-    unsigned run = block_exclusive_scan(s, &total) + b.scan_partial[blockIdx.x];
-    for (int k = 0; k < kScanItems; ++k) {
-        if ((first + k) < count) b.prefix[first + k] = run;
-        run += v[k];
-    }
+__device__ __forceinline__ unsigned kd_prefix(const KdReplayBuffers<T>& b, int s) {
+    return b.prefix[s] + b.scan_partial[s / kKdTile];
 }
 
 // Who trades places with whom (nanoflann.hpp:1125-1160): inside a node, with F = number of flagged
@@ -240,43 +216,36 @@ __global__ void __launch_bounds__(kScanThreads) kd_scan_apply_kernel(KdReplayBuf
 // unflagged slot of [lo, lo + F) (ascending) exchanges with the j-th flagged slot of [lo + F, last)
 // (descending).
 template <typename T, int kSweep>
-__global__ void kd_partner_kernel(KdReplayBuffers<T> b, int m) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m) return;
+__device__ __forceinline__ void kd_partner_slot(const KdReplayBuffers<T>& b, int s) {
     const int node = b.node_of[s];
     if (node < 0) return;
     KdNode<T>& nd = b.nodes[node];
     if (nd.feat < 0) return;
     const int lo = kSweep == 1 ? nd.first : nd.first + nd.n_less;
-    const unsigned at_lo = b.prefix[lo], at_last = b.prefix[nd.last];
+    const unsigned at_lo = kd_prefix<T>(b, lo), at_last = kd_prefix<T>(b, nd.last);
     const int F = (int)(at_last - at_lo);
     if (s == nd.first) {
         if (kSweep == 1) nd.n_less = F; else nd.n_less_eq = nd.n_less + F;
     }
     if (s < lo) return;
-    const bool flagged = b.prefix[s + 1] != b.prefix[s];
+    const unsigned here = kd_prefix<T>(b, s), next = kd_prefix<T>(b, s + 1);
+    const bool flagged = next != here;
     const int r = s - lo;
-    if (r < F && !flagged) {
-        const int j = r - (int)(b.prefix[s] - at_lo);
-        b.left_pos[lo + j] = s;
-    } else if (r >= F && flagged) {
-        const int j = (int)(at_last - b.prefix[s + 1]);
-        b.right_pos[lo + j] = s;
-    }
+    if (r < F && !flagged) b.left_pos[lo + (r - (int)(here - at_lo))] = s;
+    else if (r >= F && flagged) b.right_pos[lo + (int)(at_last - next)] = s;
 }
 
 template <typename T, int kSweep>
-__global__ void kd_exchange_kernel(KdReplayBuffers<T> b, int m) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m) return;
+__device__ __forceinline__ void kd_exchange_slot(const KdReplayBuffers<T>& b, int s) {
     const int node = b.node_of[s];
     if (node < 0) return;
     const KdNode<T>& nd = b.nodes[node];
     if (nd.feat < 0) return;
+    // n_less / n_less_eq were stored by the partner phase
     const int lo = kSweep == 1 ? nd.first : nd.first + nd.n_less;
     if (s < lo) return;
-    const int F = (int)(b.prefix[nd.last] - b.prefix[lo]);
-    const int misplaced = F - (int)(b.prefix[lo + F] - b.prefix[lo]);   // unflagged slots inside [lo, lo + F)
+    const int F = kSweep == 1 ? nd.n_less : nd.n_less_eq - nd.n_less;
+    const int misplaced = F - (int)(kd_prefix<T>(b, lo + F) - kd_prefix<T>(b, lo));   // unflagged slots inside [lo, lo + F)
     const int j = s - lo;
     if (j >= misplaced) return;
     const int a = b.left_pos[lo + j], c = b.right_pos[lo + j];
@@ -285,57 +254,140 @@ __global__ void kd_exchange_kernel(KdReplayBuffers<T> b, int m) {
     b.order[c] = t;
 }
 
-// children of every split node of the current level (nanoflann.hpp:1098-1110, :1033-1045)
+// children of one split node (nanoflann.hpp:1098-1110, :1033-1045)
 template <typename T>
-__global__ void kd_children_kernel(KdReplayBuffers<T> b) {
+__device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, int id) {
     using R = Real<T>;
-    const KdCounters c = *b.counters;
-    for (int id = c.level_begin + blockIdx.x * blockDim.x + threadIdx.x; id < c.level_end; id += gridDim.x * blockDim.x) {
-        KdNode<T>& nd = b.nodes[id];
-        if (nd.feat < 0) continue;
-        const int count = nd.last - nd.first;
-        int left;
-        if (nd.n_less > count / 2) left = nd.n_less;
-        else if (nd.n_less_eq < count / 2) left = nd.n_less_eq;
-        else left = count / 2;
-        const int k0 = atomicAdd(&b.counters->n_nodes, 2);
-        atomicAdd(&b.counters->n_split, 1);
-        nd.kid0 = k0; nd.kid1 = k0 + 1;
-        for (int side = 0; side < 2; ++side) {
-            KdNode<T> ch{};
-            ch.feat = -2;
-            ch.first = side == 0 ? nd.first : nd.first + left;
-            ch.last = side == 0 ? nd.first + left : nd.last;
-            ch.kid0 = ch.kid1 = -1; ch.parent = id; ch.side = side;
-            for (int d = 0; d < 3; ++d) {
-                ch.loose_lo[d] = nd.loose_lo[d]; ch.loose_hi[d] = nd.loose_hi[d];
-                ch.tight_lo[d] = ordered<T>(R::inf()); ch.tight_hi[d] = ordered<T>(-R::inf());
-            }
-            if (side == 0) ch.loose_hi[nd.feat] = nd.cut; else ch.loose_lo[nd.feat] = nd.cut;
-            b.nodes[k0 + side] = ch;
+    KdNode<T>& nd = b.nodes[id];
+    if (nd.feat < 0) return;
+    const int count = nd.last - nd.first;
+    int left;
+    if (nd.n_less > count / 2) left = nd.n_less;
+    else if (nd.n_less_eq < count / 2) left = nd.n_less_eq;
+    else left = count / 2;
+    const int k0 = atomicAdd(&b.counters->n_nodes, 2);
+    atomicAdd(&b.counters->n_split, 1);
+    nd.kid0 = k0; nd.kid1 = k0 + 1;
+    for (int side = 0; side < 2; ++side) {
+        KdNode<T> ch{};
+        ch.feat = -2;
+        ch.first = side == 0 ? nd.first : nd.first + left;
+        ch.last = side == 0 ? nd.first + left : nd.last;
+        ch.kid0 = ch.kid1 = -1; ch.parent = id; ch.side = side;
+        for (int d = 0; d < 3; ++d) {
+            ch.loose_lo[d] = nd.loose_lo[d]; ch.loose_hi[d] = nd.loose_hi[d];
+            ch.tight_lo[d] = ordered<T>(R::inf()); ch.tight_hi[d] = ordered<T>(-R::inf());
         }
+        if (side == 0) ch.loose_hi[nd.feat] = nd.cut; else ch.loose_lo[nd.feat] = nd.cut;
+        b.nodes[k0 + side] = ch;
     }
 }
 
-// slots move down to the child that now owns them; slots of leaves retire
-template <typename T>
-__global__ void kd_descend_kernel(KdReplayBuffers<T> b, int m) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m) return;
-    const int node = b.node_of[s];
-    if (node < 0) return;
-    const KdNode<T>& nd = b.nodes[node];
-    if (nd.feat < 0) { b.node_of[s] = -1; return; }
-    b.node_of[s] = s < b.nodes[nd.kid0].last ? nd.kid0 : nd.kid1;
+// One flag-and-scan phase of the cooperative build: in-tile exclusive prefixes + tile totals, then
+// (after a grid barrier) the first CTA turns the totals into tile offsets.
+template <typename T, int kSweep>
+__device__ __forceinline__ void kd_scan_phase(cooperative_groups::grid_group& grid, const KdReplayBuffers<T>& b,
+                                              const T* __restrict__ pts, int m) {
+    const int count = m + 1;
+    const int ntiles = (count + kKdTile - 1) / kKdTile;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int first = tile * kKdTile + threadIdx.x * kKdItems;
+        unsigned v[kKdItems];
+        unsigned sum = 0;
+#pragma unroll
+        for (int k = 0; k < kKdItems; ++k) { v[k] = (first + k) < count ? kd_flag<T, kSweep>(b, pts, first + k, m) : 0u; sum += v[k]; }
+        unsigned total;
+        unsigned run = kd_block_exclusive_scan(sum, &total);
+#pragma unroll
+        for (int k = 0; k < kKdItems; ++k) {
+            if ((first + k) < count) b.prefix[first + k] = run;
+            run += v[k];
+        }
+        if (threadIdx.x == 0) b.scan_partial[tile] = total;
+    }
+    grid.sync();
+    if (blockIdx.x == 0) {
+        unsigned carry = 0;
+        for (int base = 0; base < ntiles; base += kThreads) {
+            const int i = base + threadIdx.x;
+            const unsigned v = i < ntiles ? b.scan_partial[i] : 0u;
+            unsigned total;
+            const unsigned ex = kd_block_exclusive_scan(v, &total);
+            if (i < ntiles) b.scan_partial[i] = carry + ex;
+            carry += total;
+        }
+    }
+    grid.sync();
 }
 
+// The whole build in one cooperative launch.  `gate` (may be null): device counter; when it reads
+// zero nobody needs the tree and every CTA returns immediately.
 template <typename T>
-__global__ void kd_next_level_kernel(KdReplayBuffers<T> b) {
-    KdCounters c = *b.counters;
-    c.level_begin = c.level_end;
-    c.level_end = c.n_nodes;
-    c.n_split = 0;
-    *b.counters = c;
+__global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b, const T* __restrict__ pts, int m,
+                                                            int leaf_cap, const unsigned* __restrict__ gate) {
+    namespace cg = cooperative_groups;
+    using R = Real<T>;
+    if (gate != nullptr && *gate == 0u) return;   // uniform over the grid
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gsize = gridDim.x * blockDim.x;
+    const int m_warp = (m + 31) & ~31;            // whole warps take part in the tight-box reduction
+
+    for (int s = gtid; s < m; s += gsize) { b.order[s] = s; b.node_of[s] = 0; }
+    if (gtid == 0) {
+        KdNode<T> nd{};
+        nd.feat = -2; nd.first = 0; nd.last = m; nd.kid0 = nd.kid1 = -1; nd.parent = -1; nd.side = 0;
+        for (int d = 0; d < 3; ++d) { nd.tight_lo[d] = ordered<T>(R::inf()); nd.tight_hi[d] = ordered<T>(-R::inf()); }
+        b.nodes[0] = nd;
+        KdCounters c{}; c.n_nodes = 1; c.level_begin = 0; c.level_end = 1;
+        *b.counters = c;
+    }
+    grid.sync();
+    for (int s = gtid; s < m_warp; s += gsize) kd_tight_box_slot<T>(b, pts, s, m);
+    grid.sync();
+
+    for (int level = 0; level < 4096; ++level) {
+        const int lb = *(volatile int*)&b.counters->level_begin, le = *(volatile int*)&b.counters->level_end;
+        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap);
+        grid.sync();
+        // sweep 1: strictly-less-than-the-cut to the front
+        kd_scan_phase<T, 1>(grid, b, pts, m);
+        for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 1>(b, s);
+        grid.sync();
+        for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 1>(b, s);
+        grid.sync();
+        // sweep 2: equal-to-the-cut next
+        kd_scan_phase<T, 2>(grid, b, pts, m);
+        for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 2>(b, s);
+        grid.sync();
+        for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 2>(b, s);
+        grid.sync();
+        for (int id = lb + gtid; id < le; id += gsize) kd_children_node<T>(b, id);
+        grid.sync();
+        // slots move down to the child that now owns them (slots of leaves retire) and immediately
+        // contribute to that child's tight box
+        for (int s = gtid; s < m_warp; s += gsize) {
+            if (s < m) {
+                const int node = b.node_of[s];
+                if (node >= 0) {
+                    const KdNode<T>& nd = b.nodes[node];
+                    b.node_of[s] = nd.feat < 0 ? -1 : (s < b.nodes[nd.kid0].last ? nd.kid0 : nd.kid1);
+                }
+            }
+            kd_tight_box_slot<T>(b, pts, s, m);
+        }
+        if (gtid == 0) {
+            KdCounters c = *b.counters;
+            c.done = c.n_split == 0;
+            c.level_begin = c.level_end;
+            c.level_end = c.n_nodes;
+            c.n_split = 0;
+            c.levels = level + 1;
+            *b.counters = c;
+        }
+        grid.sync();
+        if (*(volatile int*)&b.counters->done) break;
+    }
 }
 
 // ---- search ---------------------------------------------------------------------------------------
@@ -367,8 +419,13 @@ template <typename T>
 __device__ void kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__ pts, const T q[3], int k, bool squared,
                               T* out_d, long long* out_i) {
     using R = Real<T>;
+    // short lists live in (L1-cached) local memory while the tree is walked; long ones in the output row
+    T local_d[32];
+    long long local_i[32];
+    T* work_d = k <= 32 ? local_d : out_d;
+    long long* work_i = k <= 32 ? local_i : out_i;
     KdBest<T> best;
-    best.init(out_d, out_i, k);
+    best.init(work_d, work_i, k);
     struct Frame { int node; T bound; T off[3]; bool far; };
     Frame stack[kKdStack];
     int top = 0;
@@ -414,7 +471,10 @@ __device__ void kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__
             f.node = near_kid;
         }
     }
-    for (int c = 0; c < best.have; ++c) if (!squared) out_d[c] = R::root(out_d[c]);
+    for (int c = 0; c < best.have; ++c) {
+        out_d[c] = squared ? work_d[c] : R::root(work_d[c]);
+        out_i[c] = work_i[c];
+    }
     for (int c = best.have; c < k; ++c) { out_d[c] = (T)-1; out_i[c] = -1; }
 }
 
@@ -422,11 +482,12 @@ template <typename T>
 __global__ void kd_replay_kernel(KdReplayBuffers<T> b, const T* __restrict__ query, const T* __restrict__ pts, int k,
                                  int squared, const long long* __restrict__ rows, const unsigned* __restrict__ n_rows,
                                  T* out_dist, long long* out_idx) {
-    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= *n_rows) return;
-    const long long row = rows[t];
-    const T q[3] = {query[3 * row], query[3 * row + 1], query[3 * row + 2]};
-    kd_search_one<T>(b, pts, q, k, squared != 0, out_dist + row * k, out_idx + row * k);
+    const unsigned n = *n_rows;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const long long row = rows[t];
+        const T q[3] = {query[3 * row], query[3 * row + 1], query[3 * row + 2]};
+        kd_search_one<T>(b, pts, q, k, squared != 0, out_dist + row * k, out_idx + row * k);
+    }
 }
 
 // single query taken from a stats record (the Hausdorff witness)
@@ -448,58 +509,42 @@ __global__ void kd_witness_kernel(KdReplayBuffers<T> b, const T* __restrict__ qu
         if (cudaGetLastError() != cudaSuccess) return PCU_B200_CUDA_ERROR;            \
     } while (0)
 
-// Builds the replica of the reference's tree for `pts` (m points).  Synchronises once per level.
+// Enqueues the build of the reference-tree replica for `pts` (m points): one cooperative launch, no
+// host synchronisation.  With a non-null `gate` the kernel is a no-op when *gate == 0.
 template <typename T>
-int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int leaf_cap, cudaStream_t stream,
-                     std::atomic<long long>& launches) {
+int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int leaf_cap, const unsigned* gate,
+                     cudaStream_t stream, std::atomic<long long>& launches) {
     if (m_ll > b.capacity || m_ll >= 0x7fffffffLL) return PCU_B200_INTERNAL;
-    const int m = (int)m_ll;
-    const unsigned eb = (unsigned)((m + 1 + kThreads - 1) / kThreads);
-    const int scan_count = m + 1;
-    const unsigned sb = (unsigned)((scan_count + kScanTile - 1) / kScanTile);
-    KD_LAUNCH(kd_init_kernel<T>, eb, kThreads, stream, b, m);
-    for (int level = 0; level < 4096; ++level) {
-        KD_LAUNCH(kd_tight_box_kernel<T>, eb, kThreads, stream, b, pts, m);
-        KD_LAUNCH(kd_decide_kernel<T>, 256, kThreads, stream, b, leaf_cap);
-        // sweep 1: strictly less than the cut to the front
-        KD_LAUNCH((kd_flag_kernel<T, 1>), eb, kThreads, stream, b, pts, m);
-        KD_LAUNCH(kd_scan_reduce_kernel<T>, sb, kScanThreads, stream, b, scan_count);
-        KD_LAUNCH(kd_scan_partials_kernel<T>, 1, kScanThreads, stream, b, (int)sb);
-        KD_LAUNCH(kd_scan_apply_kernel<T>, sb, kScanThreads, stream, b, scan_count);
-        KD_LAUNCH((kd_partner_kernel<T, 1>), eb, kThreads, stream, b, m);
-        KD_LAUNCH((kd_exchange_kernel<T, 1>), eb, kThreads, stream, b, m);
-        // sweep 2: equal to the cut next
-        KD_LAUNCH((kd_flag_kernel<T, 2>), eb, kThreads, stream, b, pts, m);
-        KD_LAUNCH(kd_scan_reduce_kernel<T>, sb, kScanThreads, stream, b, scan_count);
-        KD_LAUNCH(kd_scan_partials_kernel<T>, 1, kScanThreads, stream, b, (int)sb);
-        KD_LAUNCH(kd_scan_apply_kernel<T>, sb, kScanThreads, stream, b, scan_count);
-        KD_LAUNCH((kd_partner_kernel<T, 2>), eb, kThreads, stream, b, m);
-        KD_LAUNCH((kd_exchange_kernel<T, 2>), eb, kThreads, stream, b, m);
-        KD_LAUNCH(kd_children_kernel<T>, 256, kThreads, stream, b);
-        KD_LAUNCH(kd_descend_kernel<T>, eb, kThreads, stream, b, m);
-        KdCounters h;
-        if (cudaMemcpyAsync(&h, b.counters, sizeof h, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-        if (cudaStreamSynchronize(stream) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-        if (h.n_split == 0) return PCU_B200_OK;
-        KD_LAUNCH(kd_next_level_kernel<T>, 1, 1, stream, b);
+    int m = (int)m_ll;
+    static int blocks_per_sm = 0, sms = 0;
+    if (blocks_per_sm == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+        int f32 = 0, f64 = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f32, kd_build_kernel<float>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f64, kd_build_kernel<double>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+        blocks_per_sm = std::max(1, std::min(8, std::min(f32, f64)));   // enough threads to cover the latency of the element passes
     }
-    return PCU_B200_INTERNAL;
+    const long long want = (m_ll + kThreads - 1) / kThreads;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)blocks_per_sm * sms));
+    void* args[] = {(void*)&b, (void*)&pts, (void*)&m, (void*)&leaf_cap, (void*)&gate};
+    if (cudaLaunchCooperativeKernel((void*)kd_build_kernel<T>, dim3(grid), dim3(kThreads), args, 0, stream) != cudaSuccess)
+        return PCU_B200_CUDA_ERROR;
+    launches.fetch_add(1, std::memory_order_relaxed);
+    return PCU_B200_OK;
 }
 
-// Re-answers the rows listed in tie_list with the reference's own tie order.  Reads the list length
-// back (one synchronisation); does nothing more when it is zero.
+// Re-answers the rows listed in tie_list with the reference's own tie order.  Both launches are gated on
+// the device-side list length: nothing happens (and nothing synchronises) when no query was flagged.
 template <typename T>
 int enqueue_tie_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, long long m, int k, int squared,
-                       int leaf_cap, const long long* tie_list, const unsigned* tie_count, T* out_dist,
-                       long long* out_idx, cudaStream_t stream, std::atomic<long long>& launches) {
-    unsigned h_count = 0;
-    if (cudaMemcpyAsync(&h_count, tie_count, sizeof h_count, cudaMemcpyDeviceToHost, stream) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-    if (cudaStreamSynchronize(stream) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-    if (h_count == 0) return PCU_B200_OK;
-    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, stream, launches);
+                       int leaf_cap, const long long* tie_list, const unsigned* tie_count, long long max_rows,
+                       T* out_dist, long long* out_idx, cudaStream_t stream, std::atomic<long long>& launches) {
+    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, tie_count, stream, launches);
     if (st != PCU_B200_OK) return st;
-    KD_LAUNCH(kd_replay_kernel<T>, (h_count + 127) / 128, 128, stream, b, query, dataset, k, squared, tie_list,
-              tie_count, out_dist, out_idx);
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + 127) / 128, 1184));
+    KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx);
     return PCU_B200_OK;
 }
 
@@ -507,7 +552,7 @@ int enqueue_tie_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, 
 template <typename T>
 int enqueue_witness_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, long long m, int leaf_cap,
                            pcu_b200_nn_stats* stats, cudaStream_t stream, std::atomic<long long>& launches) {
-    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, stream, launches);
+    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, nullptr, stream, launches);
     if (st != PCU_B200_OK) return st;
     KD_LAUNCH(kd_witness_kernel<T>, 1, 1, stream, b, query, dataset, stats);
     return PCU_B200_OK;

@@ -419,7 +419,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     if (!ws->opts.disable_tie_replay) {
         const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
         const int rs = enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
-                                             plan.args.sweep[0].counters + 1, out_dist, out_idx, stream, g_launches);
+                                             plan.args.sweep[0].counters + 1, n, out_dist, out_idx, stream, g_launches);
         if (rs != PCU_B200_OK) return fail(rs, "tie replay failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (out_n_tied) {

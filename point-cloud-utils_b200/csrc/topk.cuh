@@ -252,26 +252,58 @@ __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const Cloud<T>* __
 #pragma unroll
     for (int s = 0; s < K; ++s) list[s] = s < K - k ? ListKey<T>::dead() : ListKey<T>::empty();
     T rej = R::inf();   // smallest distance turned away or pushed out: equal to the k-th => order-dependent answer
-    int r = 0;
-    unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
-    for (;;) {
-        if (j < e) {
-            const Pt<T> p = load_pt<T>(dc.sorted + j);
-            ++j;
-            const T d = dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z);
-            const ListKey<T> key = ListKey<T>::make(d, p.i);
+    // Candidates that beat the current k-th are first parked in a small per-lane queue.  An insertion
+    // costs ~6 instructions per list slot and is paid by the whole warp whenever ANY lane inserts, so
+    // the warp inserts in rounds -- one parked candidate per lane -- only when some lane's queue is
+    // full: the number of rounds follows the busiest lane instead of the union of all lanes.
+    constexpr int kPark = 4;
+    ListKey<T> park[kPark];
+    int parked = 0;
+    auto insert_round = [&]() {
+        if (parked > 0) {
+            const ListKey<T> key = park[0];
+#pragma unroll
+            for (int u = 0; u + 1 < kPark; ++u) park[u] = park[u + 1];
+            --parked;
             if (key.less(list[K - 1])) {
                 if (!list[K - 1].is_empty()) rej = R::vmin(rej, list[K - 1].dist());
                 list_insert<T, K>(list, key);
             } else {
-                rej = R::vmin(rej, d);
+                rej = R::vmin(rej, key.dist());
             }
+        }
+    };
+    auto offer = [&](T d, typename R::index_t i, bool valid) {
+        const ListKey<T> key = ListKey<T>::make(d, i);
+        const bool pass = valid && key.less(list[K - 1]);
+        if (valid && !pass) rej = R::vmin(rej, d);
+        if (pass) {
+#pragma unroll
+            for (int u = 0; u < kPark; ++u) if (u == parked) park[u] = key;
+            ++parked;
+        }
+        if (__any_sync(__activemask(), parked == kPark)) insert_round();
+    };
+    int r = 0;
+    unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
+    for (;;) {
+        if (j < e) {
+            // two candidates per step: both loads are in flight before either distance is needed
+            const bool two = j + 1 < e;
+            const Pt<T> p0 = load_pt<T>(dc.sorted + j);
+            const Pt<T> p1 = load_pt<T>(dc.sorted + (two ? j + 1 : j));
+            j += 2;
+            const T d0 = dist2<T>(q.x, q.y, q.z, p0.x, p0.y, p0.z);
+            const T d1 = dist2<T>(q.x, q.y, q.z, p1.x, p1.y, p1.z);
+            offer(d0, p0.i, true);
+            offer(d1, p1.i, two);
         } else {
             if (++r >= 9) break;
             // skip a row only if all of it is strictly farther than the current k-th distance
             if (!(rows.bound[r][tid] > list[K - 1].dist())) { j = rows.begin[r][tid]; e = rows.end[r][tid]; }
         }
     }
+    while (parked > 0) insert_round();
     const int ya = max(cy - 1, 0), yb = min(cy + 1, g.dim[1] - 1);
     const int za = max(cz - 1, 0), zb = min(cz + 1, g.dim[2] - 1);
     T lb = sq_gap<T>(q.x, __ldg(lo_x + xa));
