@@ -135,23 +135,25 @@ __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const Cloud<T>* __
         const double d2 = fmin(fmax(ceil(ext2 / hh), 1.0), (double)maxdim);
         return d0 * d1 * d2;
     };
-    // Smallest h with cells_at(h) <= cap (cells_at is non-increasing in h): three rounds of a
-    // blockDim-ary search over a geometric ladder between s_lo and s_hi.
+    // Smallest h with cells_at(h) <= cap (cells_at is non-increasing in h): two rounds of a
+    // blockDim-ary search over a geometric ladder between s_lo and s_hi (resolution of the ratio
+    // hi/lo <= 2048 after two rounds: 2048^(1/65536), i.e. h to ~0.01 %).
     if (emax > 0.0) {
-        for (int round = 0; round < 3; ++round) {
+        for (int round = 0; round < 2; ++round) {
             const double lo_h = s_lo, hi_h = s_hi;
             __syncthreads();
             if (threadIdx.x == 0) s_first = blockDim.x - 1;
             __syncthreads();
             const double frac = (double)(threadIdx.x + 1) / (double)blockDim.x;
-            const double cand = threadIdx.x + 1 == blockDim.x ? hi_h : lo_h * pow(hi_h / lo_h, frac);
+            const double cand = threadIdx.x + 1 == blockDim.x ? hi_h : lo_h * (double)exp2f((float)frac * log2f((float)(hi_h / lo_h)));
             if (cells_at(cand) <= cap) atomicMin(&s_first, (int)threadIdx.x);
             __syncthreads();
             const int first = s_first;
             __syncthreads();
             if ((int)threadIdx.x == first) {
                 s_hi = cand;
-                if (first > 0) s_lo = lo_h * pow(hi_h / lo_h, (double)first / (double)blockDim.x);
+                if (first > 0)   // the candidate just below; the ladder is monotone, a float-rounded rung is still a valid bracket
+                    s_lo = fmin(cand, lo_h * (double)exp2f((float)first / (float)blockDim.x * log2f((float)(hi_h / lo_h))) * (1.0 - 1e-6));
             }
             __syncthreads();
         }
@@ -193,10 +195,13 @@ __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const Cloud<T>* __
     __syncthreads();
     // wall tables: bisection over the ordered-integer image of the reals, using the very cell
     // function the binning kernels use, so the walls are exact by construction.
+    // only entries 0 .. dim of each axis are ever read
     const int stride = c.stride;
-    for (int t = threadIdx.x; t < 3 * stride; t += blockDim.x) {
-        const int a = t / stride, j = t - a * stride;
+    const int span = max(hdr.dim[0], max(hdr.dim[1], hdr.dim[2])) + 1;
+    for (int t = threadIdx.x; t < 3 * span; t += blockDim.x) {
+        const int a = t / span, j = t - a * span;
         const int dim = hdr.dim[a];
+        if (j > dim) continue;
         T wl, wh;
         if (j == 0) { wl = -R::inf(); wh = -R::inf(); }
         else if (j >= dim) { wl = R::inf(); wh = R::inf(); }
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const Cloud<T>* __
             wl = unordered<T>(lo_u);
             wh = unordered<T>(hi_u);
         }
-        c.wall_lo[t] = wl;
-        c.wall_hi[t] = wh;
+        c.wall_lo[a * stride + j] = wl;
+        c.wall_hi[a * stride + j] = wh;
     }
 }
 
