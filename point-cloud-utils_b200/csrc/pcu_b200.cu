@@ -410,9 +410,12 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         else              PCU_LAUNCH((knn_thread_kernel<T, 32>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
         PCU_LAUNCH((knn_warp_kernel<T, true>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((knn_descend_kernel<T, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 7, stream);
     } else {
-        PCU_LAUNCH(knn_big_kernel<T>, dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        // large k: generic path, every query descends the occupancy pyramid
+        PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH((knn_descend_kernel<T, true>), dim3(std::min<unsigned>(qblocks, 2368u), 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
         mark(ws, 6, stream);
         mark(ws, 7, stream);
     }

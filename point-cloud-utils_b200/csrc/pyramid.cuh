@@ -48,7 +48,70 @@ __device__ void build_pyramid(const Cloud<T>& dc) {
     }
 }
 
-// One thread per very-far query: depth-first descent, nearer children first.
+// Depth-first descent of the occupancy pyramid for one query, nearer children first.
+//   worst()        current k-th distance: a node is entered unless its bound is STRICTLY above it
+//   visit(a, b)    scan the sorted points [a, b) of one cell
+template <typename T, typename Worst, typename Visit>
+__device__ __forceinline__ void pyramid_descend(const GridHeader<T>& g, const PyramidShape& ps, const Cloud<T>& dc,
+                                                const Pt<T>& q, Worst&& worst, Visit&& visit) {
+    using R = Real<T>;
+    const int st = g.stride;
+    const T* lo[3] = {dc.wall_lo, dc.wall_lo + st, dc.wall_lo + 2 * st};
+    const T* hi[3] = {dc.wall_hi, dc.wall_hi + st, dc.wall_hi + 2 * st};
+    const T qv[3] = {q.x, q.y, q.z};
+    int qc3[3];
+    for (int a = 0; a < 3; ++a) qc3[a] = cell_of<T>(qv[a], g.origin[a], g.inv_h, g.dim[a]);
+    // node = level (4 bits) | x (12) | y (12) | z (12)
+    unsigned long long stack[8 * kMaxLevels + 8];
+    int top = 0;
+    stack[top++] = (unsigned long long)ps.levels << 36;
+    while (top > 0) {
+        const unsigned long long nd = stack[--top];
+        const int l = (int)(nd >> 36), x = (int)((nd >> 24) & 0xfff), y = (int)((nd >> 12) & 0xfff), z = (int)(nd & 0xfff);
+        const int c0[3] = {x << l, y << l, z << l};
+        int pref = 0;   // bit a set: the query lies towards the upper half of the node along axis a
+        T gap[3];
+        for (int a = 0; a < 3; ++a) {
+            const int c1 = min(((c0[a] >> l) + 1 << l) - 1, g.dim[a] - 1);
+            gap[a] = qc3[a] < c0[a] ? sq_gap<T>(qv[a], hi[a][c0[a]])
+                                    : (qc3[a] > c1 ? sq_gap<T>(qv[a], lo[a][c1 + 1]) : (T)0);
+            if (l > 0 && qc3[a] >= c0[a] + (1 << (l - 1))) pref |= 1 << a;
+        }
+        if (R::add(R::add(gap[0], gap[1]), gap[2]) > worst()) continue;   // everything below is strictly farther
+        if (l == 0) {
+            const unsigned lin = (unsigned)((z * g.dim[1] + y) * g.dim[0] + x);
+            visit(dc.cell_start[lin], dc.cell_start[lin + 1]);
+            continue;
+        }
+        const int cl = l - 1;
+        const int nx = ps.lvl_dim[cl][0], ny = ps.lvl_dim[cl][1], nz = ps.lvl_dim[cl][2];
+        const unsigned* lvl = dc.pyramid + ps.lvl_off[cl];
+        // children in order of increasing Hamming distance from the preferred octant; pushed in
+        // reverse so that the nearest is popped first
+        const int order[8] = {7, 6, 5, 3, 4, 2, 1, 0};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = order[j] ^ pref;
+            const int xx = 2 * x + (ch & 1), yy = 2 * y + ((ch >> 1) & 1), zz = 2 * z + ((ch >> 2) & 1);
+            if (xx >= nx || yy >= ny || zz >= nz) continue;
+            const unsigned lin = (unsigned)((zz * ny + yy) * nx + xx);
+            const unsigned count = cl == 0 ? dc.cell_start[lin + 1] - dc.cell_start[lin] : lvl[lin];
+            if (count == 0) continue;
+            stack[top++] = ((unsigned long long)cl << 36) | ((unsigned long long)xx << 24) |
+                           ((unsigned long long)yy << 12) | (unsigned long long)zz;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_shapes(const Cloud<T>& dc, GridHeader<T>& g, PyramidShape& ps) {
+    if (threadIdx.x == 0) g = *dc.grid;
+    for (int w = threadIdx.x; w < (int)(sizeof(PyramidShape) / sizeof(int)); w += blockDim.x)
+        reinterpret_cast<int*>(&ps)[w] = reinterpret_cast<const int*>(dc.shape)[w];
+    __syncthreads();
+}
+
+// k = 1: one thread per very-far query.
 // grid (sw.far_blocks, nsweeps), thread-stride loop over the very-far list.
 template <typename T, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const Cloud<T>* __restrict__ clouds,
@@ -64,64 +127,13 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const Cloud<T>* __re
     if (n_vfar > 0) {
         __shared__ GridHeader<T> g;
         __shared__ PyramidShape ps;
-        if (threadIdx.x == 0) g = *dc.grid;
-        for (int w = threadIdx.x; w < (int)(sizeof(PyramidShape) / sizeof(int)); w += blockDim.x)
-            reinterpret_cast<int*>(&ps)[w] = reinterpret_cast<const int*>(dc.shape)[w];
-        __syncthreads();
-        const int st = g.stride;
-        const T* lo[3] = {dc.wall_lo, dc.wall_lo + st, dc.wall_lo + 2 * st};
-        const T* hi[3] = {dc.wall_hi, dc.wall_hi + st, dc.wall_hi + 2 * st};
+        load_shapes<T>(dc, g, ps);
         const unsigned step = gridDim.x * blockDim.x;
         for (unsigned f = blockIdx.x * blockDim.x + threadIdx.x; f < n_vfar; f += step) {
             const Pt<T> q = load_pt<T>(qc.sorted + sw.vfar_list[f]);
-            const T qv[3] = {q.x, q.y, q.z};
-            int qc3[3];
-            for (int a = 0; a < 3; ++a) qc3[a] = cell_of<T>(qv[a], g.origin[a], g.inv_h, g.dim[a]);
             Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
-            // node = level (4 bits) | x (12) | y (12) | z (12)
-            unsigned long long stack[8 * kMaxLevels + 8];
-            int top = 0;
-            stack[top++] = (unsigned long long)ps.levels << 36;
-            while (top > 0) {
-                const unsigned long long nd = stack[--top];
-                const int l = (int)(nd >> 36), x = (int)((nd >> 24) & 0xfff), y = (int)((nd >> 12) & 0xfff), z = (int)(nd & 0xfff);
-                const int c0[3] = {x << l, y << l, z << l};
-                T bound = (T)0;
-                int pref = 0;   // bit a set: the query lies towards the upper half of the node along axis a
-                {
-                    T gap[3];
-                    for (int a = 0; a < 3; ++a) {
-                        const int c1 = min(((c0[a] >> l) + 1 << l) - 1, g.dim[a] - 1);
-                        gap[a] = qc3[a] < c0[a] ? sq_gap<T>(qv[a], hi[a][c0[a]])
-                                                : (qc3[a] > c1 ? sq_gap<T>(qv[a], lo[a][c1 + 1]) : (T)0);
-                        if (l > 0 && qc3[a] >= c0[a] + (1 << (l - 1))) pref |= 1 << a;
-                    }
-                    bound = R::add(R::add(gap[0], gap[1]), gap[2]);
-                }
-                if (bound > best.d) continue;   // everything below is strictly farther
-                if (l == 0) {
-                    const unsigned lin = (unsigned)((z * g.dim[1] + y) * g.dim[0] + x);
-                    scan_run1<T>(dc.sorted, dc.cell_start[lin], dc.cell_start[lin + 1], q.x, q.y, q.z, best);
-                    continue;
-                }
-                const int cl = l - 1;
-                const int nx = ps.lvl_dim[cl][0], ny = ps.lvl_dim[cl][1], nz = ps.lvl_dim[cl][2];
-                const unsigned* lvl = dc.pyramid + ps.lvl_off[cl];
-                // children in order of increasing Hamming distance from the preferred octant; pushed in
-                // reverse so that the nearest is popped first
-                const int order[8] = {7, 6, 5, 3, 4, 2, 1, 0};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int ch = order[j] ^ pref;
-                    const int xx = 2 * x + (ch & 1), yy = 2 * y + ((ch >> 1) & 1), zz = 2 * z + ((ch >> 2) & 1);
-                    if (xx >= nx || yy >= ny || zz >= nz) continue;
-                    const unsigned lin = (unsigned)((zz * ny + yy) * nx + xx);
-                    const unsigned count = cl == 0 ? dc.cell_start[lin + 1] - dc.cell_start[lin] : lvl[lin];
-                    if (count == 0) continue;
-                    stack[top++] = ((unsigned long long)cl << 36) | ((unsigned long long)xx << 24) |
-                                   ((unsigned long long)yy << 12) | (unsigned long long)zz;
-                }
-            }
+            pyramid_descend<T>(g, ps, dc, q, [&]() { return best.d; },
+                               [&](unsigned a, unsigned b) { scan_run1<T>(dc.sorted, a, b, q.x, q.y, q.z, best); });
             finish_query1<T, kOut, kStats>(sw, true, best, (long long)q.i, sum, sumsq, mc, ties);
         }
     }
@@ -151,6 +163,67 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const Cloud<T>* __re
                 }
             }
         }
+    }
+}
+
+// Builds the pyramid of every sweep's dataset unconditionally (k > 32 path, which descends it for
+// every query).  grid (1, nsweeps)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pyramid_build_kernel(const Cloud<T>* __restrict__ clouds,
+                                                                 const Sweep<T>* __restrict__ sweeps) {
+    const Cloud<T> dc = clouds[sweeps[blockIdx.y].dcloud];
+    build_pyramid<T>(dc);
+}
+
+// k > 1 by pyramid descent: one thread per query, the (distance, index)-sorted list lives in the caller's
+// output row (squared distances while searching).  kAll == false: the very-far list left by the ring
+// passes (k <= 32); kAll == true: every query (k > 32, generic and slow -- large k is not a hot
+// configuration).  grid (blocks, nsweeps), thread-stride loop.
+template <typename T, bool kAll>
+__global__ void __launch_bounds__(kThreads) knn_descend_kernel(const Cloud<T>* __restrict__ clouds,
+                                                               const Sweep<T>* __restrict__ sweeps) {
+    using R = Real<T>;
+    const Sweep<T> sw = sweeps[blockIdx.y];
+    const Cloud<T> qc = clouds[sw.qcloud];
+    const Cloud<T> dc = clouds[sw.dcloud];
+    const long long count = kAll ? qc.n : (long long)sw.counters[2];
+    if (count == 0) return;
+    __shared__ GridHeader<T> g;
+    __shared__ PyramidShape ps;
+    load_shapes<T>(dc, g, ps);
+    const int k = sw.k;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < count; f += step) {
+        const Pt<T> q = load_pt<T>(qc.sorted + (kAll ? f : (long long)sw.vfar_list[f]));
+        const long long row = (long long)q.i;
+        T* ld = sw.out_dist + row * k;
+        long long* li = sw.out_idx + row * k;
+        int have = 0;
+        T worst = R::inf();
+        long long worst_i = 0x7fffffffffffffffLL;
+        T rej = R::inf();
+        pyramid_descend<T>(g, ps, dc, q, [&]() { return worst; },
+            [&](unsigned a, unsigned b) {
+                for (unsigned j = a; j < b; ++j) {
+                    const Pt<T> p = load_pt<T>(dc.sorted + j);
+                    const T d = dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z);
+                    const long long pi = (long long)p.i;
+                    if (!(d < worst || (d == worst && pi < worst_i))) { rej = R::vmin(rej, d); continue; }
+                    if (have == k) rej = R::vmin(rej, ld[k - 1]);
+                    int s = have < k ? have : k - 1;
+                    while (s > 0 && (ld[s - 1] > d || (ld[s - 1] == d && li[s - 1] > pi))) {
+                        ld[s] = ld[s - 1]; li[s] = li[s - 1]; --s;
+                    }
+                    ld[s] = d; li[s] = pi;
+                    if (have < k) ++have;
+                    if (have == k) { worst = ld[k - 1]; worst_i = li[k - 1]; }
+                }
+            });
+        bool tie = have == k && rej == worst;
+        for (int s = 0; s + 1 < have; ++s) tie = tie || (ld[s] == ld[s + 1]);
+        if (!sw.squared) for (int s = 0; s < have; ++s) ld[s] = R::root(ld[s]);
+        for (int s = have; s < k; ++s) { ld[s] = (T)-1; li[s] = -1; }
+        if (tie) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
     }
 }
 

@@ -93,10 +93,12 @@ __device__ __forceinline__ void scan_run1(const Pt<T>* __restrict__ pts, unsigne
 // units), starting at ring r0.  `visit(a, b, bound)` receives a contiguous run [a, b) of sorted
 // points and a lower bound of the distance to all of them; `settled(lb)` is asked after each ring
 // with the lower bound for everything not examined so far.
+// Returns true when the search is complete (bound closed or whole grid examined), false when it
+// stopped because `max_ring` rings were not enough.
 template <typename T, typename Visit, typename Settled>
-__device__ __forceinline__ void expand_rings(const GridHeader<T>& g, const T* __restrict__ wall_lo,
+__device__ __forceinline__ bool expand_rings(const GridHeader<T>& g, const T* __restrict__ wall_lo,
                                              const T* __restrict__ wall_hi, const unsigned* __restrict__ cell_start,
-                                             T qx, T qy, T qz, int r0, Visit&& visit, Settled&& settled) {
+                                             T qx, T qy, T qz, int r0, int max_ring, Visit&& visit, Settled&& settled) {
     using R = Real<T>;
     const int cx = cell_of<T>(qx, g.origin[0], g.inv_h, g.dim[0]);
     const int cy = cell_of<T>(qy, g.origin[1], g.inv_h, g.dim[1]);
@@ -105,7 +107,7 @@ __device__ __forceinline__ void expand_rings(const GridHeader<T>& g, const T* __
     const T* lo_x = wall_lo;           const T* hi_x = wall_hi;
     const T* lo_y = wall_lo + st;      const T* hi_y = wall_hi + st;
     const T* lo_z = wall_lo + 2 * st;  const T* hi_z = wall_hi + 2 * st;
-    for (int r = r0;; ++r) {
+    for (int r = r0; r <= max_ring; ++r) {
         const int xa = max(cx - r, 0), xb = min(cx + r, g.dim[0] - 1);
         const int ya = max(cy - r, 0), yb = min(cy + r, g.dim[1] - 1);
         const int za = max(cz - r, 0), zb = min(cz + r, g.dim[2] - 1);
@@ -135,9 +137,10 @@ __device__ __forceinline__ void expand_rings(const GridHeader<T>& g, const T* __
         lb = R::vmin(lb, sq_gap<T>(qy, hi_y[yb + 1]));
         lb = R::vmin(lb, sq_gap<T>(qz, lo_z[za]));
         lb = R::vmin(lb, sq_gap<T>(qz, hi_z[zb + 1]));
-        if (settled(lb)) return;
-        if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) return;
+        if (settled(lb)) return true;
+        if (xa == 0 && ya == 0 && za == 0 && xb == g.dim[0] - 1 && yb == g.dim[1] - 1 && zb == g.dim[2] - 1) return true;
     }
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------

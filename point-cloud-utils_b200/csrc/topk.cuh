@@ -16,7 +16,7 @@ namespace pcu {
 // grid (ceil(max_n * 32 / kThreads), nsweeps).
 template <typename T>
 __device__ __forceinline__ void knn_warp_one(const Sweep<T>& sw, const Cloud<T>& qc, const Cloud<T>& dc,
-                                             const GridHeader<T>& g, long long t, int lane) {
+                                             const GridHeader<T>& g, long long t, int lane, int max_ring) {
     using R = Real<T>;
     using index_t = typename R::index_t;
     const int k = sw.k;
@@ -69,8 +69,12 @@ __device__ __forceinline__ void knn_warp_one(const Sweep<T>& sw, const Cloud<T>&
             }
         }
     };
-    expand_rings<T>(g, dc.wall_lo, dc.wall_hi, dc.cell_start, q.x, q.y, q.z, 0, visit,
-                    [&](T lb) { return worst < lb; });
+    const bool settled = expand_rings<T>(g, dc.wall_lo, dc.wall_hi, dc.cell_start, q.x, q.y, q.z, 0, max_ring, visit,
+                                         [&](T lb) { return worst < lb; });
+    if (!settled) {   // rings grow cubically with the distance to the data: the pyramid descent takes over
+        if (lane == 0) sw.vfar_list[atomicAdd(sw.counters + 2, 1u)] = (unsigned)t;
+        return;
+    }
 
     const long long row = (long long)q.i;
     if (lane < k) {
@@ -96,65 +100,30 @@ __global__ void __launch_bounds__(kThreads) knn_warp_kernel(const Cloud<T>* __re
     const int lane = threadIdx.x & 31;
     if (kFar) {
         const unsigned n_far = sw.counters[0];
-        if (n_far == 0) return;
-        const GridHeader<T> g = *dc.grid;
-        const unsigned warps_total = gridDim.x * (kThreads / 32);
-        for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total)
-            knn_warp_one<T>(sw, qc, dc, g, (long long)sw.far_list[f], lane);
+        if (n_far > 0) {
+            const GridHeader<T> g = *dc.grid;
+            const unsigned warps_total = gridDim.x * (kThreads / 32);
+            for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total)
+                knn_warp_one<T>(sw, qc, dc, g, (long long)sw.far_list[f], lane, kMaxRing);
+        }
+        // the CTA that finishes last builds the occupancy pyramid if some query is still open
+        __shared__ bool s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(sw.counters + 5, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (*(volatile unsigned*)(sw.counters + 2) > 0) build_pyramid<T>(dc);
+        }
     } else {
         const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if (t >= qc.n) return;   // warp-uniform
         const GridHeader<T> g = *dc.grid;
-        knn_warp_one<T>(sw, qc, dc, g, t, lane);
+        knn_warp_one<T>(sw, qc, dc, g, t, lane, 1 << 30);
     }
-}
-
-// k > 32: one thread per query, the (distance, index)-sorted list lives in the caller's output rows
-// (squared distances while searching).  Generic and slow; large k is not a hot configuration.
-// grid (ceil(max_n / kThreads), nsweeps).
-template <typename T>
-__global__ void __launch_bounds__(kThreads) knn_big_kernel(const Cloud<T>* __restrict__ clouds,
-                                                           const Sweep<T>* __restrict__ sweeps) {
-    using R = Real<T>;
-    const Sweep<T> sw = sweeps[blockIdx.y];
-    const Cloud<T> qc = clouds[sw.qcloud];
-    const Cloud<T> dc = clouds[sw.dcloud];
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= qc.n) return;
-    const GridHeader<T> g = *dc.grid;
-    const Pt<T> q = load_pt<T>(qc.sorted + t);
-    const int k = sw.k;
-    const long long row = (long long)q.i;
-    T* ld = sw.out_dist + row * k;
-    long long* li = sw.out_idx + row * k;
-    int have = 0;
-    T worst = R::inf();
-    long long worst_i = 0x7fffffffffffffffLL;
-    T rej = R::inf();
-    auto visit = [&](unsigned a, unsigned b, T bound) {
-        if (bound > worst) return;
-        for (unsigned j = a; j < b; ++j) {
-            const Pt<T> p = load_pt<T>(dc.sorted + j);
-            const T d = dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z);
-            const long long pi = (long long)p.i;
-            if (!(d < worst || (d == worst && pi < worst_i))) { rej = R::vmin(rej, d); continue; }
-            if (have == k) rej = R::vmin(rej, ld[k - 1]);
-            int s = have < k ? have : k - 1;
-            while (s > 0 && (ld[s - 1] > d || (ld[s - 1] == d && li[s - 1] > pi))) {
-                ld[s] = ld[s - 1]; li[s] = li[s - 1]; --s;
-            }
-            ld[s] = d; li[s] = pi;
-            if (have < k) ++have;
-            if (have == k) { worst = ld[k - 1]; worst_i = li[k - 1]; }
-        }
-    };
-    expand_rings<T>(g, dc.wall_lo, dc.wall_hi, dc.cell_start, q.x, q.y, q.z, 0, visit,
-                    [&](T lb) { return worst < lb; });
-    bool tie = have == k && rej == worst;
-    for (int s = 0; s + 1 < have; ++s) tie = tie || (ld[s] == ld[s + 1]);
-    if (!sw.squared) for (int s = 0; s < have; ++s) ld[s] = R::root(ld[s]);
-    for (int s = have; s < k; ++s) { ld[s] = (T)-1; li[s] = -1; }
-    if (tie) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
 }
 
 // ---------------------------------------------------------------------------------------------

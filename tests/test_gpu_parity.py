@@ -221,3 +221,17 @@ def test_million_point_clouds_against_oracle(pcu, oracle, k):
         ref = float(oracle.chamfer_distance(q, d))
         assert abs(float(pcu.chamfer_distance(q, d)) - ref) <= REL * ref
         assert pcu.hausdorff_distance(q, d, return_index=True) == oracle.hausdorff_distance(q, d, return_index=True)
+
+
+@pytest.mark.parametrize("k", [3, 16, 40])
+def test_topk_far_from_data(pcu, oracle, k):
+    """k > 1 with queries far from every dataset point: ring passes hand over to the pyramid descent
+    (k <= 32) or every query descends it (k > 32)."""
+    rng = np.random.default_rng(77 + k)
+    q = rng.random((3000, 3), dtype=np.float32)
+    d = (rng.random((20000, 3)) * 0.3 + np.array([5.0, -3.0, 2.0])).astype(np.float32)
+    blobs = np.concatenate([rng.normal(c, 0.003, (4000, 3)) for c in ((0.1, 0.1, 0.1), (0.9, 0.8, 0.7))]).astype(np.float32)
+    for data in (d, blobs):
+        got = pcu.k_nearest_neighbors(q, data, k)
+        ref = oracle.k_nearest_neighbors(q, data, k)
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
