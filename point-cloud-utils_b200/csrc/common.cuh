@@ -166,6 +166,19 @@ struct Cloud {
     int pad;
 };
 
+// How kernels receive the cloud descriptors: a device array (batches) or, for a single pair, by value
+// in kernel-parameter space (constant bank: no dependent global loads at the start of every CTA).
+template <typename T>
+struct CloudsPtr {
+    const Cloud<T>* p;
+    __device__ __forceinline__ const Cloud<T>& operator[](int i) const { return p[i]; }
+};
+template <typename T>
+struct CloudsVal {
+    Cloud<T> v[2];
+    __device__ __forceinline__ const Cloud<T>& operator[](int i) const { return v[i]; }
+};
+
 constexpr int kMaxBBoxBlocks = 1024;    // partial bounding boxes per cloud, upper bound
 constexpr int kBBoxPerThread = 8;       // scalars each thread folds per pass
 constexpr int kScanItems = 8;           // items per thread in the scan

@@ -16,8 +16,8 @@ constexpr int kBinPerThread = 1;   // points per thread in the histogram / scatt
 
 // ---------------------------------------------------------------------------------------------
 // 1. partial bounding boxes: grid (max bbox_blocks, nclouds)
-template <typename T>
-__global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const Cloud<T>* __restrict__ clouds) {
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_constant__ CS clouds) {
     using R = Real<T>;
     const Cloud<T> c = clouds[blockIdx.y];
     if ((int)blockIdx.x >= c.bbox_blocks) return;
@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const Cloud<T>* 
 
 // ---------------------------------------------------------------------------------------------
 // 2. grid shape + wall tables: grid (1, nclouds), kThreads threads
-template <typename T>
-__global__ void __launch_bounds__(kThreads) grid_setup_kernel(const Cloud<T>* __restrict__ clouds) {
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_constant__ CS clouds) {
     using R = Real<T>;
     using bits_t = typename R::bits_t;
     const Cloud<T> c = clouds[blockIdx.y];
@@ -231,8 +231,8 @@ __device__ __forceinline__ int linear_cell(const GridHeader<T>& g, T x, T y, T z
 
 // 3. histogram; the atomic's return value is the point's rank inside its cell.
 //    grid (ceil(max_n / kThreads), nclouds)
-template <typename T>
-__global__ void __launch_bounds__(kThreads) cell_count_kernel(const Cloud<T>* __restrict__ clouds) {
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kThreads) cell_count_kernel(const __grid_constant__ CS clouds) {
     const Cloud<T> c = clouds[blockIdx.y];
     __shared__ GridHeader<T> g;
     if (threadIdx.x == 0) g = *c.grid;
@@ -293,8 +293,8 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
 // before it.  state word = status (bits 63:62; 1 = tile total, 2 = inclusive prefix) | value (low 32).
 // Ticket and states must be zero on entry (they live in the call's zeroed region).
 // grid (tiles, nclouds)
-template <typename T>
-__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const Cloud<T>* __restrict__ clouds) {
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const __grid_constant__ CS clouds) {
     const Cloud<T> c = clouds[blockIdx.y];
     const long long count = (long long)c.cell_cap + 1;
     __shared__ unsigned s_tile, s_carry;
@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const Cloud
 
 // ---------------------------------------------------------------------------------------------
 // 5. scatter into cell order: grid (ceil(max_n / kThreads), nclouds)
-template <typename T>
-__global__ void __launch_bounds__(kThreads) scatter_kernel(const Cloud<T>* __restrict__ clouds) {
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kThreads) scatter_kernel(const __grid_constant__ CS clouds) {
     const Cloud<T> c = clouds[blockIdx.y];
     __shared__ GridHeader<T> g;
     if (threadIdx.x == 0) g = *c.grid;

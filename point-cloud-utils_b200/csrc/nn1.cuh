@@ -97,9 +97,8 @@ __device__ __forceinline__ bool warp_ring_search(const GridHeader<T>& g, const C
 //   (nn1_far_kernel below; doing them here, one warp each, cost more in registers and idle warps
 //   than the extra launch -- measured).
 // grid (ceil(max_n / kThreads), nsweeps).
-template <typename T, bool kOut, bool kStats>
-__global__ void __launch_bounds__(kThreads) nn1_kernel(const Cloud<T>* __restrict__ clouds,
-                                                       const Sweep<T>* __restrict__ sweeps) {
+template <typename T, typename CS, typename SS, bool kOut, bool kStats>
+__global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];
@@ -205,9 +204,8 @@ template <typename T> __device__ void build_pyramid(const Cloud<T>& dc);   // py
 // The CTA that finishes last builds the dataset's occupancy pyramid if that list is not empty, so the
 // pyramid pass that follows needs no launch of its own for it.
 // grid (sw.far_blocks, nsweeps), warp-stride loop over the far list.
-template <typename T, bool kOut, bool kStats>
-__global__ void __launch_bounds__(kThreads) nn1_far_kernel(const Cloud<T>* __restrict__ clouds,
-                                                           const Sweep<T>* __restrict__ sweeps) {
+template <typename T, typename CS, typename SS, bool kOut, bool kStats>
+__global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     const Sweep<T> sw = sweeps[blockIdx.y];
     const unsigned n_far = sw.counters[0];
     const Cloud<T> qc = clouds[sw.qcloud];

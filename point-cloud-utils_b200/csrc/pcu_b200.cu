@@ -62,6 +62,21 @@ int fail(int status, const char* fmt, ...) {
         PCU_CUDA(cudaGetLastError());                                  \
     } while (0)
 
+// Descriptor-taking kernels exist in two flavours: descriptors by value in parameter space (single
+// pair: `plan.by_value`) or in a device array (batches).  K<T, CloudsX<T>[, SweepsX<T>][, extra...]>.
+#define PCU_LAUNCH_C(K, grid, block)                                                                      \
+    do {                                                                                                  \
+        if (plan.by_value) PCU_LAUNCH((K<T, CloudsVal<T>>), grid, block, stream, plan.cv);                \
+        else PCU_LAUNCH((K<T, CloudsPtr<T>>), grid, block, stream, plan.cp);                              \
+    } while (0)
+#define PCU_LAUNCH_CS(K, grid, block, ...)                                                                \
+    do {                                                                                                  \
+        if (plan.by_value)                                                                                \
+            PCU_LAUNCH((K<T, CloudsVal<T>, SweepsVal<T>, ##__VA_ARGS__>), grid, block, stream, plan.cv, plan.sv); \
+        else                                                                                              \
+            PCU_LAUNCH((K<T, CloudsPtr<T>, SweepsPtr<T>, ##__VA_ARGS__>), grid, block, stream, plan.cp, plan.sp); \
+    } while (0)
+
 // Per-field byte strides between consecutive pairs of a batch (side 0 = first cloud of each pair,
 // side 1 = second cloud; direction 0 = first -> second, direction 1 = second -> first).
 struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_state, scan_ticket, pyramid, shape; };
@@ -231,6 +246,11 @@ struct Plan {
     DescriptorArgs<T> args{};
     Cloud<T>* d_clouds = nullptr;
     Sweep<T>* d_sweeps = nullptr;
+    bool by_value = false;        // single pair: descriptors travel in kernel-parameter space
+    CloudsVal<T> cv{};
+    SweepsVal<T> sv{};
+    CloudsPtr<T> cp{};
+    SweepsPtr<T> sp{};
     pcu_b200_nn_stats* d_stats = nullptr;
     unsigned char* zero_begin = nullptr;
     size_t zero_bytes = 0;
@@ -322,11 +342,28 @@ struct Plan {
         }
         if (sp.replay_points > 0) replay.carve(cv, sp.replay_points);
         total = cv.off;
+        // descriptor sources
+        this->cp.p = d_clouds;
+        this->sp.p = d_sweeps;
+        by_value = B == 1;
+        if (by_value) {
+            for (int s = 0; s < 2; ++s) this->cv.v[s] = args.cloud[s];
+            for (int d = 0; d < sp.nsweeps; ++d) {
+                Sweep<T> w = args.sweep[d];
+                w.qcloud = d; w.dcloud = 1 - d;
+                w.stats = args.stats ? args.stats + d : nullptr;
+                w.pair_stats = args.stats;
+                w.pair_ticket = args.sweep[0].counters + 4;
+                w.value_out = (sp.nsweeps == 2) ? args.value_out : nullptr;
+                this->sv.v[d] = w;
+            }
+        }
     }
 };
 
 template <typename T>
 int upload_descriptors(Plan<T>& plan, cudaStream_t stream) {
+    if (plan.by_value) return PCU_B200_OK;   // nothing to upload: descriptors ride along with every launch
     const unsigned blocks = (unsigned)((plan.args.batch + 127) / 128);
     PCU_LAUNCH(descriptors_kernel<T>, blocks, 128, stream, plan.args, plan.d_clouds, plan.d_sweeps);
     return PCU_B200_OK;
@@ -347,15 +384,15 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
     const unsigned pts_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
-    PCU_LAUNCH(bbox_partial_kernel<T>, dim3(plan.max_bbox_blocks, nclouds), kThreads, stream, plan.d_clouds);
-    PCU_LAUNCH(grid_setup_kernel<T>, dim3(1, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH_C(bbox_partial_kernel, dim3(plan.max_bbox_blocks, nclouds), kThreads);
+    PCU_LAUNCH_C(grid_setup_kernel, dim3(1, nclouds), kThreads);
     mark(ws, 2, stream);
     const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads * kBinPerThread - 1) / (kThreads * kBinPerThread));
-    PCU_LAUNCH(cell_count_kernel<T>, dim3(bin_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH_C(cell_count_kernel, dim3(bin_blocks, nclouds), kThreads);
     mark(ws, 3, stream);
-    PCU_LAUNCH(scan_lookback_kernel<T>, dim3(scan_blocks, nclouds), kScanThreads, stream, plan.d_clouds);
+    PCU_LAUNCH_C(scan_lookback_kernel, dim3(scan_blocks, nclouds), kScanThreads);
     mark(ws, 4, stream);
-    PCU_LAUNCH(scatter_kernel<T>, dim3(bin_blocks, nclouds), kThreads, stream, plan.d_clouds);
+    PCU_LAUNCH_C(scatter_kernel, dim3(bin_blocks, nclouds), kThreads);
     mark(ws, 5, stream);
     return PCU_B200_OK;
 }
@@ -397,25 +434,25 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     PCU_TRY(enqueue_binning(ws, plan, stream));
     const unsigned qblocks = (unsigned)((n + kThreads - 1) / kThreads);
     if (k == 1) {
-        PCU_LAUNCH((nn1_kernel<T, true, false>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, 1), kThreads, true, false);
         mark(ws, 6, stream);
-        PCU_LAUNCH((nn1_far_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        PCU_LAUNCH((nn1_vfar_kernel<T, true, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH_CS(nn1_far_kernel, dim3(plan.far_blocks, 1), kThreads, true, false);
+        PCU_LAUNCH_CS(nn1_vfar_kernel, dim3(plan.far_blocks, 1), kThreads, true, false);
         mark(ws, 7, stream);
     } else if (k <= 32) {
         // thread-per-query lists in registers (capacity = next power of two), warp pass for the rest
-        if (k <= 4)       PCU_LAUNCH((knn_thread_kernel<T, 4>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        else if (k <= 8)  PCU_LAUNCH((knn_thread_kernel<T, 8>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        else if (k <= 16) PCU_LAUNCH((knn_thread_kernel<T, 16>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        else              PCU_LAUNCH((knn_thread_kernel<T, 32>), dim3(qblocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        if (k <= 4)       PCU_LAUNCH_CS(knn_thread_kernel, dim3(qblocks, 1), kThreads, 4);
+        else if (k <= 8)  PCU_LAUNCH_CS(knn_thread_kernel, dim3(qblocks, 1), kThreads, 8);
+        else if (k <= 16) PCU_LAUNCH_CS(knn_thread_kernel, dim3(qblocks, 1), kThreads, 16);
+        else              PCU_LAUNCH_CS(knn_thread_kernel, dim3(qblocks, 1), kThreads, 32);
         mark(ws, 6, stream);
-        PCU_LAUNCH((knn_warp_kernel<T, true>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        PCU_LAUNCH((knn_descend_kernel<T, false>), dim3(plan.far_blocks, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH_CS(knn_warp_kernel, dim3(plan.far_blocks, 1), kThreads, true);
+        PCU_LAUNCH_CS(knn_descend_kernel, dim3(plan.far_blocks, 1), kThreads, false);
         mark(ws, 7, stream);
     } else {
         // large k: generic path, every query descends the occupancy pyramid
-        PCU_LAUNCH(pyramid_build_kernel<T>, dim3(1, 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        PCU_LAUNCH((knn_descend_kernel<T, true>), dim3(std::min<unsigned>(qblocks, 2368u), 1), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH_CS(pyramid_build_kernel, dim3(1, 1), kThreads);
+        PCU_LAUNCH_CS(knn_descend_kernel, dim3(std::min<unsigned>(qblocks, 2368u), 1), kThreads, true);
         mark(ws, 6, stream);
         mark(ws, 7, stream);
     }
@@ -455,10 +492,10 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     mark(ws, 1, stream);
     PCU_TRY(enqueue_binning(ws, plan, stream));
     const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
-    PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, ns), kThreads, false, true);
     mark(ws, 6, stream);
-    PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-    PCU_LAUNCH((nn1_vfar_kernel<T, false, true>), dim3(plan.far_blocks, ns), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+    PCU_LAUNCH_CS(nn1_far_kernel, dim3(plan.far_blocks, ns), kThreads, false, true);
+    PCU_LAUNCH_CS(nn1_vfar_kernel, dim3(plan.far_blocks, ns), kThreads, false, true);
     mark(ws, 7, stream);
     mark(ws, 8, stream);
     return PCU_B200_OK;
@@ -512,10 +549,10 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         mark(ws, 1, stream);
         PCU_TRY(enqueue_binning(ws, plan, stream));
         const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
-        PCU_LAUNCH((nn1_kernel<T, false, true>), dim3(qblocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, plan.nsweeps_total), kThreads, false, true);
         mark(ws, 6, stream);
-        PCU_LAUNCH((nn1_far_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
-        PCU_LAUNCH((nn1_vfar_kernel<T, false, true>), dim3(plan.far_blocks, plan.nsweeps_total), kThreads, stream, plan.d_clouds, plan.d_sweeps);
+        PCU_LAUNCH_CS(nn1_far_kernel, dim3(plan.far_blocks, plan.nsweeps_total), kThreads, false, true);
+        PCU_LAUNCH_CS(nn1_vfar_kernel, dim3(plan.far_blocks, plan.nsweeps_total), kThreads, false, true);
         mark(ws, 7, stream);
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,
                    out_per_pair ? out_per_pair + first : (T*)nullptr, out_sum);

@@ -113,9 +113,8 @@ __device__ __forceinline__ void load_shapes(const Cloud<T>& dc, GridHeader<T>& g
 
 // k = 1: one thread per very-far query.
 // grid (sw.far_blocks, nsweeps), thread-stride loop over the very-far list.
-template <typename T, bool kOut, bool kStats>
-__global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const Cloud<T>* __restrict__ clouds,
-                                                            const Sweep<T>* __restrict__ sweeps) {
+template <typename T, typename CS, typename SS, bool kOut, bool kStats>
+__global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const unsigned n_vfar = sw.counters[2];
@@ -168,9 +167,8 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const Cloud<T>* __re
 
 // Builds the pyramid of every sweep's dataset unconditionally (k > 32 path, which descends it for
 // every query).  grid (1, nsweeps)
-template <typename T>
-__global__ void __launch_bounds__(kThreads) pyramid_build_kernel(const Cloud<T>* __restrict__ clouds,
-                                                                 const Sweep<T>* __restrict__ sweeps) {
+template <typename T, typename CS, typename SS>
+__global__ void __launch_bounds__(kThreads) pyramid_build_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     const Cloud<T> dc = clouds[sweeps[blockIdx.y].dcloud];
     build_pyramid<T>(dc);
 }
@@ -179,9 +177,8 @@ __global__ void __launch_bounds__(kThreads) pyramid_build_kernel(const Cloud<T>*
 // output row (squared distances while searching).  kAll == false: the very-far list left by the ring
 // passes (k <= 32); kAll == true: every query (k > 32, generic and slow -- large k is not a hot
 // configuration).  grid (blocks, nsweeps), thread-stride loop.
-template <typename T, bool kAll>
-__global__ void __launch_bounds__(kThreads) knn_descend_kernel(const Cloud<T>* __restrict__ clouds,
-                                                               const Sweep<T>* __restrict__ sweeps) {
+template <typename T, typename CS, typename SS, bool kAll>
+__global__ void __launch_bounds__(kThreads) knn_descend_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];

@@ -51,6 +51,17 @@ struct Sweep {
 };
 
 template <typename T>
+struct SweepsPtr {
+    const Sweep<T>* p;
+    __device__ __forceinline__ const Sweep<T>& operator[](int i) const { return p[i]; }
+};
+template <typename T>
+struct SweepsVal {
+    Sweep<T> v[2];
+    __device__ __forceinline__ const Sweep<T>& operator[](int i) const { return v[i]; }
+};
+
+template <typename T>
 struct Best1 {
     T d;
     typename Real<T>::index_t i;
