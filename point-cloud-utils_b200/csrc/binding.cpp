@@ -37,9 +37,12 @@ namespace {
 }
 inline void check(int status) { if (status != PCU_B200_OK) raise_status(status); }
 
-// One workspace per (device, stream): a workspace serves one stream at a time.
+// One workspace per (device, stream): a workspace serves one stream at a time.  Calls that share a
+// workspace (several Python threads on the same stream) are serialised by `busy`: enqueueing is what
+// must not interleave, the work itself is ordered by the stream.
 struct Pool {
     std::mutex mu;
+    std::mutex busy;
     std::map<std::pair<int, uintptr_t>, pcu_b200_workspace*> items;
     pcu_b200_workspace* get(int device, uintptr_t stream) {
         std::lock_guard<std::mutex> lock(mu);
@@ -58,17 +61,25 @@ struct Pool {
     }
 };
 Pool& pool() { static Pool p; return p; }
+// Released GIL + exclusive use of the native library for the duration of one call.
+struct CallScope {
+    py::gil_scoped_release nogil;
+    std::lock_guard<std::mutex> lock;
+    CallScope() : nogil(), lock(pool().busy) {}
+};
 
 struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; };
 Options& defaults() { static Options o; return o; }
 
-void apply_options(pcu_b200_workspace* ws, int max_points_per_leaf) {
+// Validates the per-call options (with the GIL held); they are applied to the workspace inside the
+// call's exclusive section so that concurrent callers cannot mix them up.
+pcu_b200_options make_options(int max_points_per_leaf) {
     if (max_points_per_leaf <= 0) throw py::value_error("max_points_per_leaf must be greater than 0.");
     pcu_b200_options o{};
     o.max_points_per_leaf = max_points_per_leaf;
     o.cell_occupancy = defaults().occupancy;
     o.disable_tie_replay = defaults().disable_replay;
-    check(pcu_b200_workspace_set_options(ws, &o));
+    return o;
 }
 
 enum class Dt { f32, f64 };
@@ -136,11 +147,12 @@ py::tuple knn_numpy(const py::array& q_in, const py::array& d_in, int k, bool sq
     py::array_t<T> dists({(py::ssize_t)n, (py::ssize_t)k});
     py::array_t<int64_t> corrs({(py::ssize_t)n, (py::ssize_t)k});
     pcu_b200_workspace* ws = pool().get(device, 0);
-    apply_options(ws, leaf);
+    const pcu_b200_options opts = make_options(leaf);
     int status;
     int64_t tied = 0;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         if (sizeof(T) == 4)
             status = pcu_b200_knn_host_f32(ws, (const float*)q.data(), n, (const float*)d.data(), m, k, squared,
                                            (float*)dists.mutable_data(), corrs.mutable_data(), &tied);
@@ -184,11 +196,12 @@ pcu_b200_nn_stats one_sided_numpy(const py::array& s_in, const py::array& t_in, 
     auto s = dense<T>(s_in);
     auto t = dense<T>(t_in);
     pcu_b200_workspace* ws = pool().get(device, 0);
-    apply_options(ws, leaf);
+    const pcu_b200_options opts = make_options(leaf);
     pcu_b200_nn_stats st{};
     int status;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         if (sizeof(T) == 4)
             status = pcu_b200_nn_stats_host_f32(ws, (const float*)s.data(), s.shape(0), (const float*)t.data(), t.shape(0), &st);
         else
@@ -223,7 +236,7 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
     check_shapes(x_in, y_in, "x", "y");
     const int dev = current_device_or_default(device);
     pcu_b200_workspace* ws = pool().get(dev, 0);
-    apply_options(ws, max_points_per_leaf);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
     pcu_b200_nn_stats st[2] = {};
     int status;
     py::object value;
@@ -231,7 +244,7 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
         auto x = dense<float>(x_in);
         auto y = dense<float>(y_in);
         float v = 0.f;
-        { py::gil_scoped_release nogil;
+        { CallScope scope; pcu_b200_workspace_set_options(ws, &opts);
           status = pcu_b200_chamfer_host_f32(ws, x.data(), x.shape(0), y.data(), y.shape(0), st, &v); }
         check(status);
         value = py::module_::import("numpy").attr("float32")(v);
@@ -239,7 +252,7 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
         auto x = dense<double>(x_in);
         auto y = dense<double>(y_in);
         double v = 0.0;
-        { py::gil_scoped_release nogil;
+        { CallScope scope; pcu_b200_workspace_set_options(ws, &opts);
           status = pcu_b200_chamfer_host_f64(ws, x.data(), x.shape(0), y.data(), y.shape(0), st, &v); }
         check(status);
         value = py::module_::import("numpy").attr("float64")(v);
@@ -253,10 +266,11 @@ void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int6
                 uintptr_t stream) {
     if (k <= 0) throw py::value_error("Invalid value for k (" + std::to_string(k) + ") must be greater than 0.");
     pcu_b200_workspace* ws = pool().get(device, stream);
-    apply_options(ws, max_points_per_leaf);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         status = is_f64 ? pcu_b200_knn_f64(ws, (const double*)query, n, (const double*)dataset, m, k, squared,
                                            (double*)out_dist, (int64_t*)out_idx, (int64_t*)out_n_tied, (void*)stream)
                         : pcu_b200_knn_f32(ws, (const float*)query, n, (const float*)dataset, m, k, squared,
@@ -268,10 +282,11 @@ void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int6
 void stats_device(bool is_f64, bool both, uintptr_t a, int64_t n, uintptr_t b, int64_t m, uintptr_t out_stats,
                   uintptr_t out_value, int max_points_per_leaf, int device, uintptr_t stream) {
     pcu_b200_workspace* ws = pool().get(device, stream);
-    apply_options(ws, max_points_per_leaf);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         auto* st = (pcu_b200_nn_stats*)out_stats;
         if (both)
             status = is_f64 ? pcu_b200_chamfer_f64(ws, (const double*)a, n, (const double*)b, m, st, (double*)out_value, (void*)stream)
@@ -298,10 +313,11 @@ py::tuple batched_chamfer_numpy(const py::array& x_in, const py::array& y_in, in
     double sum = 0.0;
     const int dev = current_device_or_default(device);
     pcu_b200_workspace* ws = pool().get(dev, 0);
-    apply_options(ws, max_points_per_leaf);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         status = pcu_b200_batched_chamfer_host_f32(ws, x.data(), y.data(), B, n, m, out.mutable_data(),
                                                    B <= 16384 ? &sum : nullptr);
     }
@@ -312,10 +328,11 @@ py::tuple batched_chamfer_numpy(const py::array& x_in, const py::array& y_in, in
 void batched_chamfer_device(uintptr_t x, uintptr_t y, int64_t B, int64_t n, int64_t m, uintptr_t out_per_pair,
                             uintptr_t out_sum, int max_points_per_leaf, int device, uintptr_t stream) {
     pcu_b200_workspace* ws = pool().get(device, stream);
-    apply_options(ws, max_points_per_leaf);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         status = pcu_b200_batched_chamfer_f32(ws, (const float*)x, (const float*)y, B, n, m, (float*)out_per_pair,
                                               (double*)out_sum, (void*)stream);
     }
@@ -360,10 +377,11 @@ py::dict debug_kd_tree(const py::array& pts, int leaf, int device) {
 void resolve_witness_device(bool is_f64, uintptr_t q, int64_t n, uintptr_t d, int64_t m, uintptr_t stats,
                             int max_points_per_leaf, int device, uintptr_t stream) {
     pcu_b200_workspace* ws = pool().get(device, stream);
-    apply_options(ws, max_points_per_leaf);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        py::gil_scoped_release nogil;
+        CallScope scope;
+        pcu_b200_workspace_set_options(ws, &opts);
         status = is_f64 ? pcu_b200_resolve_witness_f64(ws, (const double*)q, n, (const double*)d, m,
                                                        (pcu_b200_nn_stats*)stats, (void*)stream)
                         : pcu_b200_resolve_witness_f32(ws, (const float*)q, n, (const float*)d, m,

@@ -235,3 +235,26 @@ def test_topk_far_from_data(pcu, oracle, k):
         got = pcu.k_nearest_neighbors(q, data, k)
         ref = oracle.k_nearest_neighbors(q, data, k)
         assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+
+
+def test_concurrent_python_threads(pcu, oracle):
+    """Several Python threads calling at once (the GIL is released inside the native call): results are
+    the same as serial calls."""
+    import threading
+    rng = np.random.default_rng(99)
+    clouds = [(rng.random((20000 + 1000 * i, 3), dtype=np.float32), rng.random((15000, 3), dtype=np.float32))
+              for i in range(6)]
+    expect = [oracle.k_nearest_neighbors(a, b, 3, max_points_per_leaf=10 + i) for i, (a, b) in enumerate(clouds)]
+    got = [None] * len(clouds)
+
+    def work(i):
+        a, b = clouds[i]
+        got[i] = pcu.k_nearest_neighbors(a, b, 3, max_points_per_leaf=10 + i)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(clouds))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for g, e in zip(got, expect):
+        assert np.array_equal(g[1], e[1]) and np.array_equal(g[0], e[0])
