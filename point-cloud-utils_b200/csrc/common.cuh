@@ -17,6 +17,12 @@ constexpr int kMaxGridDim = 2048;   // cells per axis, upper bound
 constexpr int kThreads = 256;       // default CTA size of the streaming kernels
 constexpr int kMaxLevels = 12;      // 2^11 = kMaxGridDim, plus one
 
+// Programmatic dependent launch: every kernel of a call's chain is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs may be scheduled while the previous
+// kernel drains; this wait (first statement of every kernel) blocks until that kernel has completed
+// and its writes are visible.  A no-op for ordinary launches.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <typename T> struct Real;
 
 template <> struct Real<float> {

@@ -18,6 +18,7 @@ constexpr int kBinPerThread = 1;   // points per thread in the histogram / scatt
 // 1. partial bounding boxes: grid (max bbox_blocks, nclouds)
 template <typename T, typename CS>
 __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
     using R = Real<T>;
     const Cloud<T> c = clouds[blockIdx.y];
     if ((int)blockIdx.x >= c.bbox_blocks) return;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_con
 // 2. grid shape + wall tables: grid (1, nclouds), kThreads threads
 template <typename T, typename CS>
 __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
     using R = Real<T>;
     using bits_t = typename R::bits_t;
     const Cloud<T> c = clouds[blockIdx.y];
@@ -233,6 +235,7 @@ __device__ __forceinline__ int linear_cell(const GridHeader<T>& g, T x, T y, T z
 //    grid (ceil(max_n / kThreads), nclouds)
 template <typename T, typename CS>
 __global__ void __launch_bounds__(kThreads) cell_count_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
     const Cloud<T> c = clouds[blockIdx.y];
     __shared__ GridHeader<T> g;
     if (threadIdx.x == 0) g = *c.grid;
@@ -295,6 +298,7 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* t
 // grid (tiles, nclouds)
 template <typename T, typename CS>
 __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
     const Cloud<T> c = clouds[blockIdx.y];
     const long long count = (long long)c.cell_cap + 1;
     __shared__ unsigned s_tile, s_carry;
@@ -347,6 +351,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const __gri
 // 5. scatter into cell order: grid (ceil(max_n / kThreads), nclouds)
 template <typename T, typename CS>
 __global__ void __launch_bounds__(kThreads) scatter_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
     const Cloud<T> c = clouds[blockIdx.y];
     __shared__ GridHeader<T> g;
     if (threadIdx.x == 0) g = *c.grid;

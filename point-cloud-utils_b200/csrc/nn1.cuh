@@ -99,6 +99,7 @@ __device__ __forceinline__ bool warp_ring_search(const GridHeader<T>& g, const C
 // grid (ceil(max_n / kThreads), nsweeps).
 template <typename T, typename CS, typename SS, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];
@@ -206,6 +207,7 @@ template <typename T> __device__ void build_pyramid(const Cloud<T>& dc);   // py
 // grid (sw.far_blocks, nsweeps), warp-stride loop over the far list.
 template <typename T, typename CS, typename SS, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     const Sweep<T> sw = sweeps[blockIdx.y];
     const unsigned n_far = sw.counters[0];
     const Cloud<T> qc = clouds[sw.qcloud];

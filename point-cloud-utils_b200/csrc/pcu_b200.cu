@@ -62,19 +62,36 @@ int fail(int status, const char* fmt, ...) {
         PCU_CUDA(cudaGetLastError());                                  \
     } while (0)
 
+// Launch with programmatic stream serialisation: the kernel (which starts with grid_dependency_wait())
+// may have its CTAs scheduled while its predecessor in the stream is still draining.
+#define PCU_LAUNCH_PDL(kernel, grid, block, stream, ...)                                       \
+    do {                                                                                       \
+        cudaLaunchConfig_t cfg__ = {};                                                         \
+        cfg__.gridDim = dim3(grid);                                                            \
+        cfg__.blockDim = dim3(block);                                                          \
+        cfg__.stream = stream;                                                                 \
+        cudaLaunchAttribute attr__[1];                                                         \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
+        attr__[0].val.programmaticStreamSerializationAllowed = 1;                              \
+        cfg__.attrs = attr__;                                                                  \
+        cfg__.numAttrs = 1;                                                                    \
+        PCU_CUDA(cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__));                             \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    } while (0)
+
 // Descriptor-taking kernels exist in two flavours: descriptors by value in parameter space (single
 // pair: `plan.by_value`) or in a device array (batches).  K<T, CloudsX<T>[, SweepsX<T>][, extra...]>.
 #define PCU_LAUNCH_C(K, grid, block)                                                                      \
     do {                                                                                                  \
-        if (plan.by_value) PCU_LAUNCH((K<T, CloudsVal<T>>), grid, block, stream, plan.cv);                \
-        else PCU_LAUNCH((K<T, CloudsPtr<T>>), grid, block, stream, plan.cp);                              \
+        if (plan.by_value) PCU_LAUNCH_PDL((K<T, CloudsVal<T>>), grid, block, stream, plan.cv);            \
+        else PCU_LAUNCH_PDL((K<T, CloudsPtr<T>>), grid, block, stream, plan.cp);                          \
     } while (0)
 #define PCU_LAUNCH_CS(K, grid, block, ...)                                                                \
     do {                                                                                                  \
         if (plan.by_value)                                                                                \
-            PCU_LAUNCH((K<T, CloudsVal<T>, SweepsVal<T>, ##__VA_ARGS__>), grid, block, stream, plan.cv, plan.sv); \
+            PCU_LAUNCH_PDL((K<T, CloudsVal<T>, SweepsVal<T>, ##__VA_ARGS__>), grid, block, stream, plan.cv, plan.sv); \
         else                                                                                              \
-            PCU_LAUNCH((K<T, CloudsPtr<T>, SweepsPtr<T>, ##__VA_ARGS__>), grid, block, stream, plan.cp, plan.sp); \
+            PCU_LAUNCH_PDL((K<T, CloudsPtr<T>, SweepsPtr<T>, ##__VA_ARGS__>), grid, block, stream, plan.cp, plan.sp); \
     } while (0)
 
 // Per-field byte strides between consecutive pairs of a batch (side 0 = first cloud of each pair,

@@ -115,6 +115,7 @@ __device__ __forceinline__ void load_shapes(const Cloud<T>& dc, GridHeader<T>& g
 // grid (sw.far_blocks, nsweeps), thread-stride loop over the very-far list.
 template <typename T, typename CS, typename SS, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const unsigned n_vfar = sw.counters[2];
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
 // every query).  grid (1, nsweeps)
 template <typename T, typename CS, typename SS>
 __global__ void __launch_bounds__(kThreads) pyramid_build_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     const Cloud<T> dc = clouds[sweeps[blockIdx.y].dcloud];
     build_pyramid<T>(dc);
 }
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) pyramid_build_kernel(const __grid_co
 // configuration).  grid (blocks, nsweeps), thread-stride loop.
 template <typename T, typename CS, typename SS, bool kAll>
 __global__ void __launch_bounds__(kThreads) knn_descend_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];

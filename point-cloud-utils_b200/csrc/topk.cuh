@@ -93,6 +93,7 @@ __device__ __forceinline__ void knn_warp_one(const Sweep<T>& sw, const Cloud<T>&
 // kFar == true : warp-stride loop over the far list left by knn_thread_kernel.   grid (far_blocks, nsweeps)
 template <typename T, typename CS, typename SS, bool kFar>
 __global__ void __launch_bounds__(kThreads) knn_warp_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];
     const Cloud<T> dc = clouds[sw.dcloud];
@@ -174,6 +175,7 @@ __device__ __forceinline__ void list_insert(ListKey<T> (&a)[K], const ListKey<T>
 // grid (ceil(max_n / kThreads), nsweeps)
 template <typename T, typename CS, typename SS, int K>
 __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+    grid_dependency_wait();
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];
