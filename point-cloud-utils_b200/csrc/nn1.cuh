@@ -151,20 +151,18 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
         int r = 0;
         unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
         for (;;) {
-            // Every trip first steps past exhausted / pruned rows (at most two, predicated) and THEN
-            // evaluates candidates, so the lanes of a warp stay in the same instruction stream: a lane
-            // that has just changed rows does not force a separate pass over the candidate code for
-            // the lanes that have not (ncu showed 8 of 32 lanes active there before).
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (j >= e && r < 8) {
-                    ++r;
-                    // a row whose bound exceeds the current best only holds strictly farther points
-                    const bool keep = !(rows.bound[r][tid] > best.d);
-                    const unsigned nb = rows.begin[r][tid], ne = rows.end[r][tid];
-                    j = keep ? nb : 0u;
-                    e = keep ? ne : 0u;
-                }
+            // Every trip first steps to the next row if the current run is exhausted (predicated; a pruned
+            // row leaves the lane idle for this trip) and THEN evaluates candidates, so the lanes of a
+            // warp stay in one instruction stream: a lane that has just changed rows does not force a
+            // separate pass over the candidate code for the lanes that have not (ncu had shown 8 of 32
+            // lanes active there).  One step per trip measured faster than two (158 vs 170 us).
+            if (j >= e && r < 8) {
+                ++r;
+                // a row whose bound exceeds the current best only holds strictly farther points
+                const bool keep = !(rows.bound[r][tid] > best.d);
+                const unsigned nb = rows.begin[r][tid], ne = rows.end[r][tid];
+                j = keep ? nb : 0u;
+                e = keep ? ne : 0u;
             }
             const bool has = j < e;
             if (!has && r >= 8) break;
