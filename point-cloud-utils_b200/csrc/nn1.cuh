@@ -239,37 +239,29 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
     }
 }
 
-// Combines the per-block partials of one sweep into its pcu_b200_nn_stats (called by ONE CTA).
+// Reads one per-block partial written by another CTA (possibly in this very launch): around L1.
+template <typename T>
+__device__ __forceinline__ SweepPartial<T> load_partial(const SweepPartial<T>* src) {
+    SweepPartial<T> p;
+    p.sum = __ldcg(&src->sum); p.sumsq = __ldcg(&src->sumsq); p.max_d2 = __ldcg(&src->max_d2);
+    p.arg_q = __ldcg(&src->arg_q); p.arg_d = __ldcg(&src->arg_d);
+    p.n_tied = __ldcg(&src->n_tied); p.tie_at_max = __ldcg(&src->tie_at_max);
+    return p;
+}
+
+// Combines the partials of the two slow passes (the pyramid pass has already folded the main pass's
+// partials into its own) into the sweep's pcu_b200_nn_stats.  Called by ONE CTA.
 template <typename T>
 __device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, long long n) {
-    const int main_used = (int)((n + kThreads - 1) / kThreads);
-    const int total = main_used + 2 * sw.far_blocks;   // main pass | far pass | pyramid pass
+    const int total = 2 * sw.far_blocks;   // far pass | pyramid pass (which carries the main pass)
     double sum = 0.0, sumsq = 0.0;
     unsigned ties = 0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
-    constexpr int kBatch = 4;   // independent loads in flight per thread
-    for (int s0 = threadIdx.x; s0 < total; s0 += blockDim.x * kBatch) {
-        SweepPartial<T> p[kBatch];
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int s = s0 + u * blockDim.x;
-            if (s < total) {
-                // written by other CTAs (some of them in this very launch): read around L1
-                const SweepPartial<T>* src = sw.partial + (s < main_used ? s : sw.main_blocks + (s - main_used));
-                p[u].sum = __ldcg(&src->sum); p[u].sumsq = __ldcg(&src->sumsq); p[u].max_d2 = __ldcg(&src->max_d2);
-                p[u].arg_q = __ldcg(&src->arg_q); p[u].arg_d = __ldcg(&src->arg_d);
-                p[u].n_tied = __ldcg(&src->n_tied); p[u].tie_at_max = __ldcg(&src->tie_at_max);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-            const int s = s0 + u * blockDim.x;
-            if (s < total) {
-                sum += p[u].sum; sumsq += p[u].sumsq; ties += p[u].n_tied;
-                MaxCand<T> c; c.d2 = p[u].max_d2; c.q = p[u].arg_q; c.d = p[u].arg_d; c.tie = p[u].tie_at_max;
-                take_max<T>(mc, c);
-            }
-        }
+    for (int s = threadIdx.x; s < total; s += blockDim.x) {
+        const SweepPartial<T> p = load_partial<T>(sw.partial + sw.main_blocks + s);
+        sum += p.sum; sumsq += p.sumsq; ties += p.n_tied;
+        MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.d = p.arg_d; c.tie = p.tie_at_max;
+        take_max<T>(mc, c);
     }
     __shared__ SweepPartial<T> result;
     block_reduce_stats<T>(sum, sumsq, mc, ties, &result);

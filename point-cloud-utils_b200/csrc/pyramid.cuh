@@ -138,6 +138,16 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
         }
     }
     if (kStats) {
+        // every CTA of this pass first folds its share of the main pass's per-block partials (slot s
+        // belongs to CTA s mod gridDim) into its own accumulators, so the CTA that finishes last only
+        // has the 2 * far_blocks partials of the slow passes left to combine
+        const int main_used = (int)((qc.n + kThreads - 1) / kThreads);
+        for (int s = blockIdx.x + threadIdx.x * gridDim.x; s < main_used; s += gridDim.x * blockDim.x) {
+            const SweepPartial<T> p = load_partial<T>(sw.partial + s);
+            sum += p.sum; sumsq += p.sumsq; ties += p.n_tied;
+            MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.d = p.arg_d; c.tie = p.tie_at_max;
+            take_max<T>(mc, c);
+        }
         block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + sw.far_blocks + blockIdx.x);
         // The CTA that finishes last folds all partials of this sweep (main pass + this pass) into the
         // caller's statistics record; for a bidirectional call the sweep that finishes second also
