@@ -174,8 +174,12 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
                 j += 2;
                 const T d0 = dist2<T>(q.x, q.y, q.z, p0.x, p0.y, p0.z);
                 const T d1 = dist2<T>(q.x, q.y, q.z, p1.x, p1.y, p1.z);
-                offer1_select<T>(best, d0, p0.i, true);
-                offer1_select<T>(best, d1, p1.i, two);
+                if constexpr (kOut) {
+                    offer1_select<T>(best, d0, p0.i, true);
+                    offer1_select<T>(best, d1, p1.i, two);
+                } else {   // statistics only: the minimum distance is all the scalar metrics need
+                    best.d = R::vmin(best.d, R::vmin(d0, two ? d1 : d0));
+                }
             }
         }
         const int ya = max(cy - 1, 0), yb = min(cy + 1, g.dim[1] - 1);
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
     double sum = 0.0, sumsq = 0.0;
     unsigned ties = 0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
-    finish_query1<T, kOut, kStats>(sw, active && settled, best, row, sum, sumsq, mc, ties);
+    finish_query1<T, kOut, kStats>(sw, active && settled, best, row, (unsigned)t, sum, sumsq, mc, ties);
     if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + blockIdx.x);
 }
 
@@ -223,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
             Best1<T> best;
             const bool ok = warp_ring_search<T>(g, dc, q, lane, best);
             if (!ok && lane == 0) sw.vfar_list[atomicAdd(sw.counters + 2, 1u)] = qt;
-            finish_query1<T, kOut, kStats>(sw, ok && lane == 0, best, (long long)q.i, sum, sumsq, mc, ties);
+            finish_query1<T, kOut, kStats>(sw, ok && lane == 0, best, (long long)q.i, qt, sum, sumsq, mc, ties);
         }
     }
     if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + blockIdx.x);
@@ -252,7 +256,7 @@ __device__ __forceinline__ SweepPartial<T> load_partial(const SweepPartial<T>* s
 // Combines the partials of the two slow passes (the pyramid pass has already folded the main pass's
 // partials into its own) into the sweep's pcu_b200_nn_stats.  Called by ONE CTA.
 template <typename T>
-__device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, long long n) {
+__device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, SweepPartial<T>* result /* shared */) {
     const int total = 2 * sw.far_blocks;   // far pass | pyramid pass (which carries the main pass)
     double sum = 0.0, sumsq = 0.0;
     unsigned ties = 0;
@@ -263,22 +267,8 @@ __device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, long long n) 
         MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.d = p.arg_d; c.tie = p.tie_at_max;
         take_max<T>(mc, c);
     }
-    __shared__ SweepPartial<T> result;
-    block_reduce_stats<T>(sum, sumsq, mc, ties, &result);
+    block_reduce_stats<T>(sum, sumsq, mc, ties, result);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        pcu_b200_nn_stats s;
-        s.sum_dist = result.sum;
-        s.sum_sq_dist = result.sumsq;
-        s.max_sq_dist = (double)result.max_d2;
-        s.argmax_query = result.arg_q;
-        s.argmax_data = result.arg_d;
-        s.n_queries = n;
-        s.n_tied = result.n_tied;
-        s.n_far = (long long)sw.counters[0];   // includes the very far ones (counters[2])
-        s.witness_tied = result.tie_at_max ? 1 : 0;
-        *sw.stats = s;
-    }
 }
 
 // chamfer = mean_x |x - NN_y(x)| + mean_y |y - NN_x(y)|  (point_cloud_utils/__init__.py:112-115)

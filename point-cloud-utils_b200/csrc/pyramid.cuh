@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
             Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
             pyramid_descend<T>(g, ps, dc, q, [&]() { return best.d; },
                                [&](unsigned a, unsigned b) { scan_run1<T>(dc.sorted, a, b, q.x, q.y, q.z, best); });
-            finish_query1<T, kOut, kStats>(sw, true, best, (long long)q.i, sum, sumsq, mc, ties);
+            finish_query1<T, kOut, kStats>(sw, true, best, (long long)q.i, sw.vfar_list[f], sum, sumsq, mc, ties);
         }
     }
     if (kStats) {
@@ -160,7 +160,42 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
         __syncthreads();
         if (s_last) {
             __threadfence();
-            finalize_sweep<T>(sw, qc.n);
+            __shared__ SweepPartial<T> result;
+            finalize_sweep<T>(sw, &result);
+            // Hausdorff witness: the neighbour of the one query that attains the maximum (and whether it
+            // was decided by tie order) -- a single warp repeats that query's search with full bookkeeping
+            __shared__ GridHeader<T> wg;
+            __shared__ PyramidShape wps;
+            if (threadIdx.x == 0) wg = *dc.grid;
+            __syncthreads();
+            if (threadIdx.x < 32 && result.max_d2 >= (T)0) {
+                const Pt<T> wq = load_pt<T>(qc.sorted + (unsigned)result.arg_d);
+                Best1<T> wb; wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
+                const bool ok = warp_ring_search<T>(wg, dc, wq, threadIdx.x, wb);
+                if (!ok) {   // beyond the rings: the pyramid exists (this query was on the very-far list)
+                    wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
+                    for (int w = threadIdx.x; w < (int)(sizeof(PyramidShape) / sizeof(int)); w += 32)
+                        reinterpret_cast<int*>(&wps)[w] = reinterpret_cast<const int*>(dc.shape)[w];
+                    __syncwarp();
+                    if (threadIdx.x == 0)
+                        pyramid_descend<T>(wg, wps, dc, wq, [&]() { return wb.d; },
+                                           [&](unsigned a, unsigned b) { scan_run1<T>(dc.sorted, a, b, wq.x, wq.y, wq.z, wb); });
+                }
+                if (threadIdx.x == 0) {
+                    pcu_b200_nn_stats st;
+                    st.sum_dist = result.sum;
+                    st.sum_sq_dist = result.sumsq;
+                    st.max_sq_dist = (double)result.max_d2;
+                    st.argmax_query = result.arg_q;
+                    st.argmax_data = wb.i != no_index<T>() ? (long long)wb.i : -1;
+                    st.n_queries = qc.n;
+                    st.n_tied = -1;   // not tracked by the statistics-only sweep
+                    st.n_far = (long long)sw.counters[0];
+                    st.witness_tied = wb.tie ? 1 : 0;
+                    *sw.stats = st;
+                }
+            }
+            __syncthreads();
             if (sw.value_out != nullptr && threadIdx.x == 0) {
                 __threadfence();
                 if (atomicAdd(sw.pair_ticket, 1u) == 1u) {

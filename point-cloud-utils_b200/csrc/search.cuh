@@ -231,25 +231,29 @@ __device__ __forceinline__ void block_reduce_stats(double sum, double sumsq, Max
     }
 }
 
+// kOut: write the query's neighbour to the caller's arrays.  kStats: fold its distance into the fused
+// statistics.  In the statistics-only sweeps the hot loop tracks the minimum distance and nothing else:
+// the only index the scalar metrics ever need is the neighbour of the ONE query that attains the
+// Hausdorff maximum, and that is recovered afterwards (resolve_witness, nn1.cuh), so MaxCand::d
+// carries the query's position in cell order there, not a neighbour index.
 template <typename T, bool kOut, bool kStats>
 __device__ __forceinline__ void finish_query1(const Sweep<T>& sw, bool have, const Best1<T>& best, long long row,
-                                              double& sum, double& sumsq, MaxCand<T>& mc, unsigned& ties) {
+                                              unsigned pos, double& sum, double& sumsq, MaxCand<T>& mc,
+                                              unsigned& ties) {
     using R = Real<T>;
     if (!have) return;
-    const bool found = best.i != no_index<T>();
-    const long long di = found ? (long long)best.i : -1;
     const T root = R::root(best.d);
     if (kOut) {
-        sw.out_idx[row] = di;
+        const bool found = best.i != no_index<T>();
+        sw.out_idx[row] = found ? (long long)best.i : -1;
         sw.out_dist[row] = found ? (sw.squared ? best.d : root) : (T)-1;
         if (best.tie) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
     }
     if (kStats) {
         sum += (double)root;
         sumsq += (double)best.d;
-        MaxCand<T> c; c.d2 = best.d; c.q = row; c.d = di; c.tie = best.tie ? 1u : 0u;
+        MaxCand<T> c; c.d2 = best.d; c.q = row; c.d = (long long)pos; c.tie = 0u;
         take_max<T>(mc, c);
-        ties += best.tie ? 1u : 0u;
     }
 }
 
