@@ -67,7 +67,7 @@ typedef struct pcu_b200_nn_stats {
     int64_t argmax_query; /* first (lowest-index) query attaining it (Eigen maxCoeff, :221-223)   */
     int64_t argmax_data;  /* its nearest neighbour in the dataset (:225)                          */
     int64_t n_queries;    /* n                                                                    */
-    int64_t n_tied;       /* queries whose nearest neighbour was decided by tie order             */
+    int64_t n_tied;       /* -1: the fused sweeps track distances only (ties only matter to witness_tied) */
     int64_t n_far;        /* queries that needed the ring-expansion slow path (diagnostic)        */
     int64_t witness_tied; /* 1: argmax_query had several equally near neighbours, so argmax_data  */
                           /* is the lowest such index, not necessarily the reference's pick; the  */
