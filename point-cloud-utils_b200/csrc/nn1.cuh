@@ -194,10 +194,9 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
         if (!settled) sw.far_list[atomicAdd(sw.counters, 1u)] = (unsigned)t;
     }
     double sum = 0.0, sumsq = 0.0;
-    unsigned ties = 0;
-    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
-    finish_query1<T, kOut, kStats>(sw, active && settled, best, row, (unsigned)t, sum, sumsq, mc, ties);
-    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + blockIdx.x);
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
+    finish_query1<T, kOut, kStats>(sw, active && settled, best, row, (unsigned)t, sum, sumsq, mc);
+    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, sw.partial + blockIdx.x);
 }
 
 template <typename T> __device__ void build_pyramid(const Cloud<T>& dc);   // pyramid.cuh
@@ -217,8 +216,7 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
     const int lane = threadIdx.x & 31;
     const unsigned warps_total = gridDim.x * (kThreads / 32);
     double sum = 0.0, sumsq = 0.0;
-    unsigned ties = 0;
-    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
     if (n_far > 0) {
         const GridHeader<T> g = *dc.grid;
         for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total) {
@@ -227,10 +225,10 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
             Best1<T> best;
             const bool ok = warp_ring_search<T>(g, dc, q, lane, best);
             if (!ok && lane == 0) sw.vfar_list[atomicAdd(sw.counters + 2, 1u)] = qt;
-            finish_query1<T, kOut, kStats>(sw, ok && lane == 0, best, (long long)q.i, qt, sum, sumsq, mc, ties);
+            finish_query1<T, kOut, kStats>(sw, ok && lane == 0, best, (long long)q.i, qt, sum, sumsq, mc);
         }
     }
-    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + blockIdx.x);
+    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, sw.partial + sw.main_blocks + blockIdx.x);
     __shared__ bool s_last;
     if (threadIdx.x == 0) {
         __threadfence();
@@ -248,8 +246,7 @@ template <typename T>
 __device__ __forceinline__ SweepPartial<T> load_partial(const SweepPartial<T>* src) {
     SweepPartial<T> p;
     p.sum = __ldcg(&src->sum); p.sumsq = __ldcg(&src->sumsq); p.max_d2 = __ldcg(&src->max_d2);
-    p.arg_q = __ldcg(&src->arg_q); p.arg_d = __ldcg(&src->arg_d);
-    p.n_tied = __ldcg(&src->n_tied); p.tie_at_max = __ldcg(&src->tie_at_max);
+    p.arg_q = __ldcg(&src->arg_q); p.arg_pos = __ldcg(&src->arg_pos);
     return p;
 }
 
@@ -259,15 +256,14 @@ template <typename T>
 __device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, SweepPartial<T>* result /* shared */) {
     const int total = 2 * sw.far_blocks;   // far pass | pyramid pass (which carries the main pass)
     double sum = 0.0, sumsq = 0.0;
-    unsigned ties = 0;
-    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
     for (int s = threadIdx.x; s < total; s += blockDim.x) {
         const SweepPartial<T> p = load_partial<T>(sw.partial + sw.main_blocks + s);
-        sum += p.sum; sumsq += p.sumsq; ties += p.n_tied;
-        MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.d = p.arg_d; c.tie = p.tie_at_max;
+        sum += p.sum; sumsq += p.sumsq;
+        MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.pos = p.arg_pos;
         take_max<T>(mc, c);
     }
-    block_reduce_stats<T>(sum, sumsq, mc, ties, result);
+    block_reduce_stats<T>(sum, sumsq, mc, result);
     __syncthreads();
 }
 

@@ -122,8 +122,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
     const Cloud<T> qc = clouds[sw.qcloud];
     const Cloud<T> dc = clouds[sw.dcloud];
     double sum = 0.0, sumsq = 0.0;
-    unsigned ties = 0;
-    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0x7fffffffffffffffLL; mc.d = -1; mc.tie = 0;
+    MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
     if (n_vfar > 0) {
         __shared__ GridHeader<T> g;
         __shared__ PyramidShape ps;
@@ -134,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
             Best1<T> best; best.d = R::inf(); best.i = no_index<T>(); best.tie = false;
             pyramid_descend<T>(g, ps, dc, q, [&]() { return best.d; },
                                [&](unsigned a, unsigned b) { scan_run1<T>(dc.sorted, a, b, q.x, q.y, q.z, best); });
-            finish_query1<T, kOut, kStats>(sw, true, best, (long long)q.i, sw.vfar_list[f], sum, sumsq, mc, ties);
+            finish_query1<T, kOut, kStats>(sw, true, best, (long long)q.i, sw.vfar_list[f], sum, sumsq, mc);
         }
     }
     if (kStats) {
@@ -144,11 +143,11 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
         const int main_used = (int)((qc.n + kThreads - 1) / kThreads);
         for (int s = blockIdx.x + threadIdx.x * gridDim.x; s < main_used; s += gridDim.x * blockDim.x) {
             const SweepPartial<T> p = load_partial<T>(sw.partial + s);
-            sum += p.sum; sumsq += p.sumsq; ties += p.n_tied;
-            MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.d = p.arg_d; c.tie = p.tie_at_max;
+            sum += p.sum; sumsq += p.sumsq;
+            MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.pos = p.arg_pos;
             take_max<T>(mc, c);
         }
-        block_reduce_stats<T>(sum, sumsq, mc, ties, sw.partial + sw.main_blocks + sw.far_blocks + blockIdx.x);
+        block_reduce_stats<T>(sum, sumsq, mc, sw.partial + sw.main_blocks + sw.far_blocks + blockIdx.x);
         // The CTA that finishes last folds all partials of this sweep (main pass + this pass) into the
         // caller's statistics record; for a bidirectional call the sweep that finishes second also
         // writes the Chamfer value.  No separate finalize launch.
@@ -169,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
             if (threadIdx.x == 0) wg = *dc.grid;
             __syncthreads();
             if (threadIdx.x < 32 && result.max_d2 >= (T)0) {
-                const Pt<T> wq = load_pt<T>(qc.sorted + (unsigned)result.arg_d);
+                const Pt<T> wq = load_pt<T>(qc.sorted + result.arg_pos);
                 Best1<T> wb; wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
                 const bool ok = warp_ring_search<T>(wg, dc, wq, threadIdx.x, wb);
                 if (!ok) {   // beyond the rings: the pyramid exists (this query was on the very-far list)
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
                     st.sum_dist = result.sum;
                     st.sum_sq_dist = result.sumsq;
                     st.max_sq_dist = (double)result.max_d2;
-                    st.argmax_query = result.arg_q;
+                    st.argmax_query = (long long)result.arg_q;
                     st.argmax_data = wb.i != no_index<T>() ? (long long)wb.i : -1;
                     st.n_queries = qc.n;
                     st.n_tied = -1;   // not tracked by the statistics-only sweep

@@ -22,9 +22,8 @@ template <typename T>
 struct SweepPartial {
     double sum, sumsq;
     T max_d2;
-    long long arg_q, arg_d;
-    unsigned n_tied;
-    unsigned tie_at_max;
+    unsigned arg_q;     // caller-order row of the query attaining max_d2 (first one)
+    unsigned arg_pos;   // its position in cell order (the witness search starts from there)
 };
 
 // One query-cloud -> dataset-cloud direction.
@@ -158,9 +157,9 @@ __device__ __forceinline__ bool expand_rings(const GridHeader<T>& g, const T* __
 // block-level reduction of the fused statistics
 template <typename T>
 struct MaxCand {
-    T d2;
-    long long q, d;
-    unsigned tie;
+    T d2;           // -1: neutral element
+    unsigned q;     // caller-order row (clouds are limited to 2^31 - 1 points)
+    unsigned pos;   // position in cell order
 };
 template <typename T>
 __device__ __forceinline__ void take_max(MaxCand<T>& a, const MaxCand<T>& b) {
@@ -176,8 +175,7 @@ __device__ __forceinline__ MaxCand<T> warp_take_max(MaxCand<T> mc) {
         MaxCand<T> other;
         other.d2 = __shfl_xor_sync(0xffffffffu, mc.d2, o);
         other.q = __shfl_xor_sync(0xffffffffu, mc.q, o);
-        other.d = __shfl_xor_sync(0xffffffffu, mc.d, o);
-        other.tie = __shfl_xor_sync(0xffffffffu, mc.tie, o);
+        other.pos = __shfl_xor_sync(0xffffffffu, mc.pos, o);
         take_max<T>(mc, other);
     }
     return mc;
@@ -190,43 +188,38 @@ __device__ __forceinline__ MaxCand<float> warp_take_max<float>(MaxCand<float> mc
     const unsigned bits = real ? __float_as_uint(mc.d2) : 0u;
     const unsigned top = __reduce_max_sync(0xffffffffu, bits);
     const bool holds = real && bits == top;
-    const unsigned row = holds ? (unsigned)mc.q : 0xffffffffu;
+    const unsigned row = holds ? mc.q : 0xffffffffu;
     const unsigned first = __reduce_min_sync(0xffffffffu, row);
     const unsigned who = __ballot_sync(0xffffffffu, holds && row == first);
     if (who == 0u) return mc;         // nobody holds a real candidate: all lanes are neutral
     const int src = __ffs(who) - 1;
     MaxCand<float> out;
-    out.d2 = __shfl_sync(0xffffffffu, mc.d2, src);
-    out.q = (long long)first;
-    out.d = __shfl_sync(0xffffffffu, mc.d, src);
-    out.tie = __shfl_sync(0xffffffffu, mc.tie, src);
+    out.d2 = __uint_as_float(top);
+    out.q = first;
+    out.pos = __shfl_sync(0xffffffffu, mc.pos, src);
     return out;
 }
 
 template <typename T>
-__device__ __forceinline__ void block_reduce_stats(double sum, double sumsq, MaxCand<T> mc, unsigned ties,
-                                                   SweepPartial<T>* out) {
+__device__ __forceinline__ void block_reduce_stats(double sum, double sumsq, MaxCand<T> mc, SweepPartial<T>* out) {
     __shared__ double s_sum[kThreads / 32], s_sq[kThreads / 32];
     __shared__ MaxCand<T> s_mc[kThreads / 32];
-    __shared__ unsigned s_t[kThreads / 32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
     }
-    ties = __reduce_add_sync(0xffffffffu, ties);
     mc = warp_take_max<T>(mc);
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { s_sum[w] = sum; s_sq[w] = sumsq; s_mc[w] = mc; s_t[w] = ties; }
+    if (l == 0) { s_sum[w] = sum; s_sq[w] = sumsq; s_mc[w] = mc; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < kThreads / 32; ++i) {   // fixed order: deterministic
-            sum += s_sum[i]; sumsq += s_sq[i]; ties += s_t[i];
+            sum += s_sum[i]; sumsq += s_sq[i];
             take_max<T>(mc, s_mc[i]);
         }
         SweepPartial<T> p;
-        p.sum = sum; p.sumsq = sumsq; p.max_d2 = mc.d2; p.arg_q = mc.q; p.arg_d = mc.d; p.n_tied = ties;
-        p.tie_at_max = mc.tie;
+        p.sum = sum; p.sumsq = sumsq; p.max_d2 = mc.d2; p.arg_q = mc.q; p.arg_pos = mc.pos;
         *out = p;
     }
 }
@@ -234,12 +227,10 @@ __device__ __forceinline__ void block_reduce_stats(double sum, double sumsq, Max
 // kOut: write the query's neighbour to the caller's arrays.  kStats: fold its distance into the fused
 // statistics.  In the statistics-only sweeps the hot loop tracks the minimum distance and nothing else:
 // the only index the scalar metrics ever need is the neighbour of the ONE query that attains the
-// Hausdorff maximum, and that is recovered afterwards (resolve_witness, nn1.cuh), so MaxCand::d
-// carries the query's position in cell order there, not a neighbour index.
+// Hausdorff maximum, and that is recovered afterwards by one warp (last CTA of the pyramid pass).
 template <typename T, bool kOut, bool kStats>
 __device__ __forceinline__ void finish_query1(const Sweep<T>& sw, bool have, const Best1<T>& best, long long row,
-                                              unsigned pos, double& sum, double& sumsq, MaxCand<T>& mc,
-                                              unsigned& ties) {
+                                              unsigned pos, double& sum, double& sumsq, MaxCand<T>& mc) {
     using R = Real<T>;
     if (!have) return;
     const T root = R::root(best.d);
@@ -252,7 +243,7 @@ __device__ __forceinline__ void finish_query1(const Sweep<T>& sw, bool have, con
     if (kStats) {
         sum += (double)root;
         sumsq += (double)best.d;
-        MaxCand<T> c; c.d2 = best.d; c.q = row; c.d = (long long)pos; c.tie = 0u;
+        MaxCand<T> c; c.d2 = best.d; c.q = (unsigned)row; c.pos = pos;
         take_max<T>(mc, c);
     }
 }
