@@ -45,6 +45,16 @@ WORKLOADS = {
 }
 ALGO_BYTES_PER_QPT = {"c3": 24.0, "c2": 36.0, "c4": 205.2, "c5": 24.0}
 
+# Test hook (tests/test_bench_cpu.py): PCU_BENCH_SCALE=0.01 shrinks every cloud so that the reference arm's
+# JSON contract can be checked in seconds.  Never set for a measurement.
+_SCALE = float(os.environ.get("PCU_BENCH_SCALE", "1"))
+if _SCALE != 1.0:
+    for _w in WORKLOADS.values():
+        _w["n"] = max(16, int(_w["n"] * _SCALE))
+        _w["m"] = max(16, int(_w["m"] * _SCALE))
+        if "batch" in _w:
+            _w["batch"] = max(2, int(_w["batch"] * _SCALE))
+
 
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")

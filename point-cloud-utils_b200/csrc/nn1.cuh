@@ -91,8 +91,8 @@ __device__ __forceinline__ bool warp_ring_search(const GridHeader<T>& g, const C
 
 // Main pass: one thread per (cell-sorted) query.
 //   phase A (uniform): look up the 9 runs and the wall bound of each row;
-//   phase B (flattened): ONE loop in which a lane either evaluates its next two candidates or steps to
-//     its next row that is not pruned by its bound;
+//   phase B: ONE loop in which every trip a lane first steps to its next row if its run is exhausted
+//     (skipping rows pruned by their bound) and then evaluates its next two candidates;
 //   queries the 3 x 3 x 3 neighbourhood cannot settle (empty surroundings) go to the far list
 //   (nn1_far_kernel below; doing them here, one warp each, cost more in registers and idle warps
 //   than the extra launch -- measured).

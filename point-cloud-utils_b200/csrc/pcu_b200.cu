@@ -399,7 +399,6 @@ template <typename T>
 int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream) {
     const int nclouds = plan.nclouds;
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
-    const unsigned pts_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
     PCU_LAUNCH_C(bbox_partial_kernel, dim3(plan.max_bbox_blocks, nclouds), kThreads);
     PCU_LAUNCH_C(grid_setup_kernel, dim3(1, nclouds), kThreads);
@@ -463,7 +462,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         else if (k <= 16) PCU_LAUNCH_CS(knn_thread_kernel, dim3(qblocks, 1), kThreads, 16);
         else              PCU_LAUNCH_CS(knn_thread_kernel, dim3(qblocks, 1), kThreads, 32);
         mark(ws, 6, stream);
-        PCU_LAUNCH_CS(knn_warp_kernel, dim3(plan.far_blocks, 1), kThreads, true);
+        PCU_LAUNCH_CS(knn_warp_kernel, dim3(plan.far_blocks, 1), kThreads);
         PCU_LAUNCH_CS(knn_descend_kernel, dim3(plan.far_blocks, 1), kThreads, false);
         mark(ws, 7, stream);
     } else {

@@ -9,11 +9,11 @@
 namespace pcu {
 
 // ---------------------------------------------------------------------------------------------
-// 2 <= k <= 32: one warp per query; lane j holds the j-th best (distance, index) pair, candidates
-// are evaluated 32 at a time and inserted with shuffles.  Order inside the list is (distance, index)
-// ascending, which is deterministic; queries whose answer depends on how the reference orders equal
-// distances are reported in tie_list and re-answered by the kd-tree replay.
-// grid (ceil(max_n * 32 / kThreads), nsweeps).
+// One query answered by a whole warp (the slow pass of 2 <= k <= 32): lane j holds the j-th best
+// (distance, index) pair, candidates are evaluated 32 at a time and inserted with shuffles.  Order
+// inside the list is (distance, index) ascending, which is deterministic; queries whose answer depends
+// on how the reference orders equal distances are reported in tie_list and re-answered by the kd-tree
+// replay.  At most `max_ring` rings are walked; a query still open after that goes to the very-far list.
 template <typename T>
 __device__ __forceinline__ void knn_warp_one(const Sweep<T>& sw, const Cloud<T>& qc, const Cloud<T>& dc,
                                              const GridHeader<T>& g, long long t, int lane, int max_ring) {
@@ -89,40 +89,33 @@ __device__ __forceinline__ void knn_warp_one(const Sweep<T>& sw, const Cloud<T>&
     if (any && lane == 0) sw.tie_list[atomicAdd(sw.counters + 1, 1u)] = row;
 }
 
-// kFar == false: warp w answers sorted query w.            grid (ceil(max_n * 32 / kThreads), nsweeps)
-// kFar == true : warp-stride loop over the far list left by knn_thread_kernel.   grid (far_blocks, nsweeps)
-template <typename T, typename CS, typename SS, bool kFar>
+// Slow pass of 2 <= k <= 32: warp-stride loop over the far list left by knn_thread_kernel, at most
+// kMaxRing rings per query; the CTA that finishes last builds the occupancy pyramid if some query is
+// still open (knn_descend_kernel then answers it).  grid (far_blocks, nsweeps)
+template <typename T, typename CS, typename SS>
 __global__ void __launch_bounds__(kThreads) knn_warp_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     grid_dependency_wait();
     const Sweep<T> sw = sweeps[blockIdx.y];
     const Cloud<T> qc = clouds[sw.qcloud];
     const Cloud<T> dc = clouds[sw.dcloud];
     const int lane = threadIdx.x & 31;
-    if (kFar) {
-        const unsigned n_far = sw.counters[0];
-        if (n_far > 0) {
-            const GridHeader<T> g = *dc.grid;
-            const unsigned warps_total = gridDim.x * (kThreads / 32);
-            for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total)
-                knn_warp_one<T>(sw, qc, dc, g, (long long)sw.far_list[f], lane, kMaxRing);
-        }
-        // the CTA that finishes last builds the occupancy pyramid if some query is still open
-        __shared__ bool s_last;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            s_last = atomicAdd(sw.counters + 5, 1u) == gridDim.x - 1;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            if (*(volatile unsigned*)(sw.counters + 2) > 0) build_pyramid<T>(dc);
-        }
-    } else {
-        const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-        if (t >= qc.n) return;   // warp-uniform
+    const unsigned n_far = sw.counters[0];
+    if (n_far > 0) {
         const GridHeader<T> g = *dc.grid;
-        knn_warp_one<T>(sw, qc, dc, g, t, lane, 1 << 30);
+        const unsigned warps_total = gridDim.x * (kThreads / 32);
+        for (unsigned f = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); f < n_far; f += warps_total)
+            knn_warp_one<T>(sw, qc, dc, g, (long long)sw.far_list[f], lane, kMaxRing);
+    }
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(sw.counters + 5, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (*(volatile unsigned*)(sw.counters + 2) > 0) build_pyramid<T>(dc);
     }
 }
 
