@@ -403,7 +403,7 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     PCU_LAUNCH_C(bbox_partial_kernel, dim3(plan.max_bbox_blocks, nclouds), kThreads);
     PCU_LAUNCH_C(grid_setup_kernel, dim3(1, nclouds), kThreads);
     mark(ws, 2, stream);
-    const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads * kBinPerThread - 1) / (kThreads * kBinPerThread));
+    const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     PCU_LAUNCH_C(cell_count_kernel, dim3(bin_blocks, nclouds), kThreads);
     mark(ws, 3, stream);
     PCU_LAUNCH_C(scan_lookback_kernel, dim3(scan_blocks, nclouds), kScanThreads);

@@ -258,3 +258,18 @@ def test_concurrent_python_threads(pcu, oracle):
         t.join()
     for g, e in zip(got, expect):
         assert np.array_equal(g[1], e[1]) and np.array_equal(g[0], e[0])
+
+
+def test_batched_chamfer_matches_per_pair(pcu, oracle):
+    """Batched entry point: every pair equals the single-pair call (and the oracle), including cloud sizes
+    whose per-pair offsets are not 16-byte aligned (plain-load path instead of the bulk tile copy)."""
+    rng = np.random.default_rng(5)
+    for n, m in ((1001, 777), (4096, 2048)):
+        x = rng.random((5, n, 3), dtype=np.float32)
+        y = rng.random((5, m, 3), dtype=np.float32)
+        got = pcu.batched_chamfer_distance(x, y)
+        assert got.shape == (5,) and got.dtype == np.float32
+        for b in range(5):
+            ref = float(oracle.chamfer_distance(x[b], y[b]))
+            assert abs(float(got[b]) - ref) <= REL * ref
+            assert abs(float(got[b]) - float(pcu.chamfer_distance(x[b], y[b]))) <= 1e-7 * ref
