@@ -232,22 +232,19 @@ def main():
     yp = torch.from_numpy(yh).pin_memory()
     xd, yd = xp.to(dev, non_blocking=True), yp.to(dev, non_blocking=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    acc = torch.zeros(1, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def device_step():
         if wl_key == "c3":
-            c = pcu.chamfer_distance(xd, yd)
-            res = c.double().reshape(1)
+            res = pcu.chamfer_distance(xd, yd)                       # 0-dim CUDA tensor, no synchronisation
         elif wl_key == "c5":
-            _, s = bmod.batched_chamfer(xd, yd, return_sum=True)
-            res = s.reshape(1)
+            _, res = bmod.batched_chamfer(xd, yd, return_sum=True)   # fp64 sum of this rank's pairs
         else:
-            d, i = pcu.k_nearest_neighbors(xd, yd, k)
+            pcu.k_nearest_neighbors(xd, yd, k)
             return None
-        if world > 1:
-            dist.all_reduce(res, op=dist.ReduceOp.SUM)   # the path's only exchange: one fp64 scalar
-        acc.copy_(res)
+        if world > 1:   # the path's only exchange: one fp64 scalar per rank
+            res = res.to(torch.float64).reshape(1)
+            dist.all_reduce(res, op=dist.ReduceOp.SUM)
         return res
 
     def host_step():
