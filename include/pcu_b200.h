@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PCU_B200_ABI_VERSION 1
+#define PCU_B200_ABI_VERSION 2
 
 typedef enum pcu_b200_status {
     PCU_B200_OK = 0,
@@ -80,6 +80,8 @@ typedef struct pcu_b200_options {
     int max_points_per_leaf; /* reference kwarg; only influences how exact-distance ties are ordered (default 10) */
     float cell_occupancy;    /* target dataset points per grid cell (default: 2 for k = 1, ~k/2 otherwise)        */
     int disable_tie_replay;  /* 1: keep the (distance, lowest index) order for tied queries (diagnostic only)     */
+    int binning;             /* 0: automatic; 1: always the multi-launch grid build; 2: the one-CTA-per-cloud     */
+                             /* build whenever a cloud's cell counters fit in shared memory (diagnostic only)    */
 } pcu_b200_options;
 
 /* ---- library / error plumbing ------------------------------------------------------------ */

@@ -68,7 +68,7 @@ struct CallScope {
     CallScope() : nogil(), lock(pool().busy) {}
 };
 
-struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; };
+struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; int binning = 0; };
 Options& defaults() { static Options o; return o; }
 
 // Validates the per-call options (with the GIL held); they are applied to the workspace inside the
@@ -79,6 +79,7 @@ pcu_b200_options make_options(int max_points_per_leaf) {
     o.max_points_per_leaf = max_points_per_leaf;
     o.cell_occupancy = defaults().occupancy;
     o.disable_tie_replay = defaults().disable_replay;
+    o.binning = defaults().binning;
     return o;
 }
 
@@ -430,10 +431,12 @@ PYBIND11_MODULE(_pcu_internal, mod) {
         for (int i = 0; i < n; ++i) d[py::str(pcu_b200_profile_stage_name(i))] = ms[i];
         return d;
     });
-    mod.def("_set_defaults", [](float cell_occupancy, bool disable_tie_replay) {
+    mod.def("_set_defaults", [](float cell_occupancy, bool disable_tie_replay, int binning) {
+        if (binning < 0 || binning > 2) throw py::value_error("binning must be 0 (auto), 1 (multi-launch) or 2 (one CTA per cloud)");
         defaults().occupancy = cell_occupancy;
         defaults().disable_replay = disable_tie_replay ? 1 : 0;
-    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = false);
+        defaults().binning = binning;
+    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = false, py::arg("binning") = 0);
     mod.def("_release_workspaces", []() { pool().clear(); });
     // destroy workspaces before the CUDA context goes away at interpreter exit
     py::module_::import("atexit").attr("register")(py::cpp_function([]() { pool().clear(); }));

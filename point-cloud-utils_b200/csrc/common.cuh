@@ -186,9 +186,13 @@ struct CloudsVal {
 };
 
 constexpr int kMaxBBoxBlocks = 1024;    // partial bounding boxes per cloud, upper bound
-constexpr int kBBoxPerThread = 8;       // scalars each thread folds per pass
+constexpr int kBBoxPerThread = 12;      // scalars each thread folds per pass (multiple of 3)
 constexpr int kScanItems = 8;           // items per thread in the scan
 constexpr int kScanThreads = 512;
 constexpr int kScanTile = kScanItems * kScanThreads;
+// one-CTA binning of small clouds (bin_small_kernel): the cell counters live in shared memory
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallMaxCells = 50 * 1024;      // counters: 200 KB of the 227 KB a CTA may own
+constexpr long long kSmallMaxPoints = 128 * 1024;
 
 }  // namespace pcu

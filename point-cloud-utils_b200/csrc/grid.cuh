@@ -13,41 +13,41 @@
 namespace pcu {
 
 // ---------------------------------------------------------------------------------------------
-// 1. partial bounding boxes: grid (max bbox_blocks, nclouds)
-template <typename T, typename CS>
-__global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_constant__ CS clouds) {
-    grid_dependency_wait();
+// 1. bounding box.  block_bbox folds the scalars of the chunks chunk0, chunk0 + chunk_step, ... (a chunk
+//    is blockDim * kBBoxPerThread consecutive scalars of the flat (n, 3) array) and leaves
+//    {lo x, lo y, lo z, hi x, hi y, hi z} in dst (written by threads 0..5; no barrier after the write).
+//    The walk is flat and fully coalesced: thread t reads scalars t, t + blockDim, t + 2 blockDim, ...
+//    of a chunk.  blockDim = 1 (mod 3) and the chunk length is a multiple of 3, so the k-th scalar a
+//    thread reads belongs to axis (t + k) mod 3: three running boxes per thread, no index arithmetic.
+template <typename T>
+__device__ __forceinline__ void block_bbox(const T* __restrict__ raw, long long total, long long chunk0, long long chunk_step, T* dst) {
     using R = Real<T>;
-    const Cloud<T> c = clouds[blockIdx.y];
-    if ((int)blockIdx.x >= c.bbox_blocks) return;
-    T lo[3] = {R::inf(), R::inf(), R::inf()};
-    T hi[3] = {-R::inf(), -R::inf(), -R::inf()};
-    // Flat, fully coalesced walk over the 3n scalars.  Each thread folds kBBoxPerThread scalars per
-    // pass, spaced 3 * blockDim apart so that all of them belong to the same axis; the loads of a
-    // pass are independent, which keeps several requests in flight per thread.
-    const long long total = 3 * c.n;
-    const long long pass = (long long)c.bbox_blocks * blockDim.x * 3 * kBBoxPerThread;
-    T vlo = R::inf(), vhi = -R::inf();
-    for (long long base = ((long long)blockIdx.x * kBBoxPerThread) * (3 * blockDim.x) + threadIdx.x; base < total; base += pass) {
+    static_assert(kBBoxPerThread % 3 == 0, "a chunk must hold whole points per thread column");
+    const long long chunk = (long long)blockDim.x * kBBoxPerThread;
+    T alo[3] = {R::inf(), R::inf(), R::inf()};
+    T ahi[3] = {-R::inf(), -R::inf(), -R::inf()};
+    for (long long base = chunk0 * chunk + threadIdx.x; base < total; base += chunk_step * chunk) {
         T v[kBBoxPerThread];
 #pragma unroll
         for (int k = 0; k < kBBoxPerThread; ++k) {
-            const long long e = base + (long long)k * 3 * blockDim.x;
-            v[k] = e < total ? __ldg(c.raw + e) : R::inf();
+            const long long e = base + (long long)k * blockDim.x;
+            v[k] = e < total ? __ldg(raw + e) : R::inf();
         }
 #pragma unroll
         for (int k = 0; k < kBBoxPerThread; ++k) {
-            const long long e = base + (long long)k * 3 * blockDim.x;
-            vlo = R::vmin(vlo, v[k]);
-            if (e < total) vhi = R::vmax(vhi, v[k]);
+            const long long e = base + (long long)k * blockDim.x;
+            alo[k % 3] = R::vmin(alo[k % 3], v[k]);
+            if (e < total) ahi[k % 3] = R::vmax(ahi[k % 3], v[k]);
         }
     }
-    // every index this thread touched is threadIdx.x plus a multiple of 3
-    const int my_axis = (int)(threadIdx.x % 3);
+    // slot r of this thread holds axis (threadIdx.x + r) mod 3
+    const int t3 = (int)(threadIdx.x % 3);
+    T lo[3], hi[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        lo[a] = a == my_axis ? vlo : R::inf();
-        hi[a] = a == my_axis ? vhi : -R::inf();
+        const int r = (a - t3 + 3) % 3;
+        lo[a] = r == 0 ? alo[0] : (r == 1 ? alo[1] : alo[2]);
+        hi[a] = r == 0 ? ahi[0] : (r == 1 ? ahi[1] : ahi[2]);
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_con
             lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
             hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
-    __shared__ T s[kThreads / 32][6];
+    __shared__ T s[32][6];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (l == 0) {
 #pragma unroll
@@ -65,53 +65,31 @@ __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_con
     __syncthreads();
     if (threadIdx.x < 6) {
         T v = s[0][threadIdx.x];
-        for (int i = 1; i < kThreads / 32; ++i)
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
             v = threadIdx.x < 3 ? R::vmin(v, s[i][threadIdx.x]) : R::vmax(v, s[i][threadIdx.x]);
-        c.bbox_partial[blockIdx.x * 6 + threadIdx.x] = v;
+        dst[threadIdx.x] = v;
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// 2. grid shape + wall tables: grid (1, nclouds), kThreads threads
+//    partial boxes of a large cloud: grid (max bbox_blocks, nclouds)
 template <typename T, typename CS>
-__global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_constant__ CS clouds) {
+__global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_constant__ CS clouds) {
     grid_dependency_wait();
+    static_assert(kThreads % 3 == 1, "block_bbox relies on blockDim = 1 (mod 3)");
+    const Cloud<T> c = clouds[blockIdx.y];
+    if ((int)blockIdx.x >= c.bbox_blocks) return;
+    block_bbox<T>(c.raw, 3 * c.n, blockIdx.x, c.bbox_blocks, c.bbox_partial + blockIdx.x * 6);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. grid shape + wall tables.  grid_setup_body: block-wide; `box` (shared, 6 values, already visible to
+//    the block) -> `hdr` (shared) plus the header, pyramid shape and wall tables in device memory.
+template <typename T>
+__device__ void grid_setup_body(const Cloud<T>& c, const T* box, GridHeader<T>& hdr) {
     using R = Real<T>;
     using bits_t = typename R::bits_t;
-    const Cloud<T> c = clouds[blockIdx.y];
-    __shared__ T box[6];
-    __shared__ T red[kThreads / 32][6];
-    __shared__ GridHeader<T> hdr;
     __shared__ double s_ext[3], s_lo, s_hi;
     __shared__ int s_first;
-    {   // fold the partial boxes: thread t takes partials t, t + blockDim, ...
-        T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
-        for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = R::vmin(lo[a], c.bbox_partial[i * 6 + a]);
-                hi[a] = R::vmax(hi[a], c.bbox_partial[i * 6 + 3 + a]);
-            }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-                hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-            }
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
-        __syncthreads();
-        if (threadIdx.x < 6) {
-            T v = red[0][threadIdx.x];
-            for (int i = 1; i < kThreads / 32; ++i)
-                v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
-            box[threadIdx.x] = v;
-        }
-        __syncthreads();
-    }
     const int maxdim = c.stride - 1;
     if (threadIdx.x == 0) {
         double emax = 0.0;
@@ -218,6 +196,46 @@ __global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_const
         c.wall_lo[a * stride + j] = wl;
         c.wall_hi[a * stride + j] = wh;
     }
+}
+
+//    grid (1, nclouds), kThreads threads: folds the partial boxes, then the body above
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
+    using R = Real<T>;
+    const Cloud<T> c = clouds[blockIdx.y];
+    __shared__ T box[6];
+    __shared__ T red[kThreads / 32][6];
+    __shared__ GridHeader<T> hdr;
+    {   // fold the partial boxes: thread t takes partials t, t + blockDim, ...
+        T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
+        for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = R::vmin(lo[a], c.bbox_partial[i * 6 + a]);
+                hi[a] = R::vmax(hi[a], c.bbox_partial[i * 6 + 3 + a]);
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            T v = red[0][threadIdx.x];
+            for (int i = 1; i < kThreads / 32; ++i)
+                v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
+            box[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    grid_setup_body<T>(c, box, hdr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -396,6 +414,93 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const __grid_constant
     if (!load_tile_point<T>(c, g, tile, bar, i, x, y, z)) return;
     const unsigned pos = c.cell_start[linear_cell<T>(g, x, y, z)] + c.rank[i];
     store_pt<T>(c.sorted + pos, x, y, z, i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-5 in one launch for small clouds: one CTA of kSmallThreads threads bins one whole cloud.  The cell
+// counters (cell_cap + 1 words, dynamic shared memory) never leave the SM: the histogram and the
+// scatter cursors are shared-memory atomics instead of L2 atomics, the scan is block-local, and a batch
+// of B pairs is one launch of 2B independent CTAs instead of five grid-wide passes.  The order of the
+// points inside a cell is arbitrary here as in the general path (every consumer orders candidates by
+// (distance, index)).  grid (nclouds), dynamic shared memory 4 * (max cell_cap + 1) bytes.
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kSmallThreads, 1) bin_small_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
+    static_assert(kSmallThreads % 3 == 1 && kSmallThreads == 1024, "block_bbox / the scan below assume 32 warps");
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    unsigned* cnt = reinterpret_cast<unsigned*>(small_smem);
+    const Cloud<T> c = clouds[blockIdx.x];
+    __shared__ T box[6];
+    __shared__ GridHeader<T> hdr;
+    __shared__ unsigned warp_tot[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int ncount = c.cell_cap + 1;
+    for (int i = t; i < ncount; i += kSmallThreads) cnt[i] = 0u;
+    block_bbox<T>(c.raw, 3 * c.n, 0, 1, box);
+    __syncthreads();
+    grid_setup_body<T>(c, box, hdr);
+    const GridHeader<T> g = hdr;
+    const int n = (int)c.n;
+    constexpr int kBatch = 4;
+    // histogram
+    for (int first = t; first < n; first += kBatch * kSmallThreads) {
+        T p[kBatch][3];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const int i = first + b * kSmallThreads;
+            if (i < n) { p[b][0] = __ldg(c.raw + 3ll * i); p[b][1] = __ldg(c.raw + 3ll * i + 1); p[b][2] = __ldg(c.raw + 3ll * i + 2); }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b)
+            if (first + b * kSmallThreads < n) atomicAdd(&cnt[linear_cell<T>(g, p[b][0], p[b][1], p[b][2])], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the counters, kSmallThreads entries per round; the prefix goes to cell_start
+    // and stays in shared memory as the scatter cursors
+    unsigned carry = 0;
+    for (int base = 0; base < ncount; base += kSmallThreads) {
+        const int i = base + t;
+        const unsigned v = i < ncount ? cnt[i] : 0u;
+        unsigned inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            unsigned s = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += u;
+            }
+            warp_tot[lane] = s;
+        }
+        __syncthreads();
+        const unsigned ex = carry + (w ? warp_tot[w - 1] : 0u) + inc - v;
+        if (i < ncount) { cnt[i] = ex; c.cell_start[i] = ex; }
+        carry += warp_tot[31];
+        __syncthreads();
+    }
+    // scatter
+    for (int first = t; first < n; first += kBatch * kSmallThreads) {
+        T p[kBatch][3];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const int i = first + b * kSmallThreads;
+            if (i < n) { p[b][0] = __ldg(c.raw + 3ll * i); p[b][1] = __ldg(c.raw + 3ll * i + 1); p[b][2] = __ldg(c.raw + 3ll * i + 2); }
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const int i = first + b * kSmallThreads;
+            if (i < n) {
+                const unsigned pos = atomicAdd(&cnt[linear_cell<T>(g, p[b][0], p[b][1], p[b][2])], 1u);
+                store_pt<T>(c.sorted + pos, p[b][0], p[b][1], p[b][2], i);
+            }
+        }
+    }
 }
 
 }  // namespace pcu

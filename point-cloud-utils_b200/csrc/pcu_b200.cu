@@ -79,6 +79,22 @@ int fail(int status, const char* fmt, ...) {
         g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
     } while (0)
 
+#define PCU_LAUNCH_PDL_SMEM(kernel, grid, block, smem, stream, ...)                            \
+    do {                                                                                       \
+        cudaLaunchConfig_t cfg__ = {};                                                         \
+        cfg__.gridDim = dim3(grid);                                                            \
+        cfg__.blockDim = dim3(block);                                                          \
+        cfg__.dynamicSmemBytes = (smem);                                                       \
+        cfg__.stream = stream;                                                                 \
+        cudaLaunchAttribute attr__[1];                                                         \
+        attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                     \
+        attr__[0].val.programmaticStreamSerializationAllowed = 1;                              \
+        cfg__.attrs = attr__;                                                                  \
+        cfg__.numAttrs = 1;                                                                    \
+        PCU_CUDA(cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__));                             \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    } while (0)
+
 // Descriptor-taking kernels exist in two flavours: descriptors by value in parameter space (single
 // pair: `plan.by_value`) or in a device array (batches).  K<T, CloudsX<T>[, SweepsX<T>][, extra...]>.
 #define PCU_LAUNCH_C(K, grid, block)                                                                      \
@@ -172,6 +188,7 @@ struct pcu_b200_workspace {
     pcu_b200_options opts{};
     int sm_count = 148;
     // optional per-stage timing (bench.py's roofline pass): events recorded on the launching stream
+    unsigned small_attr = 0;             // bin_small_kernel instantiations whose shared-memory limit has been raised
     bool profiling = false;
     cudaEvent_t marks[9] = {};
     int marks_used = 0;
@@ -249,6 +266,7 @@ struct PlanSpec {
     bool want_stats = false;
     bool want_out = false;
     float occupancy = 2.f;
+    int binning = 0;                // pcu_b200_options::binning
     T* out_dist = nullptr;          // want_out (batch == 1)
     long long* out_idx = nullptr;
     pcu_b200_nn_stats* stats = nullptr;   // caller's device buffer, or null -> carved from the arena
@@ -269,8 +287,10 @@ struct Plan {
     CloudsPtr<T> cp{};
     SweepsPtr<T> sp{};
     pcu_b200_nn_stats* d_stats = nullptr;
-    unsigned char* zero_begin = nullptr;
+    unsigned char* zero_begin = nullptr;   // zeroed per call: [cell counters | scan states, tickets, sweep counters]
     size_t zero_bytes = 0;
+    size_t zero_cells_bytes = 0;           // leading part that only the multi-launch grid build needs zeroed
+    bool one_cta_binning = false;          // bin_small_kernel instead of the five grid-wide passes
     long long max_n = 0;
     int max_cap = 0;
     int max_bbox_blocks = 1;
@@ -318,11 +338,20 @@ struct Plan {
             max_bbox_blocks = std::max(max_bbox_blocks, cl.bbox_blocks);
             args.cs[s].raw = (size_t)3 * sizes[s] * sizeof(T);
             cl.cell_start = take_strided<unsigned>(cv, (size_t)cl.cell_cap + 1, B, args.cs[s].cell_start);
+            max_cap = std::max(max_cap, cl.cell_cap);
+        }
+        zero_cells_bytes = cv.off - zero_from;
+        for (int s = 0; s < 2; ++s) {
+            Cloud<T>& cl = args.cloud[s];
             cl.scan_state = take_strided<unsigned long long>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
                                                              args.cs[s].scan_state);
             cl.scan_ticket = take_strided<unsigned>(cv, 1, B, args.cs[s].scan_ticket);
-            max_cap = std::max(max_cap, cl.cell_cap);
         }
+        // One CTA per cloud when the counters fit in shared memory and either the clouds are small enough
+        // that five dependent launches cost more than one CTA's serial passes, or there are enough clouds
+        // to fill the machine with such CTAs.
+        const bool fits = max_cap + 1 <= kSmallMaxCells && max_n <= kSmallMaxPoints;
+        one_cta_binning = fits && (sp.binning == 2 || (sp.binning == 0 && (max_n <= 16384 || 2 * B >= 128)));
         for (int d = 0; d < sp.nsweeps; ++d)
             args.sweep[d].counters = take_strided<unsigned>(cv, 8, B, args.ss[d].counters);
         zero_begin = base ? base + zero_from : nullptr;
@@ -398,6 +427,23 @@ int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, const PlanSpec<T>& spec)
 template <typename T>
 int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream) {
     const int nclouds = plan.nclouds;
+    if (plan.one_cta_binning) {
+        PCU_CUDA(cudaMemsetAsync(plan.zero_begin + plan.zero_cells_bytes, 0, plan.zero_bytes - plan.zero_cells_bytes, stream));
+        const size_t smem = ((size_t)plan.max_cap + 1) * sizeof(unsigned);
+        const unsigned bit = 1u << ((sizeof(T) == 8 ? 2 : 0) + (plan.by_value ? 1 : 0));
+        if (!(ws->small_attr & bit)) {
+            const size_t most = (size_t)kSmallMaxCells * sizeof(unsigned);
+            if (plan.by_value)
+                PCU_CUDA(cudaFuncSetAttribute(bin_small_kernel<T, CloudsVal<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+            else
+                PCU_CUDA(cudaFuncSetAttribute(bin_small_kernel<T, CloudsPtr<T>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+            ws->small_attr |= bit;
+        }
+        if (plan.by_value) PCU_LAUNCH_PDL_SMEM((bin_small_kernel<T, CloudsVal<T>>), dim3(nclouds), kSmallThreads, smem, stream, plan.cv);
+        else PCU_LAUNCH_PDL_SMEM((bin_small_kernel<T, CloudsPtr<T>>), dim3(nclouds), kSmallThreads, smem, stream, plan.cp);
+        for (int stage = 2; stage <= 5; ++stage) mark(ws, stage, stream);   // the whole build shows up as "bbox+grid"
+        return PCU_B200_OK;
+    }
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
     PCU_LAUNCH_C(bbox_partial_kernel, dim3(plan.max_bbox_blocks, nclouds), kThreads);
@@ -440,6 +486,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     spec.a = query; spec.n = n; spec.b = dataset; spec.m = m;
     spec.nsweeps = 1; spec.k = k; spec.squared = squared; spec.want_out = true;
     spec.occupancy = occupancy_for(ws, k);
+    spec.binning = ws->opts.binning;
     spec.out_dist = out_dist; spec.out_idx = out_idx;
     spec.replay_points = ws->opts.disable_tie_replay ? 0 : m;
     Plan<T> plan;
@@ -499,6 +546,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     spec.a = a; spec.n = n; spec.b = b; spec.m = m;
     spec.nsweeps = ns; spec.k = 1; spec.want_stats = true;
     spec.occupancy = occupancy_for(ws, 1);
+    spec.binning = ws->opts.binning;
     spec.stats = out_stats;
     spec.value_out = both ? out_value : nullptr;
     Plan<T> plan;
@@ -558,6 +606,7 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         spec.a = x + first * 3 * n; spec.n = n; spec.b = y + first * 3 * m; spec.m = m;
         spec.nsweeps = 2; spec.k = 1; spec.want_stats = true;
         spec.occupancy = occupancy_for(ws, 1);
+        spec.binning = ws->opts.binning;
         Plan<T> plan;
         PCU_TRY(prepare_plan(ws, plan, spec));
         mark(ws, 0, stream);
@@ -671,6 +720,7 @@ int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_option
     if (!ws || !opts) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
     if (opts->max_points_per_leaf < 0) return fail(PCU_B200_INVALID_ARGUMENT, "max_points_per_leaf must be >= 0");
     if (opts->cell_occupancy < 0.f) return fail(PCU_B200_INVALID_ARGUMENT, "cell_occupancy must be >= 0");
+    if (opts->binning < 0 || opts->binning > 2) return fail(PCU_B200_INVALID_ARGUMENT, "binning must be 0, 1 or 2");
     ws->opts = *opts;
     return PCU_B200_OK;
 }

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pcu):
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     lib.pcu_b200_abi_version.restype = ctypes.c_int
-    assert lib.pcu_b200_abi_version() == 1
+    assert lib.pcu_b200_abi_version() == 2
     lib.pcu_b200_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.pcu_b200_last_error(), bytes)
 

@@ -273,3 +273,39 @@ def test_batched_chamfer_matches_per_pair(pcu, oracle):
             ref = float(oracle.chamfer_distance(x[b], y[b]))
             assert abs(float(got[b]) - ref) <= REL * ref
             assert abs(float(got[b]) - float(pcu.chamfer_distance(x[b], y[b]))) <= 1e-7 * ref
+
+
+@pytest.mark.parametrize("binning", [1, 2])
+def test_both_grid_builds_give_the_reference_results(pcu, oracle, binning):
+    """The grid is built either by five grid-wide passes or by one CTA per cloud (counters in shared
+    memory); `binning` forces one or the other.  Same inputs, both dtypes, k = 1 / k > 1 / the metrics /
+    a batch, sizes on either side of the automatic switch -- every result must be the reference's."""
+    internal = pcu._pcu_internal
+    internal._set_defaults(binning=binning)
+    try:
+        rng = np.random.default_rng(4242)
+        for dtype, n, m in ((np.float32, 1, 1), (np.float32, 37, 5), (np.float32, 3000, 70000), (np.float64, 50001, 9999),
+                            (np.float32, 100000, 100000)):
+            q = rng.random((n, 3)).astype(dtype)
+            d = (rng.random((m, 3)) * np.array([1.0, 0.25, 2.0])).astype(dtype)
+            for k in (1, 6):
+                got = pcu.k_nearest_neighbors(q, d, k)
+                ref = oracle.k_nearest_neighbors(q, d, k)
+                assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0]), (binning, dtype, n, m, k)
+            ref = float(oracle.chamfer_distance(q, d))
+            assert abs(float(pcu.chamfer_distance(q, d)) - ref) <= REL * ref
+            assert pcu.hausdorff_distance(q, d, return_index=True) == oracle.hausdorff_distance(q, d, return_index=True)
+        # lattice points: massive ties, duplicate points, boundary cells
+        lat = np.stack(np.meshgrid(*[np.arange(12, dtype=np.float32)] * 3, indexing="ij"), -1).reshape(-1, 3)
+        lat = np.concatenate([lat, lat[:100]])
+        got = pcu.k_nearest_neighbors(lat + np.float32(0.5), lat, 4)
+        ref = oracle.k_nearest_neighbors(lat + np.float32(0.5), lat, 4)
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+        x = rng.random((130, 20000, 3), dtype=np.float32)
+        y = rng.random((130, 9000, 3), dtype=np.float32)
+        got = pcu.batched_chamfer_distance(x, y)
+        for b in (0, 64, 129):
+            ref = float(oracle.chamfer_distance(x[b], y[b]))
+            assert abs(float(got[b]) - ref) <= REL * ref
+    finally:
+        internal._set_defaults()
