@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
     }
     if (kStats) block_reduce_stats<T>(sum, sumsq, mc, sw.partial + sw.main_blocks + blockIdx.x);
     __shared__ bool s_last;
+    __syncthreads();   // every warp of this CTA has made its very-far appends before the CTA draws its ticket
     if (threadIdx.x == 0) {
         __threadfence();
         s_last = atomicAdd(sw.counters + 5, 1u) == gridDim.x - 1;

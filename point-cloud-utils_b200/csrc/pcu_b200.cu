@@ -347,11 +347,13 @@ struct Plan {
                                                              args.cs[s].scan_state);
             cl.scan_ticket = take_strided<unsigned>(cv, 1, B, args.cs[s].scan_ticket);
         }
-        // One CTA per cloud when the counters fit in shared memory and either the clouds are small enough
-        // that five dependent launches cost more than one CTA's serial passes, or there are enough clouds
-        // to fill the machine with such CTAs.
+        // One CTA per cloud when the counters fit in shared memory and the clouds are small: five dependent
+        // launches then cost more than one CTA's serial passes (measured on B200, pair of n points: 64 vs 71 us
+        // at n = 1024, 62 vs 69 us at 4096, break-even near 12k; at 65536 one SM needs ~130 us for what the
+        // grid-wide passes do in ~50 us, and a batch of 1024 such pairs is 5 % slower, so larger clouds keep
+        // the grid-wide passes whatever the batch size).
         const bool fits = max_cap + 1 <= kSmallMaxCells && max_n <= kSmallMaxPoints;
-        one_cta_binning = fits && (sp.binning == 2 || (sp.binning == 0 && (max_n <= 16384 || 2 * B >= 128)));
+        one_cta_binning = fits && (sp.binning == 2 || (sp.binning == 0 && max_n <= 8192));
         for (int d = 0; d < sp.nsweeps; ++d)
             args.sweep[d].counters = take_strided<unsigned>(cv, 8, B, args.ss[d].counters);
         zero_begin = base ? base + zero_from : nullptr;
