@@ -79,7 +79,9 @@ typedef struct pcu_b200_nn_stats {
 typedef struct pcu_b200_options {
     int max_points_per_leaf; /* reference kwarg; only influences how exact-distance ties are ordered (default 10) */
     float cell_occupancy;    /* target dataset points per grid cell (default: 2 for k = 1, ~k/2 otherwise)        */
-    int disable_tie_replay;  /* 1: keep the (distance, lowest index) order for tied queries (diagnostic only)     */
+    int disable_tie_replay;  /* diagnostic only.  1: keep the (distance, lowest index) order for tied queries;        */
+                             /* 2: replay on full reference trees only (no pruned build); 3: pruned build with    */
+                             /* zero slack (every walk hits a stub, which exercises the full-rebuild path)        */
     int binning;             /* 0: automatic; 1: always the multi-launch grid build; 2: the one-CTA-per-cloud     */
                              /* build whenever a cloud's cell counters fit in shared memory (diagnostic only)    */
 } pcu_b200_options;

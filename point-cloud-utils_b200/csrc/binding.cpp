@@ -431,12 +431,13 @@ PYBIND11_MODULE(_pcu_internal, mod) {
         for (int i = 0; i < n; ++i) d[py::str(pcu_b200_profile_stage_name(i))] = ms[i];
         return d;
     });
-    mod.def("_set_defaults", [](float cell_occupancy, bool disable_tie_replay, int binning) {
+    mod.def("_set_defaults", [](float cell_occupancy, int disable_tie_replay, int binning) {
+        if (disable_tie_replay < 0 || disable_tie_replay > 3) throw py::value_error("disable_tie_replay must be 0 .. 3");
         if (binning < 0 || binning > 2) throw py::value_error("binning must be 0 (auto), 1 (multi-launch) or 2 (one CTA per cloud)");
         defaults().occupancy = cell_occupancy;
-        defaults().disable_replay = disable_tie_replay ? 1 : 0;
+        defaults().disable_replay = disable_tie_replay;
         defaults().binning = binning;
-    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = false, py::arg("binning") = 0);
+    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = 0, py::arg("binning") = 0);
     mod.def("_release_workspaces", []() { pool().clear(); });
     // destroy workspaces before the CUDA context goes away at interpreter exit
     py::module_::import("atexit").attr("register")(py::cpp_function([]() { pool().clear(); }));

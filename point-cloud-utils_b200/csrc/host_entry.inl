@@ -64,7 +64,7 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     if (both && out_value) PCU_CUDA(cudaMemcpyAsync(out_value, dv, sizeof(T), cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
     // Hausdorff witnesses whose neighbour was decided by tie order: replay with the reference's tree
-    if (!ws->opts.disable_tie_replay) {
+    if (ws->opts.disable_tie_replay != 1) {
         for (int s = 0; s < (both ? 2 : 1); ++s) {
             if (!out_stats[s].witness_tied) continue;
             const T* qs = s == 0 ? da : db;
@@ -125,7 +125,7 @@ int debug_kd_tree(pcu_b200_workspace* ws, const T* points, long long m, int leaf
     dpts = cv.take<T>((size_t)3 * m);
     cudaStream_t st = ws->own_stream;
     PCU_CUDA(cudaMemcpyAsync(dpts, points, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
-    const int rs = build_kd_replica<T>(rb, dpts, m, leaf, nullptr, st, g_launches);
+    const int rs = build_kd_replica<T>(rb, dpts, m, leaf, nullptr, KdPrune<T>{}, st, g_launches);
     if (rs != PCU_B200_OK) return fail(rs, "kd replica build failed: %s", cudaGetErrorString(cudaGetLastError()));
     KdCounters hc;
     PCU_CUDA(cudaMemcpyAsync(&hc, rb.counters, sizeof hc, cudaMemcpyDeviceToHost, st));

@@ -36,12 +36,13 @@ constexpr int kKdTile = kThreads * kKdItems;      // slots per scan tile
 
 template <typename T>
 struct KdNode {
-    int feat;            // split dimension; -1 = leaf; -2 = not decided yet
+    int feat;            // split dimension; -1 = leaf; -2 = not decided yet; -3 = stub (pruned build: left unsplit)
     int first, last;     // slot range [first, last) in order[]
     int kid0, kid1;
     int parent;          // parent node (-1 for the root); side: 0 = left child, 1 = right child
     int side;
     int n_less, n_less_eq;
+    unsigned mask;       // pruned build: bit j set = flagged query j may walk into this node (all ones otherwise)
     T cut;
     T div_lo, div_hi;
     T loose_lo[3], loose_hi[3];
@@ -55,6 +56,7 @@ struct KdCounters {
     int n_split;        // nodes of the current level that were split
     int done;           // set when a level split nothing
     int levels;         // levels processed (diagnostic)
+    int any_eq;         // current level: some live point equals its node's cut (sweep 2 has work to do)
 };
 
 template <typename T>
@@ -68,6 +70,7 @@ struct KdReplayBuffers {
     int* right_pos = nullptr;
     KdNode<T>* nodes = nullptr;       // 2 * capacity
     KdCounters* counters = nullptr;
+    unsigned* stub_hits = nullptr;    // searches that ran into a stub of the pruned build (-> full rebuild)
     long long* one_row = nullptr;     // scratch for the single-query (witness) replay
     T* one_dist = nullptr;
     long long* one_idx = nullptr;
@@ -82,6 +85,7 @@ struct KdReplayBuffers {
         right_pos = cv.take<int>((size_t)points);
         nodes = cv.take<KdNode<T>>((size_t)2 * points + 2);
         counters = cv.take<KdCounters>(1);
+        stub_hits = cv.take<unsigned>(1);
         one_row = cv.take<long long>(1);
         one_dist = cv.take<T>(1);
         one_idx = cv.take<long long>(1);
@@ -150,10 +154,95 @@ __device__ __forceinline__ void kd_tight_box_slot(const KdReplayBuffers<T>& b, c
     }
 }
 
+// Pruned build.  The tree is only needed by the handful of flagged queries, and a query's walk only
+// enters a far child whose bound (searchLevel's mindistsq, nanoflann.hpp:1600-1612) is at most the
+// current k-th distance.  That distance is never below its final value d_k -- which the grid search
+// already knows -- and exceeds it only early in the walk, deep in the tree.  So a node that is the FAR
+// child of its parent for every flagged query that can reach the parent, with a bound above
+// slack * d_k^2 (slack = 4), is left as an unsplit stub (its slots retire like a leaf's), unless it is small.
+// This is a heuristic, not a proof: a walk that does run into a stub reports it (kd_search_one returns
+// false) and the caller rebuilds the full tree for that call, so results never depend on the pruning.
+constexpr int kKdMaxPruneQueries = 32;   // one mask bit per flagged query; more -> full build
+constexpr int kKdSmallNode = 256;        // nodes up to this many points always follow their parent
+
+template <typename T>
+struct KdPrune {
+    const T* query = nullptr;           // the call's query cloud
+    const long long* rows = nullptr;    // flagged rows
+    const unsigned* n_rows = nullptr;
+    const T* kth = nullptr;             // the call's distance output, k per row (the fast answer's distances are final)
+    int k = 0;
+    int squared = 0;
+    int enabled = 0;
+    float slack = 4.f;                  // 0 (diagnostic): every far child is a stub, which forces the full-rebuild path
+};
+
+// (bound, per-axis offsets) searchLevel holds on arrival at `target` for query q; false if the node
+// is deeper than the walk stack (then the caller keeps the node).
+template <typename T>
+__device__ bool kd_arrival_state(const KdReplayBuffers<T>& b, int target, const T q[3], T& bound, T off[3]) {
+    using R = Real<T>;
+    int chain[96];
+    int depth = 0;
+    for (int a = target; a >= 0; a = b.nodes[a].parent) {
+        if (depth == 96) return false;
+        chain[depth++] = a;
+    }
+    const KdNode<T>& root = b.nodes[chain[depth - 1]];
+    bound = (T)0;
+    for (int d = 0; d < 3; ++d) {
+        off[d] = (T)0;
+        const T lo = unordered<T>(root.tight_lo[d]), hi = unordered<T>(root.tight_hi[d]);
+        if (q[d] < lo) { off[d] = sq_gap<T>(q[d], lo); bound = R::add(bound, off[d]); }
+        if (q[d] > hi) { off[d] = sq_gap<T>(q[d], hi); bound = R::add(bound, off[d]); }
+    }
+    for (int i = depth - 1; i > 0; --i) {
+        const KdNode<T>& nd = b.nodes[chain[i]];
+        const int ft = nd.feat;
+        const T v = q[ft];
+        const bool left_near = R::add(R::sub(v, nd.div_lo), R::sub(v, nd.div_hi)) < (T)0;
+        if (chain[i - 1] != (left_near ? nd.kid0 : nd.kid1)) {
+            const T cut = left_near ? sq_gap<T>(v, nd.div_hi) : sq_gap<T>(v, nd.div_lo);
+            bound = R::sub(R::add(bound, cut), off[ft]);
+            off[ft] = cut;
+        }
+    }
+    return true;
+}
+
+// Which flagged queries may walk into node `id` (a child whose tight box and whose sibling's are final).
+template <typename T>
+__device__ unsigned kd_node_mask(const KdReplayBuffers<T>& b, const KdPrune<T>& pr, int id) {
+    using R = Real<T>;
+    const KdNode<T>& nd = b.nodes[id];
+    const KdNode<T>& par = b.nodes[nd.parent];
+    if (par.mask == 0u || nd.last - nd.first <= kKdSmallNode) return par.mask;
+    const int ft = par.feat;
+    const T div_lo = unordered<T>(b.nodes[par.kid0].tight_hi[ft]);   // what the two children hand up (divlow / divhigh)
+    const T div_hi = unordered<T>(b.nodes[par.kid1].tight_lo[ft]);
+    unsigned mask = 0u;
+    for (unsigned rest = par.mask; rest != 0u; rest &= rest - 1u) {
+        const int j = __ffs((int)rest) - 1;
+        const long long row = pr.rows[j];
+        const T q[3] = {pr.query[3 * row], pr.query[3 * row + 1], pr.query[3 * row + 2]};
+        const T v = q[ft];
+        const bool left_near = R::add(R::sub(v, div_lo), R::sub(v, div_hi)) < (T)0;
+        if (left_near == (nd.side == 0)) { mask |= 1u << j; continue; }       // near child: entered whenever the parent is
+        const T kth = pr.kth[row * pr.k + pr.k - 1];
+        if (kth < (T)0) { mask |= 1u << j; continue; }                       // fewer than k points in the cloud: everything is visited
+        const T limit = R::mul(pr.squared ? kth : R::mul(kth, kth), (T)pr.slack);
+        T bound, off[3];
+        if (!kd_arrival_state<T>(b, nd.parent, q, bound, off)) { mask |= 1u << j; continue; }
+        const T cut = left_near ? sq_gap<T>(v, div_hi) : sq_gap<T>(v, div_lo);
+        if (R::sub(R::add(bound, cut), off[ft]) <= limit) mask |= 1u << j;
+    }
+    return mask;
+}
+
 // leaf-or-split decision + split plane of one node; also hands this node's tight extent along the
 // parent's split axis up to the parent (divlow / divhigh, nanoflann.hpp:1047-1048).
 template <typename T>
-__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap) {
+__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap, const KdPrune<T>& pr, unsigned root_mask) {
     using R = Real<T>;
     KdNode<T>& nd = b.nodes[id];
     T tlo[3], thi[3];
@@ -164,8 +253,10 @@ __device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int 
     } else {
         for (int d = 0; d < 3; ++d) { nd.loose_lo[d] = tlo[d]; nd.loose_hi[d] = thi[d]; }  // root: computeBoundingBox
     }
+    nd.mask = nd.parent < 0 ? root_mask : (root_mask == 0xffffffffu ? root_mask : kd_node_mask<T>(b, pr, id));
     const int count = nd.last - nd.first;
     if (count <= leaf_cap) { nd.feat = -1; return; }
+    if (nd.mask == 0u) { nd.feat = -3; return; }   // no flagged query comes here: stub
     // middleSplit_ (nanoflann.hpp:1061-1096)
     const T eps = (T)0.00001;
     T widest = R::sub(nd.loose_hi[0], nd.loose_lo[0]);
@@ -193,6 +284,8 @@ __device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int 
 }
 
 // sweep 1: flag = (value < cut); sweep 2: flag = (value <= cut) on the part right of n_less.
+// Bit 0 of the result is the flag; in sweep 1, bit 1 says that the value EQUALS the cut (only then does
+// sweep 2 have anything to move, see kd_build_kernel).
 template <typename T, int kSweep>
 __device__ __forceinline__ unsigned kd_flag(const KdReplayBuffers<T>& b, const T* __restrict__ pts, int s, int m) {
     if (s >= m) return 0u;    // entry m is the sentinel that carries the grand total
@@ -201,7 +294,7 @@ __device__ __forceinline__ unsigned kd_flag(const KdReplayBuffers<T>& b, const T
     const KdNode<T>& nd = b.nodes[node];
     if (nd.feat < 0) return 0u;
     const T v = pts[3 * (long long)b.order[s] + nd.feat];
-    if (kSweep == 1) return v < nd.cut ? 1u : 0u;
+    if (kSweep == 1) return (v < nd.cut ? 1u : 0u) | (v == nd.cut ? 2u : 0u);
     return (s >= nd.first + nd.n_less && v <= nd.cut) ? 1u : 0u;
 }
 
@@ -225,7 +318,8 @@ __device__ __forceinline__ void kd_partner_slot(const KdReplayBuffers<T>& b, int
     const unsigned at_lo = kd_prefix<T>(b, lo), at_last = kd_prefix<T>(b, nd.last);
     const int F = (int)(at_last - at_lo);
     if (s == nd.first) {
-        if (kSweep == 1) nd.n_less = F; else nd.n_less_eq = nd.n_less + F;
+        if (kSweep == 1) { nd.n_less = F; nd.n_less_eq = F; }   // sweep 2, when it runs, overwrites n_less_eq
+        else nd.n_less_eq = nd.n_less + F;
     }
     if (s < lo) return;
     const unsigned here = kd_prefix<T>(b, s), next = kd_prefix<T>(b, s + 1);
@@ -293,9 +387,13 @@ __device__ __forceinline__ void kd_scan_phase(cooperative_groups::grid_group& gr
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int first = tile * kKdTile + threadIdx.x * kKdItems;
         unsigned v[kKdItems];
-        unsigned sum = 0;
+        unsigned sum = 0, eq = 0;
 #pragma unroll
-        for (int k = 0; k < kKdItems; ++k) { v[k] = (first + k) < count ? kd_flag<T, kSweep>(b, pts, first + k, m) : 0u; sum += v[k]; }
+        for (int k = 0; k < kKdItems; ++k) {
+            const unsigned r = (first + k) < count ? kd_flag<T, kSweep>(b, pts, first + k, m) : 0u;
+            v[k] = r & 1u; eq |= r >> 1; sum += v[k];
+        }
+        if (kSweep == 1 && __syncthreads_or((int)eq) && threadIdx.x == 0) atomicOr(&b.counters->any_eq, 1);
         unsigned total;
         unsigned run = kd_block_exclusive_scan(sum, &total);
 #pragma unroll
@@ -324,10 +422,18 @@ __device__ __forceinline__ void kd_scan_phase(cooperative_groups::grid_group& gr
 // zero nobody needs the tree and every CTA returns immediately.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b, const T* __restrict__ pts, int m,
-                                                            int leaf_cap, const unsigned* __restrict__ gate) {
+                                                            int leaf_cap, const unsigned* __restrict__ gate, KdPrune<T> pr) {
     namespace cg = cooperative_groups;
     using R = Real<T>;
-    if (gate != nullptr && *gate == 0u) return;   // uniform over the grid
+    const unsigned gate_value = gate != nullptr ? *gate : 1u;
+    // the pruned build opens a call's replay: it clears the stub counter (even when it has nothing to do)
+    if (pr.enabled && blockIdx.x == 0 && threadIdx.x == 0) *b.stub_hits = 0u;
+    if (gate_value == 0u) return;   // uniform over the grid
+    unsigned root_mask = 0xffffffffu;
+    if (pr.enabled) {
+        const unsigned nt = *pr.n_rows;
+        if (nt < (unsigned)kKdMaxPruneQueries) root_mask = (1u << nt) - 1u;
+    }
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsize = gridDim.x * blockDim.x;
@@ -348,7 +454,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
 
     for (int level = 0; level < 4096; ++level) {
         const int lb = *(volatile int*)&b.counters->level_begin, le = *(volatile int*)&b.counters->level_end;
-        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap);
+        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap, pr, root_mask);
         grid.sync();
         // sweep 1: strictly-less-than-the-cut to the front
         kd_scan_phase<T, 1>(grid, b, pts, m);
@@ -356,12 +462,16 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
         grid.sync();
         for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 1>(b, s);
         grid.sync();
-        // sweep 2: equal-to-the-cut next
-        kd_scan_phase<T, 2>(grid, b, pts, m);
-        for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 2>(b, s);
-        grid.sync();
-        for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 2>(b, s);
-        grid.sync();
+        // sweep 2: equal-to-the-cut next.  planeSplit's second loop (nanoflann.hpp:1143-1158) moves nothing
+        // when no point of the node equals the cut (lim2 == lim1); any_eq was raised by sweep 1's scan and
+        // is stable since the barrier that ended it, so the whole grid takes the same branch.
+        if (*(volatile int*)&b.counters->any_eq != 0) {
+            kd_scan_phase<T, 2>(grid, b, pts, m);
+            for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 2>(b, s);
+            grid.sync();
+            for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 2>(b, s);
+            grid.sync();
+        }
         for (int id = lb + gtid; id < le; id += gsize) kd_children_node<T>(b, id);
         grid.sync();
         // slots move down to the child that now owns them (slots of leaves retire) and immediately
@@ -383,6 +493,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
             c.level_end = c.n_nodes;
             c.n_split = 0;
             c.levels = level + 1;
+            c.any_eq = 0;
             *b.counters = c;
         }
         grid.sync();
@@ -415,8 +526,9 @@ struct KdBest {
 
 constexpr int kKdStack = 96;
 
+// Returns false (and writes nothing) when the walk ran into a stub of the pruned build.
 template <typename T>
-__device__ void kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__ pts, const T q[3], int k, bool squared,
+__device__ bool kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__ pts, const T q[3], int k, bool squared,
                               T* out_d, long long* out_i) {
     using R = Real<T>;
     // short lists live in (L1-cached) local memory while the tree is walked; long ones in the output row
@@ -446,6 +558,7 @@ __device__ void kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__
         if (f.far && !(f.bound <= best.worst())) continue;
         for (;;) {
             const KdNode<T>& nd = b.nodes[f.node];
+            if (nd.feat == -3) return false;
             if (nd.feat < 0) {
                 const T worst_on_entry = best.worst();   // cached for the whole leaf (:1555)
                 for (int s = nd.first; s < nd.last; ++s) {
@@ -476,17 +589,21 @@ __device__ void kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__
         out_i[c] = work_i[c];
     }
     for (int c = best.have; c < k; ++c) { out_d[c] = (T)-1; out_i[c] = -1; }
+    return true;
 }
 
+// `gate` (may be null): the pass only runs when *gate != 0 (second pass after a full rebuild).
 template <typename T>
 __global__ void kd_replay_kernel(KdReplayBuffers<T> b, const T* __restrict__ query, const T* __restrict__ pts, int k,
                                  int squared, const long long* __restrict__ rows, const unsigned* __restrict__ n_rows,
-                                 T* out_dist, long long* out_idx) {
+                                 T* out_dist, long long* out_idx, const unsigned* __restrict__ gate) {
+    if (gate != nullptr && *gate == 0u) return;
     const unsigned n = *n_rows;
     for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const long long row = rows[t];
         const T q[3] = {query[3 * row], query[3 * row + 1], query[3 * row + 2]};
-        kd_search_one<T>(b, pts, q, k, squared != 0, out_dist + row * k, out_idx + row * k);
+        if (!kd_search_one<T>(b, pts, q, k, squared != 0, out_dist + row * k, out_idx + row * k) && gate == nullptr)
+            atomicAdd(b.stub_hits, 1u);
     }
 }
 
@@ -496,7 +613,7 @@ __global__ void kd_witness_kernel(KdReplayBuffers<T> b, const T* __restrict__ qu
                                   pcu_b200_nn_stats* stats) {
     const long long row = stats->argmax_query;
     const T q[3] = {query[3 * row], query[3 * row + 1], query[3 * row + 2]};
-    kd_search_one<T>(b, pts, q, 1, true, b.one_dist, b.one_idx);
+    (void)kd_search_one<T>(b, pts, q, 1, true, b.one_dist, b.one_idx);   // full tree: no stubs
     stats->argmax_data = *b.one_idx;
     stats->witness_tied = 0;
 }
@@ -513,7 +630,7 @@ __global__ void kd_witness_kernel(KdReplayBuffers<T> b, const T* __restrict__ qu
 // host synchronisation.  With a non-null `gate` the kernel is a no-op when *gate == 0.
 template <typename T>
 int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int leaf_cap, const unsigned* gate,
-                     cudaStream_t stream, std::atomic<long long>& launches) {
+                     KdPrune<T> prune, cudaStream_t stream, std::atomic<long long>& launches) {
     if (m_ll > b.capacity || m_ll >= 0x7fffffffLL) return PCU_B200_INTERNAL;
     int m = (int)m_ll;
     static int blocks_per_sm = 0, sms = 0;
@@ -528,7 +645,7 @@ int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int le
     }
     const long long want = (m_ll + kThreads - 1) / kThreads;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)blocks_per_sm * sms));
-    void* args[] = {(void*)&b, (void*)&pts, (void*)&m, (void*)&leaf_cap, (void*)&gate};
+    void* args[] = {(void*)&b, (void*)&pts, (void*)&m, (void*)&leaf_cap, (void*)&gate, (void*)&prune};
     if (cudaLaunchCooperativeKernel((void*)kd_build_kernel<T>, dim3(grid), dim3(kThreads), args, 0, stream) != cudaSuccess)
         return PCU_B200_CUDA_ERROR;
     launches.fetch_add(1, std::memory_order_relaxed);
@@ -540,11 +657,23 @@ int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int le
 template <typename T>
 int enqueue_tie_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, long long m, int k, int squared,
                        int leaf_cap, const long long* tie_list, const unsigned* tie_count, long long max_rows,
-                       T* out_dist, long long* out_idx, cudaStream_t stream, std::atomic<long long>& launches) {
-    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, tie_count, stream, launches);
+                       T* out_dist, long long* out_idx, int mode, cudaStream_t stream, std::atomic<long long>& launches) {
+    // pass 1: tree pruned to what the flagged queries can reach; pass 2 (device-gated on a walk having hit
+    // a stub, which the pruning heuristic makes rare): the full tree, every flagged row again
+    KdPrune<T> prune;
+    prune.query = query; prune.rows = tie_list; prune.n_rows = tie_count; prune.kth = out_dist;
+    prune.k = k; prune.squared = squared;
+    prune.enabled = mode == 2 ? 0 : 1;          // pcu_b200_options::disable_tie_replay: 2 = full trees only
+    prune.slack = mode == 3 ? 0.f : 4.f;        // 3 = zero slack (exercises the rebuild path)
+    int st = build_kd_replica<T>(b, dataset, m, leaf_cap, tie_count, prune, stream, launches);
     if (st != PCU_B200_OK) return st;
     const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + 127) / 128, 1184));
-    KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx);
+    KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx,
+              (const unsigned*)nullptr);
+    st = build_kd_replica<T>(b, dataset, m, leaf_cap, b.stub_hits, KdPrune<T>{}, stream, launches);
+    if (st != PCU_B200_OK) return st;
+    KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx,
+              (const unsigned*)b.stub_hits);
     return PCU_B200_OK;
 }
 
@@ -552,7 +681,7 @@ int enqueue_tie_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, 
 template <typename T>
 int enqueue_witness_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, long long m, int leaf_cap,
                            pcu_b200_nn_stats* stats, cudaStream_t stream, std::atomic<long long>& launches) {
-    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, nullptr, stream, launches);
+    const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, nullptr, KdPrune<T>{}, stream, launches);
     if (st != PCU_B200_OK) return st;
     KD_LAUNCH(kd_witness_kernel<T>, 1, 1, stream, b, query, dataset, stats);
     return PCU_B200_OK;

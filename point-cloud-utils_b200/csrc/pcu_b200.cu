@@ -490,7 +490,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     spec.occupancy = occupancy_for(ws, k);
     spec.binning = ws->opts.binning;
     spec.out_dist = out_dist; spec.out_idx = out_idx;
-    spec.replay_points = ws->opts.disable_tie_replay ? 0 : m;
+    spec.replay_points = ws->opts.disable_tie_replay == 1 ? 0 : m;
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec));
     mark(ws, 0, stream);
@@ -521,10 +521,10 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         mark(ws, 6, stream);
         mark(ws, 7, stream);
     }
-    if (!ws->opts.disable_tie_replay) {
+    if (ws->opts.disable_tie_replay != 1) {
         const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
         const int rs = enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
-                                             plan.args.sweep[0].counters + 1, n, out_dist, out_idx, stream, g_launches);
+                                             plan.args.sweep[0].counters + 1, n, out_dist, out_idx, ws->opts.disable_tie_replay, stream, g_launches);
         if (rs != PCU_B200_OK) return fail(rs, "tie replay failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     if (out_n_tied) {
@@ -722,6 +722,8 @@ int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_option
     if (!ws || !opts) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
     if (opts->max_points_per_leaf < 0) return fail(PCU_B200_INVALID_ARGUMENT, "max_points_per_leaf must be >= 0");
     if (opts->cell_occupancy < 0.f) return fail(PCU_B200_INVALID_ARGUMENT, "cell_occupancy must be >= 0");
+    if (opts->disable_tie_replay < 0 || opts->disable_tie_replay > 3)
+        return fail(PCU_B200_INVALID_ARGUMENT, "disable_tie_replay must be 0 .. 3");
     if (opts->binning < 0 || opts->binning > 2) return fail(PCU_B200_INVALID_ARGUMENT, "binning must be 0, 1 or 2");
     ws->opts = *opts;
     return PCU_B200_OK;
