@@ -42,7 +42,7 @@ struct KdNode {
     int parent;          // parent node (-1 for the root); side: 0 = left child, 1 = right child
     int side;
     int n_less, n_less_eq;
-    unsigned mask;       // pruned build: bit j set = flagged query j may walk into this node (all ones otherwise)
+    unsigned mask[4];    // pruned build: bit j set = flagged query j may walk into this node (all ones otherwise)
     T cut;
     T div_lo, div_hi;
     T loose_lo[3], loose_hi[3];
@@ -162,7 +162,8 @@ __device__ __forceinline__ void kd_tight_box_slot(const KdReplayBuffers<T>& b, c
 // slack * d_k^2 (slack = 4), is left as an unsplit stub (its slots retire like a leaf's), unless it is small.
 // This is a heuristic, not a proof: a walk that does run into a stub reports it (kd_search_one returns
 // false) and the caller rebuilds the full tree for that call, so results never depend on the pruning.
-constexpr int kKdMaxPruneQueries = 32;   // one mask bit per flagged query; more -> full build
+constexpr int kKdMaskWords = 4;
+constexpr int kKdMaxPruneQueries = 32 * kKdMaskWords;   // one mask bit per flagged query; more -> full build
 constexpr int kKdSmallNode = 256;        // nodes up to this many points always follow their parent
 
 template <typename T>
@@ -211,38 +212,48 @@ __device__ bool kd_arrival_state(const KdReplayBuffers<T>& b, int target, const 
 }
 
 // Which flagged queries may walk into node `id` (a child whose tight box and whose sibling's are final).
+// Writes the node's mask; returns whether any bit is set.
 template <typename T>
-__device__ unsigned kd_node_mask(const KdReplayBuffers<T>& b, const KdPrune<T>& pr, int id) {
+__device__ bool kd_node_mask(const KdReplayBuffers<T>& b, const KdPrune<T>& pr, int id) {
     using R = Real<T>;
-    const KdNode<T>& nd = b.nodes[id];
+    KdNode<T>& nd = b.nodes[id];
     const KdNode<T>& par = b.nodes[nd.parent];
-    if (par.mask == 0u || nd.last - nd.first <= kKdSmallNode) return par.mask;
+    if (nd.last - nd.first <= kKdSmallNode) {
+        unsigned any = 0u;
+        for (int w = 0; w < kKdMaskWords; ++w) { nd.mask[w] = par.mask[w]; any |= par.mask[w]; }
+        return any != 0u;
+    }
     const int ft = par.feat;
     const T div_lo = unordered<T>(b.nodes[par.kid0].tight_hi[ft]);   // what the two children hand up (divlow / divhigh)
     const T div_hi = unordered<T>(b.nodes[par.kid1].tight_lo[ft]);
-    unsigned mask = 0u;
-    for (unsigned rest = par.mask; rest != 0u; rest &= rest - 1u) {
-        const int j = __ffs((int)rest) - 1;
-        const long long row = pr.rows[j];
-        const T q[3] = {pr.query[3 * row], pr.query[3 * row + 1], pr.query[3 * row + 2]};
-        const T v = q[ft];
-        const bool left_near = R::add(R::sub(v, div_lo), R::sub(v, div_hi)) < (T)0;
-        if (left_near == (nd.side == 0)) { mask |= 1u << j; continue; }       // near child: entered whenever the parent is
-        const T kth = pr.kth[row * pr.k + pr.k - 1];
-        if (kth < (T)0) { mask |= 1u << j; continue; }                       // fewer than k points in the cloud: everything is visited
-        const T limit = R::mul(pr.squared ? kth : R::mul(kth, kth), (T)pr.slack);
-        T bound, off[3];
-        if (!kd_arrival_state<T>(b, nd.parent, q, bound, off)) { mask |= 1u << j; continue; }
-        const T cut = left_near ? sq_gap<T>(v, div_hi) : sq_gap<T>(v, div_lo);
-        if (R::sub(R::add(bound, cut), off[ft]) <= limit) mask |= 1u << j;
+    unsigned any = 0u;
+    for (int w = 0; w < kKdMaskWords; ++w) {
+        unsigned mask = 0u;
+        for (unsigned rest = par.mask[w]; rest != 0u; rest &= rest - 1u) {
+            const int bit = __ffs((int)rest) - 1;
+            const long long row = pr.rows[32 * w + bit];
+            const T q[3] = {pr.query[3 * row], pr.query[3 * row + 1], pr.query[3 * row + 2]};
+            const T v = q[ft];
+            const bool left_near = R::add(R::sub(v, div_lo), R::sub(v, div_hi)) < (T)0;
+            if (left_near == (nd.side == 0)) { mask |= 1u << bit; continue; }     // near child: entered whenever the parent is
+            const T kth = pr.kth[row * pr.k + pr.k - 1];
+            if (kth < (T)0) { mask |= 1u << bit; continue; }                     // fewer than k points in the cloud: everything is visited
+            const T limit = R::mul(pr.squared ? kth : R::mul(kth, kth), (T)pr.slack);
+            T bound, off[3];
+            if (!kd_arrival_state<T>(b, nd.parent, q, bound, off)) { mask |= 1u << bit; continue; }
+            const T cut = left_near ? sq_gap<T>(v, div_hi) : sq_gap<T>(v, div_lo);
+            if (R::sub(R::add(bound, cut), off[ft]) <= limit) mask |= 1u << bit;
+        }
+        nd.mask[w] = mask;
+        any |= mask;
     }
-    return mask;
+    return any != 0u;
 }
 
 // leaf-or-split decision + split plane of one node; also hands this node's tight extent along the
 // parent's split axis up to the parent (divlow / divhigh, nanoflann.hpp:1047-1048).
 template <typename T>
-__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap, const KdPrune<T>& pr, unsigned root_mask) {
+__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap, const KdPrune<T>& pr, unsigned n_flagged) {
     using R = Real<T>;
     KdNode<T>& nd = b.nodes[id];
     T tlo[3], thi[3];
@@ -253,10 +264,19 @@ __device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int 
     } else {
         for (int d = 0; d < 3; ++d) { nd.loose_lo[d] = tlo[d]; nd.loose_hi[d] = thi[d]; }  // root: computeBoundingBox
     }
-    nd.mask = nd.parent < 0 ? root_mask : (root_mask == 0xffffffffu ? root_mask : kd_node_mask<T>(b, pr, id));
+    // n_flagged == 0: full build (every mask all ones); otherwise bit j < n_flagged stands for flagged row j
+    bool wanted = true;
+    if (n_flagged == 0u) {
+        for (int w = 0; w < kKdMaskWords; ++w) nd.mask[w] = 0xffffffffu;
+    } else if (nd.parent < 0) {
+        for (int w = 0; w < kKdMaskWords; ++w)
+            nd.mask[w] = n_flagged >= 32u * (w + 1) ? 0xffffffffu : (n_flagged > 32u * w ? (1u << (n_flagged - 32u * w)) - 1u : 0u);
+    } else {
+        wanted = kd_node_mask<T>(b, pr, id);
+    }
     const int count = nd.last - nd.first;
     if (count <= leaf_cap) { nd.feat = -1; return; }
-    if (nd.mask == 0u) { nd.feat = -3; return; }   // no flagged query comes here: stub
+    if (!wanted) { nd.feat = -3; return; }   // no flagged query comes here: stub
     // middleSplit_ (nanoflann.hpp:1061-1096)
     const T eps = (T)0.00001;
     T widest = R::sub(nd.loose_hi[0], nd.loose_lo[0]);
@@ -429,10 +449,10 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
     // the pruned build opens a call's replay: it clears the stub counter (even when it has nothing to do)
     if (pr.enabled && blockIdx.x == 0 && threadIdx.x == 0) *b.stub_hits = 0u;
     if (gate_value == 0u) return;   // uniform over the grid
-    unsigned root_mask = 0xffffffffu;
+    unsigned n_flagged = 0u;   // 0: full build
     if (pr.enabled) {
         const unsigned nt = *pr.n_rows;
-        if (nt < (unsigned)kKdMaxPruneQueries) root_mask = (1u << nt) - 1u;
+        if (nt <= (unsigned)kKdMaxPruneQueries) n_flagged = nt;
     }
     cg::grid_group grid = cg::this_grid();
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,7 +474,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
 
     for (int level = 0; level < 4096; ++level) {
         const int lb = *(volatile int*)&b.counters->level_begin, le = *(volatile int*)&b.counters->level_end;
-        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap, pr, root_mask);
+        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap, pr, n_flagged);
         grid.sync();
         // sweep 1: strictly-less-than-the-cut to the front
         kd_scan_phase<T, 1>(grid, b, pts, m);

@@ -313,14 +313,14 @@ def test_both_grid_builds_give_the_reference_results(pcu, oracle, binning):
 
 @pytest.mark.parametrize("mode", [0, 2, 3])
 def test_tie_replay_modes_agree_with_reference(pcu, oracle, mode):
-    """A few queries with two exactly equidistant nearest neighbours (fewer than 32 flagged rows, so the
-    replay builds the pruned reference tree).  mode 0: pruned build; 2: full trees only; 3: pruned with
+    """A few queries with two exactly equidistant nearest neighbours (50 flagged rows: fewer than 128, so the
+    replay builds the pruned reference tree, with mask bits in more than one word).  mode 0: pruned build; 2: full trees only; 3: pruned with
     zero slack, so walks run into stubs and the device-gated full rebuild answers.  All must give the
     reference's tie order."""
     internal = pcu._pcu_internal
     rng = np.random.default_rng(808)
     data = rng.random((200000, 3), dtype=np.float32)
-    q = (np.floor(rng.random((12, 3)) * 1024) / 1024).astype(np.float32)      # multiples of 2^-10: q +- 2^-12 is exact
+    q = (np.floor(rng.random((50, 3)) * 1024) / 1024).astype(np.float32)      # multiples of 2^-10: q +- 2^-12 is exact
     delta = np.float32(2.0 ** -12)
     twins = np.concatenate([q + np.array([delta, 0, 0], np.float32), q - np.array([delta, 0, 0], np.float32),
                             q + np.array([0, delta, 0], np.float32)])
