@@ -100,6 +100,11 @@ int pcu_b200_workspace_destroy(pcu_b200_workspace* ws);
 /* Bytes of device scratch currently held. */
 int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws);
 int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts);
+/* Diagnostic: how much finer than the default the two clouds' grids of the NEXT call with the last call's
+ * shapes will be (1 = default cells per point).  The library learns this from the fill statistics each
+ * call leaves behind: surfaces and other thin point sets get finer grids from the second call on.  It
+ * changes speed only, never results. */
+int pcu_b200_workspace_grid_refinement(const pcu_b200_workspace* ws, float out_mult[2]);
 /* Per-stage device timing (diagnostic; bench.py's roofline pass).  When enabled, every device entry
  * point records CUDA events on the launching stream between its stages; after that stream has been
  * synchronised, last_profile() returns the milliseconds of the LAST call's 8 stages (descriptors,

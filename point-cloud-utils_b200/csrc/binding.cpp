@@ -418,6 +418,11 @@ PYBIND11_MODULE(_pcu_internal, mod) {
     mod.def("_device_count", []() { return pcu_b200_device_count(); });
     mod.def("_launch_count", []() { return (int64_t)pcu_b200_launch_count(); });
     mod.def("_abi_version", []() { return pcu_b200_abi_version(); });
+    mod.def("_grid_refinement", [](int device, uintptr_t stream) {
+        float m[2] = {1.f, 1.f};
+        pcu_b200_workspace_grid_refinement(pool().get(device, stream), m);
+        return py::make_tuple(m[0], m[1]);
+    }, py::arg("device") = 0, py::arg("stream") = 0);
     mod.def("_workspace_bytes", [](int device, uintptr_t stream) {
         return (int64_t)pcu_b200_workspace_bytes(pool().get(device, stream));
     });

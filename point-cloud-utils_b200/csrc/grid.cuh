@@ -299,6 +299,15 @@ __device__ __forceinline__ bool load_tile_point(const Cloud<T>& c, GridHeader<T>
     return true;
 }
 
+// How densely the non-empty cells turned out to be filled, left in host-mapped memory for the NEXT call
+// with the same shapes on this workspace (pcu_b200.cu sizes that call's grid from it: surfaces and
+// other thin sets fill few cells of a box-filling grid, each with many points).  A hint only.
+template <typename T>
+__device__ __forceinline__ void publish_grid_hint(const Cloud<T>& c, unsigned nonempty) {
+    volatile unsigned* h = c.hint_out;
+    h[0] = (unsigned)c.cell_cap; h[1] = nonempty; h[2] = (unsigned)c.n; h[3] = 1u;
+}
+
 // 3. histogram; the atomic's return value is the point's rank inside its cell.
 //    grid (ceil(max_n / kThreads), nclouds)
 template <typename T, typename CS>
@@ -361,13 +370,16 @@ __global__ void __launch_bounds__(kScanThreads) scan_lookback_kernel(const __gri
     const long long base = (long long)tile * kScanTile;
     if (base >= count) return;
     unsigned v[kScanItems];
-    unsigned s = 0;
+    unsigned s = 0, nonempty = 0;
     const long long first = base + (long long)threadIdx.x * kScanItems;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         v[k] = (first + k) < count ? c.cell_start[first + k] : 0u;
         s += v[k];
+        nonempty += v[k] != 0u;
     }
+    nonempty = __reduce_add_sync(0xffffffffu, nonempty);
+    if ((threadIdx.x & 31) == 0 && nonempty != 0u) atomicAdd(c.occupied, nonempty);
     unsigned total;
     const unsigned ex = block_exclusive_scan(s, &total);
     if (threadIdx.x < 32) {
@@ -407,6 +419,7 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(const __grid_constant
     grid_dependency_wait();
     const Cloud<T> c = clouds[blockIdx.y];
     if ((long long)blockIdx.x * kThreads >= c.n) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && c.hint_out != nullptr) publish_grid_hint<T>(c, *c.occupied);
     __shared__ GridHeader<T> g;
     __shared__ __align__(16) T tile[3 * kThreads];
     __shared__ __align__(8) unsigned long long bar;
@@ -433,8 +446,10 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bin_small_kernel(const __gri
     __shared__ T box[6];
     __shared__ GridHeader<T> hdr;
     __shared__ unsigned warp_tot[32];
+    __shared__ unsigned s_nonempty;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int ncount = c.cell_cap + 1;
+    if (t == 0) s_nonempty = 0u;
     for (int i = t; i < ncount; i += kSmallThreads) cnt[i] = 0u;
     block_bbox<T>(c.raw, 3 * c.n, 0, 1, box);
     __syncthreads();
@@ -457,7 +472,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bin_small_kernel(const __gri
     __syncthreads();
     // exclusive scan of the counters, kSmallThreads entries per round; the prefix goes to cell_start
     // and stays in shared memory as the scatter cursors
-    unsigned carry = 0;
+    unsigned carry = 0, nonempty = 0;
     for (int base = 0; base < ncount; base += kSmallThreads) {
         const int i = base + t;
         const unsigned v = i < ncount ? cnt[i] : 0u;
@@ -482,7 +497,14 @@ __global__ void __launch_bounds__(kSmallThreads, 1) bin_small_kernel(const __gri
         const unsigned ex = carry + (w ? warp_tot[w - 1] : 0u) + inc - v;
         if (i < ncount) { cnt[i] = ex; c.cell_start[i] = ex; }
         carry += warp_tot[31];
+        nonempty += v != 0u;
         __syncthreads();
+    }
+    if (c.hint_out != nullptr) {
+        nonempty = __reduce_add_sync(0xffffffffu, nonempty);
+        if (lane == 0 && nonempty != 0u) atomicAdd(&s_nonempty, nonempty);
+        __syncthreads();
+        if (t == 0) publish_grid_hint<T>(c, s_nonempty);
     }
     // scatter
     for (int first = t; first < n; first += kBatch * kSmallThreads) {

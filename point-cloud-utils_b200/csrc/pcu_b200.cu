@@ -112,7 +112,7 @@ int fail(int status, const char* fmt, ...) {
 
 // Per-field byte strides between consecutive pairs of a batch (side 0 = first cloud of each pair,
 // side 1 = second cloud; direction 0 = first -> second, direction 1 = second -> first).
-struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_state, scan_ticket, pyramid, shape; };
+struct CloudStrides { size_t raw, sorted, rank, cell_start, grid, wall_lo, wall_hi, bbox_partial, scan_state, scan_ticket, occupied, pyramid, shape; };
 struct SweepStrides { size_t out_dist, out_idx, partial, far_list, vfar_list, counters, tie_list; };
 
 template <typename U>
@@ -152,6 +152,8 @@ __global__ void descriptors_kernel(const __grid_constant__ DescriptorArgs<T> a, 
         c.bbox_partial = advance(c.bbox_partial, p * st.bbox_partial);
         c.scan_state = advance(c.scan_state, p * st.scan_state);
         c.scan_ticket = advance(c.scan_ticket, p * st.scan_ticket);
+        c.occupied = advance(c.occupied, p * st.occupied);
+        if (p != 0) c.hint_out = nullptr;   // the first pair of a batch speaks for all of them
         c.pyramid = advance(c.pyramid, p * st.pyramid);
         c.shape = advance(c.shape, p * st.shape);
         clouds[2 * p + s] = c;
@@ -189,6 +191,12 @@ struct pcu_b200_workspace {
     int sm_count = 148;
     // optional per-stage timing (bench.py's roofline pass): events recorded on the launching stream
     unsigned small_attr = 0;             // bin_small_kernel instantiations whose shared-memory limit has been raised
+    // grid-sizing feedback: the binning kernels leave {cell_cap, non-empty cells, n, valid} per cloud in this
+    // host-mapped buffer; the next call with the same shapes reads it (no synchronisation: a hint only)
+    volatile unsigned* hint_host = nullptr;
+    unsigned* hint_dev = nullptr;
+    long long hint_key[5] = {0, 0, 0, 0, 0};   // n, m, k, sizeof(T), batch of the call the hints belong to
+    float cell_mult[2] = {1.f, 1.f};           // current refinement of the two clouds' grids (cells per point x this)
     bool profiling = false;
     cudaEvent_t marks[9] = {};
     int marks_used = 0;
@@ -266,6 +274,8 @@ struct PlanSpec {
     bool want_stats = false;
     bool want_out = false;
     float occupancy = 2.f;
+    float cell_mult[2] = {1.f, 1.f};   // grid refinement from the previous call's fill statistics
+    unsigned* hint_dev = nullptr;      // 2 x 4 words of host-mapped memory, or null
     int binning = 0;                // pcu_b200_options::binning
     T* out_dist = nullptr;          // want_out (batch == 1)
     long long* out_idx = nullptr;
@@ -332,7 +342,8 @@ struct Plan {
             Cloud<T>& cl = args.cloud[s];
             cl.raw = raws[s];
             cl.n = sizes[s];
-            cl.cell_cap = cell_cap_for(sizes[s], sp.occupancy);
+            cl.cell_cap = cell_cap_for(sizes[s], sp.occupancy / sp.cell_mult[s]);
+            cl.hint_out = sp.hint_dev ? sp.hint_dev + 4 * s : nullptr;
             cl.stride = std::min(kMaxGridDim, cl.cell_cap) + 1;
             cl.bbox_blocks = (int)std::min<long long>(kMaxBBoxBlocks, std::max<long long>(1, (3 * sizes[s] + 2 * kThreads * kBBoxPerThread - 1) / (2 * kThreads * kBBoxPerThread)));
             max_bbox_blocks = std::max(max_bbox_blocks, cl.bbox_blocks);
@@ -346,6 +357,7 @@ struct Plan {
             cl.scan_state = take_strided<unsigned long long>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
                                                              args.cs[s].scan_state);
             cl.scan_ticket = take_strided<unsigned>(cv, 1, B, args.cs[s].scan_ticket);
+            cl.occupied = take_strided<unsigned>(cv, 1, B, args.cs[s].occupied);
         }
         // One CTA per cloud when the counters fit in shared memory and the clouds are small: five dependent
         // launches then cost more than one CTA's serial passes (measured on B200, pair of n points: 64 vs 71 us
@@ -417,8 +429,50 @@ int upload_descriptors(Plan<T>& plan, cudaStream_t stream) {
     return PCU_B200_OK;
 }
 
+// Grid-sizing feedback.  A grid sized for `occupancy` points per cell of the bounding BOX fills only a
+// few of its cells when the cloud is a surface (or any thin set), and those hold many points each, so
+// every query wades through long candidate runs.  The binning kernels report how many cells were
+// non-empty; when the same shapes come again on this workspace (a loss evaluated every iteration, a
+// benchmark loop) and the non-empty cells held well over the target, the grid gets more cells --
+// assuming the non-empty count grows like h^-2 (a surface), so r times fewer points per non-empty cell
+// cost r^1.5 times more cells -- up to 32 times the default; a refined grid that turns out too fine for
+// the data it now sees shrinks again the same way.  Box-filling clouds never trigger it
+// (uniform data sits at 0.9 of the threshold), results never depend on it.
 template <typename T>
-int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, const PlanSpec<T>& spec) {
+void apply_grid_feedback(pcu_b200_workspace* ws, PlanSpec<T>& spec) {
+    const long long key[5] = {spec.n, spec.m, spec.k, (long long)sizeof(T), spec.batch};
+    if (!ws->hint_host) return;
+    bool same = true;
+    for (int i = 0; i < 5; ++i) same = same && key[i] == ws->hint_key[i];
+    if (!same) {
+        for (int i = 0; i < 5; ++i) ws->hint_key[i] = key[i];
+        ws->cell_mult[0] = ws->cell_mult[1] = 1.f;
+        for (int i = 0; i < 8; ++i) ws->hint_host[i] = 0u;
+    } else {
+        const long long sizes[2] = {spec.n, spec.m};
+        for (int s = 0; s < 2; ++s) {
+            const unsigned cap = ws->hint_host[4 * s], nonempty = ws->hint_host[4 * s + 1], pts = ws->hint_host[4 * s + 2],
+                           valid = ws->hint_host[4 * s + 3];
+            if (!valid || nonempty == 0u || pts != (unsigned)sizes[s]) continue;
+            if (cap != (unsigned)cell_cap_for(sizes[s], spec.occupancy / ws->cell_mult[s])) continue;   // measured under another grid
+            const double per_cell = (double)pts / (double)nonempty;
+            const double r = per_cell / (1.3 * (double)spec.occupancy);
+            // dead band 0.5 .. 1.5; outside it the cell count moves by r^1.5 (grow) or (r / 0.8)^1.5 (shrink:
+            // the data changed under the same shapes, or the surface assumption overshot), never below the default
+            if (r > 1.5) ws->cell_mult[s] = (float)std::min(32.0, (double)ws->cell_mult[s] * r * std::sqrt(r));
+            else if (r < 0.5 && ws->cell_mult[s] > 1.f)
+                ws->cell_mult[s] = (float)std::max(1.0, (double)ws->cell_mult[s] * (r / 0.8) * std::sqrt(r / 0.8));
+            ws->hint_host[4 * s + 3] = 0u;   // consumed
+        }
+    }
+    spec.cell_mult[0] = ws->cell_mult[0];
+    spec.cell_mult[1] = ws->cell_mult[1];
+    spec.hint_dev = ws->hint_dev;
+}
+
+template <typename T>
+int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, PlanSpec<T>& spec) {
+    apply_grid_feedback(ws, spec);
     plan.layout(nullptr, spec);
     PCU_TRY(ensure_arena(ws, plan.total));
     plan.layout(ws->arena, spec);
@@ -670,6 +724,20 @@ int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
     PCU_CUDA(cudaSetDevice(device));
     cudaError_t e = cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    void* hint = nullptr;
+    if (cudaHostAlloc(&hint, 8 * sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess) {
+        std::memset(hint, 0, 8 * sizeof(unsigned));
+        void* dev_view = nullptr;
+        if (cudaHostGetDevicePointer(&dev_view, hint, 0) == cudaSuccess) {
+            ws->hint_host = (volatile unsigned*)hint;
+            ws->hint_dev = (unsigned*)dev_view;
+        } else {
+            cudaGetLastError();
+            cudaFreeHost(hint);
+        }
+    } else {
+        cudaGetLastError();   // no feedback then; everything else works
+    }
     *out_ws = ws;
     return PCU_B200_OK;
 }
@@ -680,6 +748,7 @@ int pcu_b200_workspace_destroy(pcu_b200_workspace* ws) {
     cudaDeviceSynchronize();
     if (ws->arena) cudaFree(ws->arena);
     if (ws->io) cudaFree(ws->io);
+    if (ws->hint_host) cudaFreeHost((void*)ws->hint_host);
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
     for (auto& e : ws->marks) if (e) cudaEventDestroy(e);
     delete ws;
@@ -716,6 +785,13 @@ int pcu_b200_workspace_last_profile(pcu_b200_workspace* ws, float* out_ms, int c
 const char* pcu_b200_profile_stage_name(int stage) {
     static const char* names[] = {PCU_STAGE_NAMES};
     return stage >= 0 && stage < 8 ? names[stage] : "";
+}
+
+int pcu_b200_workspace_grid_refinement(const pcu_b200_workspace* ws, float out_mult[2]) {
+    if (!ws || !out_mult) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
+    out_mult[0] = ws->cell_mult[0];
+    out_mult[1] = ws->cell_mult[1];
+    return PCU_B200_OK;
 }
 
 int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts) {

@@ -335,3 +335,44 @@ def test_tie_replay_modes_agree_with_reference(pcu, oracle, mode):
             assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0]), (mode, k)
     finally:
         internal._set_defaults()
+
+
+def _sphere(rng, n, dtype, centre=(0.5, 0.5, 0.5), radius=0.45):
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    return (v * radius + np.array(centre)).astype(dtype)
+
+
+def test_grid_refinement_for_surfaces_keeps_results(pcu, oracle):
+    """Points on a surface fill few cells of a box-filling grid; from the second call with the same shapes
+    on, the library refines the grid (feedback from the fill statistics of the previous call).  Every call,
+    refined or not, must return the reference's results; box-filling clouds must not trigger it."""
+    internal = pcu._pcu_internal
+    rng = np.random.default_rng(606)
+    x = _sphere(rng, 120000, np.float32)
+    y = _sphere(rng, 90000, np.float32, centre=(0.52, 0.5, 0.49))
+    ref_c = float(oracle.chamfer_distance(x, y))
+    ref_h = oracle.hausdorff_distance(x, y, return_index=True)
+    ref_k = oracle.k_nearest_neighbors(x, y, 4)
+    seen = []
+    for rep in range(4):
+        assert abs(float(pcu.chamfer_distance(x, y)) - ref_c) <= REL * ref_c
+        seen.append(internal._grid_refinement())
+    assert seen[0] == (1.0, 1.0) and max(seen[-1]) > 2.0, seen
+    assert pcu.hausdorff_distance(x, y, return_index=True) == ref_h
+    for rep in range(3):
+        got = pcu.k_nearest_neighbors(x, y, 4)
+        assert np.array_equal(got[1], ref_k[1]) and np.array_equal(got[0], ref_k[0])
+    assert internal._grid_refinement()[1] > 1.5
+    # box-filling clouds of the same shapes right after: the refined grid is too fine for them and shrinks
+    # back to the default over a few calls; results stay the reference's throughout
+    u = rng.random((120000, 3), dtype=np.float32)
+    w = rng.random((90000, 3), dtype=np.float32)
+    ref_k = oracle.k_nearest_neighbors(u, w, 4)
+    for rep in range(8):
+        got = pcu.k_nearest_neighbors(u, w, 4)
+        assert np.array_equal(got[1], ref_k[1]) and np.array_equal(got[0], ref_k[0])
+    assert internal._grid_refinement() == (1.0, 1.0)
+    for rep in range(3):
+        pcu.k_nearest_neighbors(u, w, 16)
+    assert internal._grid_refinement() == (1.0, 1.0)

@@ -19,8 +19,11 @@ def plane(): v = torch.rand((n, 3), generator=g, device="cuda"); v[:, 2] = 0.3 +
 def blobs(): c = torch.rand((64, 3), generator=g, device="cuda"); return c[torch.randint(0, 64, (n,), generator=g, device="cuda")] + 0.01 * torch.randn((n, 3), generator=g, device="cuda")
 for name, mk in (("uniform", lambda: torch.rand((n, 3), generator=g, device="cuda")), ("sphere", sphere), ("plane", plane), ("blobs", blobs)):
     x, y = mk(), mk()
-    for occ in (0.0, 0.25, 0.05):
-        pcu._pcu_internal._set_defaults(cell_occupancy=occ)
-        ms = timeit(lambda: pcu.chamfer_distance(x, y))
-        print("%-8s occ=%-5s chamfer 2x1e6: %.3f ms -> %.3e qpts/s" % (name, occ or "dflt", ms, 2 * n / ms * 1e3), flush=True)
-pcu._pcu_internal._set_defaults(cell_occupancy=0.0)
+    # call by call: the grid-sizing feedback refines the grid from the second call on
+    seq = []
+    for call in range(8):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); pcu.chamfer_distance(x, y); b.record(); torch.cuda.synchronize()
+        seq.append("%.3f" % a.elapsed_time(b))
+    ms = timeit(lambda: pcu.chamfer_distance(x, y))
+    print("%-8s calls %s  steady %.3f ms -> %.3e qpts/s  refinement %s" % (name, " ".join(seq), ms, 2 * n / ms * 1e3, pcu._pcu_internal._grid_refinement()), flush=True)
