@@ -165,7 +165,7 @@ struct Cloud {
     unsigned long long* scan_state;  // per scan tile: status | value (decoupled look-back), zeroed per call
     unsigned* scan_ticket;           // tile ticket, zeroed per call
     unsigned* occupied;     // number of non-empty cells (counted by the scan), zeroed per call
-    unsigned* hint_out;     // host-mapped {cell_cap, non-empty cells, n, 0} for the next call's grid sizing, or null
+    unsigned* hint_out;     // host-mapped 8 words of feedback for the next call's grid sizing (grid.cuh), or null
     unsigned* pyramid;      // cell_cap + 64: point counts of the coarser levels (built only when needed)
     PyramidShape* shape;    // written by grid_setup
     int cell_cap;           // upper bound on ncells (host-known)

@@ -302,10 +302,19 @@ __device__ __forceinline__ bool load_tile_point(const Cloud<T>& c, GridHeader<T>
 // How densely the non-empty cells turned out to be filled, left in host-mapped memory for the NEXT call
 // with the same shapes on this workspace (pcu_b200.cu sizes that call's grid from it: surfaces and
 // other thin sets fill few cells of a box-filling grid, each with many points).  A hint only.
+//   words 0..3: {cell_cap, non-empty cells, n, valid}  (binning kernels)
+//   words 4..6: {queries the 27 cells around them could not settle, queries, valid}  (first slow pass of a search
+//               against this cloud)
 template <typename T>
 __device__ __forceinline__ void publish_grid_hint(const Cloud<T>& c, unsigned nonempty) {
     volatile unsigned* h = c.hint_out;
     h[0] = (unsigned)c.cell_cap; h[1] = nonempty; h[2] = (unsigned)c.n; h[3] = 1u;
+}
+template <typename T>
+__device__ __forceinline__ void publish_far_hint(const Cloud<T>& dataset, unsigned n_far, long long n_queries) {
+    if (dataset.hint_out == nullptr) return;
+    volatile unsigned* h = dataset.hint_out;
+    h[4] = n_far; h[5] = (unsigned)n_queries; h[6] = 1u;
 }
 
 // 3. histogram; the atomic's return value is the point's rank inside its cell.

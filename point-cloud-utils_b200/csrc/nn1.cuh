@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
     const Cloud<T> dc = clouds[sw.dcloud];
     const int lane = threadIdx.x & 31;
     const unsigned warps_total = gridDim.x * (kThreads / 32);
+    if (blockIdx.x == 0 && threadIdx.x == 0) publish_far_hint<T>(dc, n_far, qc.n);
     double sum = 0.0, sumsq = 0.0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
     if (n_far > 0) {

@@ -191,12 +191,14 @@ struct pcu_b200_workspace {
     int sm_count = 148;
     // optional per-stage timing (bench.py's roofline pass): events recorded on the launching stream
     unsigned small_attr = 0;             // bin_small_kernel instantiations whose shared-memory limit has been raised
-    // grid-sizing feedback: the binning kernels leave {cell_cap, non-empty cells, n, valid} per cloud in this
+    // grid-sizing feedback: the kernels leave {cell_cap, non-empty cells, n, valid, unsettled queries, queries, valid, -}
+    // per cloud in this
     // host-mapped buffer; the next call with the same shapes reads it (no synchronisation: a hint only)
     volatile unsigned* hint_host = nullptr;
     unsigned* hint_dev = nullptr;
     long long hint_key[5] = {0, 0, 0, 0, 0};   // n, m, k, sizeof(T), batch of the call the hints belong to
     float cell_mult[2] = {1.f, 1.f};           // current refinement of the two clouds' grids (cells per point x this)
+    float cell_mult_ceiling[2] = {32.f, 32.f}; // lowered when a refinement left too many queries unsettled
     bool profiling = false;
     cudaEvent_t marks[9] = {};
     int marks_used = 0;
@@ -343,7 +345,7 @@ struct Plan {
             cl.raw = raws[s];
             cl.n = sizes[s];
             cl.cell_cap = cell_cap_for(sizes[s], sp.occupancy / sp.cell_mult[s]);
-            cl.hint_out = sp.hint_dev ? sp.hint_dev + 4 * s : nullptr;
+            cl.hint_out = sp.hint_dev ? sp.hint_dev + 8 * s : nullptr;
             cl.stride = std::min(kMaxGridDim, cl.cell_cap) + 1;
             cl.bbox_blocks = (int)std::min<long long>(kMaxBBoxBlocks, std::max<long long>(1, (3 * sizes[s] + 2 * kThreads * kBBoxPerThread - 1) / (2 * kThreads * kBBoxPerThread)));
             max_bbox_blocks = std::max(max_bbox_blocks, cl.bbox_blocks);
@@ -436,7 +438,8 @@ int upload_descriptors(Plan<T>& plan, cudaStream_t stream) {
 // benchmark loop) and the non-empty cells held well over the target, the grid gets more cells --
 // assuming the non-empty count grows like h^-2 (a surface), so r times fewer points per non-empty cell
 // cost r^1.5 times more cells -- up to 32 times the default; a refined grid that turns out too fine for
-// the data it now sees shrinks again the same way.  Box-filling clouds never trigger it
+// the data it now sees (few points per non-empty cell, or many queries left unsettled by their 27
+// cells) shrinks again.  Box-filling clouds never trigger it
 // (uniform data sits at 0.9 of the threshold), results never depend on it.
 template <typename T>
 void apply_grid_feedback(pcu_b200_workspace* ws, PlanSpec<T>& spec) {
@@ -447,22 +450,30 @@ void apply_grid_feedback(pcu_b200_workspace* ws, PlanSpec<T>& spec) {
     if (!same) {
         for (int i = 0; i < 5; ++i) ws->hint_key[i] = key[i];
         ws->cell_mult[0] = ws->cell_mult[1] = 1.f;
-        for (int i = 0; i < 8; ++i) ws->hint_host[i] = 0u;
+        ws->cell_mult_ceiling[0] = ws->cell_mult_ceiling[1] = 32.f;
+        for (int i = 0; i < 16; ++i) ws->hint_host[i] = 0u;
     } else {
         const long long sizes[2] = {spec.n, spec.m};
         for (int s = 0; s < 2; ++s) {
-            const unsigned cap = ws->hint_host[4 * s], nonempty = ws->hint_host[4 * s + 1], pts = ws->hint_host[4 * s + 2],
-                           valid = ws->hint_host[4 * s + 3];
+            volatile unsigned* h = ws->hint_host + 8 * s;
+            const unsigned cap = h[0], nonempty = h[1], pts = h[2], valid = h[3];
             if (!valid || nonempty == 0u || pts != (unsigned)sizes[s]) continue;
             if (cap != (unsigned)cell_cap_for(sizes[s], spec.occupancy / ws->cell_mult[s])) continue;   // measured under another grid
             const double per_cell = (double)pts / (double)nonempty;
             const double r = per_cell / (1.3 * (double)spec.occupancy);
-            // dead band 0.5 .. 1.5; outside it the cell count moves by r^1.5 (grow) or (r / 0.8)^1.5 (shrink:
-            // the data changed under the same shapes, or the surface assumption overshot), never below the default
-            if (r > 1.5) ws->cell_mult[s] = (float)std::min(32.0, (double)ws->cell_mult[s] * r * std::sqrt(r));
-            else if (r < 0.5 && ws->cell_mult[s] > 1.f)
-                ws->cell_mult[s] = (float)std::max(1.0, (double)ws->cell_mult[s] * (r / 0.8) * std::sqrt(r / 0.8));
-            ws->hint_host[4 * s + 3] = 0u;   // consumed
+            // share of the queries searched against this cloud that the 3 x 3 x 3 cells could not settle:
+            // many of them means the cells are too fine for where the queries are (or the clouds are far
+            // apart), and finer cells only deepen the slow passes
+            const double far_share = (h[6] && h[5]) ? (double)h[4] / (double)h[5] : 0.0;
+            double m = (double)ws->cell_mult[s];
+            if (far_share > 0.05) {
+                if (m > 1.0) ws->cell_mult_ceiling[s] = (float)std::max(1.0, 0.6 * m);   // do not come back up here
+                m *= 0.35;
+            } else if (r > 1.6) m *= r * std::sqrt(r);                             // dead band 0.8 .. 1.6
+            else if (r < 0.8) m *= (r / 0.8) * std::sqrt(r / 0.8);
+            m = std::min((double)ws->cell_mult_ceiling[s], m);
+            ws->cell_mult[s] = m < 1.5 ? 1.f : (float)m;
+            h[3] = 0u; h[6] = 0u;   // consumed
         }
     }
     spec.cell_mult[0] = ws->cell_mult[0];
@@ -725,8 +736,8 @@ int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
     cudaError_t e = cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     void* hint = nullptr;
-    if (cudaHostAlloc(&hint, 8 * sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess) {
-        std::memset(hint, 0, 8 * sizeof(unsigned));
+    if (cudaHostAlloc(&hint, 16 * sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess) {
+        std::memset(hint, 0, 16 * sizeof(unsigned));
         void* dev_view = nullptr;
         if (cudaHostGetDevicePointer(&dev_view, hint, 0) == cudaSuccess) {
             ws->hint_host = (volatile unsigned*)hint;

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kThreads) knn_warp_kernel(const __grid_constan
     const Cloud<T> dc = clouds[sw.dcloud];
     const int lane = threadIdx.x & 31;
     const unsigned n_far = sw.counters[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) publish_far_hint<T>(dc, n_far, qc.n);
     if (n_far > 0) {
         const GridHeader<T> g = *dc.grid;
         const unsigned warps_total = gridDim.x * (kThreads / 32);
