@@ -120,29 +120,38 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
         const Pt<T> q = load_pt<T>(qc.sorted + t);
         row = (long long)q.i;
         const int st = g.stride;
-        const T* lo_x = dc.wall_lo;           const T* hi_x = dc.wall_hi;
-        const T* lo_y = dc.wall_lo + st;      const T* hi_y = dc.wall_hi + st;
-        const T* lo_z = dc.wall_lo + 2 * st;  const T* hi_z = dc.wall_hi + 2 * st;
         const int cx = cell_of<T>(q.x, g.origin[0], g.inv_h, g.dim[0]);
         const int cy = cell_of<T>(q.y, g.origin[1], g.inv_h, g.dim[1]);
         const int cz = cell_of<T>(q.z, g.origin[2], g.inv_h, g.dim[2]);
         const int xa = max(cx - 1, 0), xb = min(cx + 1, g.dim[0] - 1);
         // gaps to the walls of the query's own cell along y and z
-        const T gy[3] = {(T)0, sq_gap<T>(q.y, __ldg(lo_y + cy)), sq_gap<T>(q.y, __ldg(hi_y + cy + 1))};
-        const T gz[3] = {(T)0, sq_gap<T>(q.z, __ldg(lo_z + cz)), sq_gap<T>(q.z, __ldg(hi_z + cz + 1))};
-        // (dy, dz) as indices into {0: same, 1: minus one, 2: plus one}; nearest rows first
+        // wall tables indexed with unsigned 32-bit offsets off the two base pointers (axis a starts at a * st)
+        const T* __restrict__ wl = dc.wall_lo;
+        const T* __restrict__ wh = dc.wall_hi;
+        const unsigned ust = (unsigned)st;
+        const T gy[3] = {(T)0, sq_gap<T>(q.y, __ldg(wl + (ust + (unsigned)cy))), sq_gap<T>(q.y, __ldg(wh + (ust + (unsigned)cy + 1u)))};
+        const T gz[3] = {(T)0, sq_gap<T>(q.z, __ldg(wl + (2u * ust + (unsigned)cz))), sq_gap<T>(q.z, __ldg(wh + (2u * ust + (unsigned)cz + 1u)))};
+        // (dy, dz) as indices into {0: same, 1: minus one, 2: plus one}; nearest rows first.  All index
+        // arithmetic in unsigned 32 bits off one centre-row index (one IMAD.WIDE per load instead of a
+        // 64-bit add chain), the in-range tests once per direction instead of once per row.
         const int order_y[9] = {0, 1, 2, 0, 0, 1, 2, 1, 2};
         const int order_z[9] = {0, 0, 0, 1, 2, 1, 1, 2, 2};
+        const unsigned d0 = (unsigned)g.dim[0], slab = d0 * (unsigned)g.dim[1];
+        const unsigned centre = ((unsigned)cz * (unsigned)g.dim[1] + (unsigned)cy) * d0;
+        const bool ok_y[3] = {true, cy > 0, cy + 1 < g.dim[1]};
+        const bool ok_z[3] = {true, cz > 0, cz + 1 < g.dim[2]};
+        const unsigned off_y[3] = {0u, 0u - d0, d0};
+        const unsigned off_z[3] = {0u, 0u - slab, slab};
+        const unsigned* __restrict__ cs = dc.cell_start;
+        const unsigned first_x = (unsigned)xa, past_x = (unsigned)xb + 1u;
 #pragma unroll
         for (int s = 0; s < 9; ++s) {
             const int oy = order_y[s], oz = order_z[s];
-            const int y = cy + (oy == 1 ? -1 : (oy == 2 ? 1 : 0));
-            const int z = cz + (oz == 1 ? -1 : (oz == 2 ? 1 : 0));
+            const unsigned base = centre + off_y[oy] + off_z[oz];
             unsigned a = 0, b = 0;
-            if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
-                const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-                a = __ldg(dc.cell_start + base + xa);
-                b = __ldg(dc.cell_start + base + xb + 1);
+            if (ok_y[oy] && ok_z[oz]) {
+                a = __ldg(cs + (base + first_x));
+                b = __ldg(cs + (base + past_x));
             }
             rows.begin[s][tid] = a;
             rows.end[s][tid] = b;
@@ -184,12 +193,12 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
         }
         const int ya = max(cy - 1, 0), yb = min(cy + 1, g.dim[1] - 1);
         const int za = max(cz - 1, 0), zb = min(cz + 1, g.dim[2] - 1);
-        T lb = sq_gap<T>(q.x, __ldg(lo_x + xa));
-        lb = R::vmin(lb, sq_gap<T>(q.x, __ldg(hi_x + xb + 1)));
-        lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(lo_y + ya)));
-        lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(hi_y + yb + 1)));
-        lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(lo_z + za)));
-        lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(hi_z + zb + 1)));
+        T lb = sq_gap<T>(q.x, __ldg(wl + (unsigned)xa));
+        lb = R::vmin(lb, sq_gap<T>(q.x, __ldg(wh + ((unsigned)xb + 1u))));
+        lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(wl + (ust + (unsigned)ya))));
+        lb = R::vmin(lb, sq_gap<T>(q.y, __ldg(wh + (ust + (unsigned)yb + 1u))));
+        lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(wl + (2u * ust + (unsigned)za))));
+        lb = R::vmin(lb, sq_gap<T>(q.z, __ldg(wh + (2u * ust + (unsigned)zb + 1u))));
         settled = best.d < lb;
         if (!settled) sw.far_list[atomicAdd(sw.counters, 1u)] = (unsigned)t;
     }

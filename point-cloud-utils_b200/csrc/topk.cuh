@@ -196,16 +196,23 @@ __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const __grid_const
     const T gz[3] = {(T)0, sq_gap<T>(q.z, __ldg(lo_z + cz)), sq_gap<T>(q.z, __ldg(hi_z + cz + 1))};
     const int order_y[9] = {0, 1, 2, 0, 0, 1, 2, 1, 2};
     const int order_z[9] = {0, 0, 0, 1, 2, 1, 1, 2, 2};
+    // unsigned 32-bit index arithmetic off the centre row, range tests once per direction (as in nn1_kernel)
+    const unsigned d0 = (unsigned)g.dim[0], slab = d0 * (unsigned)g.dim[1];
+    const unsigned centre = ((unsigned)cz * (unsigned)g.dim[1] + (unsigned)cy) * d0;
+    const bool ok_y[3] = {true, cy > 0, cy + 1 < g.dim[1]};
+    const bool ok_z[3] = {true, cz > 0, cz + 1 < g.dim[2]};
+    const unsigned off_y[3] = {0u, 0u - d0, d0};
+    const unsigned off_z[3] = {0u, 0u - slab, slab};
+    const unsigned* __restrict__ cs = dc.cell_start;
+    const unsigned first_x = (unsigned)xa, past_x = (unsigned)xb + 1u;
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
         const int oy = order_y[s], oz = order_z[s];
-        const int y = cy + (oy == 1 ? -1 : (oy == 2 ? 1 : 0));
-        const int z = cz + (oz == 1 ? -1 : (oz == 2 ? 1 : 0));
+        const unsigned base = centre + off_y[oy] + off_z[oz];
         unsigned a = 0, b = 0;
-        if (y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
-            const unsigned base = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-            a = __ldg(dc.cell_start + base + xa);
-            b = __ldg(dc.cell_start + base + xb + 1);
+        if (ok_y[oy] && ok_z[oz]) {
+            a = __ldg(cs + (base + first_x));
+            b = __ldg(cs + (base + past_x));
         }
         rows.begin[s][tid] = a;
         rows.end[s][tid] = b;
