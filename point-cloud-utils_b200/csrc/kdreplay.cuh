@@ -679,17 +679,21 @@ int enqueue_tie_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, 
                        int leaf_cap, const long long* tie_list, const unsigned* tie_count, long long max_rows,
                        T* out_dist, long long* out_idx, int mode, cudaStream_t stream, std::atomic<long long>& launches) {
     // pass 1: tree pruned to what the flagged queries can reach; pass 2 (device-gated on a walk having hit
-    // a stub, which the pruning heuristic makes rare): the full tree, every flagged row again
+    // a stub, which the pruning heuristic makes rare): the full tree, every flagged row again.
+    // k = 1 calls (exact ties are rare there and the call is short) skip the pruning and with it the two
+    // gated launches of pass 2, which cost ~15 us even when they have nothing to do.
+    const bool pruned = mode != 2 && (k > 1 || mode == 3);
     KdPrune<T> prune;
     prune.query = query; prune.rows = tie_list; prune.n_rows = tie_count; prune.kth = out_dist;
     prune.k = k; prune.squared = squared;
-    prune.enabled = mode == 2 ? 0 : 1;          // pcu_b200_options::disable_tie_replay: 2 = full trees only
+    prune.enabled = pruned ? 1 : 0;             // pcu_b200_options::disable_tie_replay: 2 = full trees only
     prune.slack = mode == 3 ? 0.f : 4.f;        // 3 = zero slack (exercises the rebuild path)
     int st = build_kd_replica<T>(b, dataset, m, leaf_cap, tie_count, prune, stream, launches);
     if (st != PCU_B200_OK) return st;
     const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + 127) / 128, 1184));
     KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx,
               (const unsigned*)nullptr);
+    if (!pruned) return PCU_B200_OK;
     st = build_kd_replica<T>(b, dataset, m, leaf_cap, b.stub_hits, KdPrune<T>{}, stream, launches);
     if (st != PCU_B200_OK) return st;
     KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx,
