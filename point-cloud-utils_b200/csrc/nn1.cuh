@@ -15,11 +15,15 @@ constexpr int kMaxRing = 2;   // rings the in-kernel slow path walks before a qu
 // Per-thread table of the 9 rows (fixed y, z; three x-adjacent cells = one contiguous run of the
 // sorted dataset) of a query's 3 x 3 x 3 neighbourhood, nearest rows first.  Indexed [row][thread]
 // so that lanes hit distinct banks whatever row each lane is currently on.
+// The query's own row (bound 0, always scanned first) stays in registers; the table holds the other
+// eight.  That keeps the fp32 sweep at 25.9 KB of shared memory per CTA: six CTAs then fit the 164 KB
+// carve-out instead of needing the 196 KB one, which leaves 92 KB instead of 60 KB of the SM's 256 KB
+// to the L1 that serves the candidate loads.
 template <typename T>
 struct RowTable {
-    unsigned begin[9][kThreads];
-    unsigned end[9][kThreads];
-    T bound[9][kThreads];
+    unsigned begin[8][kThreads];
+    unsigned end[8][kThreads];
+    T bound[8][kThreads];
 };
 
 // Merges the running best of two lanes (after each lane has scanned disjoint cells).
@@ -98,7 +102,7 @@ __device__ __forceinline__ bool warp_ring_search(const GridHeader<T>& g, const C
 //   than the extra launch -- measured).
 // grid (ceil(max_n / kThreads), nsweeps).
 template <typename T, typename CS, typename SS, bool kOut, bool kStats>
-__global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 6 : 4) nn1_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
     grid_dependency_wait();
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
         const unsigned off_z[3] = {0u, 0u - slab, slab};
         const unsigned* __restrict__ cs = dc.cell_start;
         const unsigned first_x = (unsigned)xa, past_x = (unsigned)xb + 1u;
+        unsigned j = 0, e = 0;
 #pragma unroll
         for (int s = 0; s < 9; ++s) {
             const int oy = order_y[s], oz = order_z[s];
@@ -153,12 +158,14 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
                 a = __ldg(cs + (base + first_x));
                 b = __ldg(cs + (base + past_x));
             }
-            rows.begin[s][tid] = a;
-            rows.end[s][tid] = b;
-            rows.bound[s][tid] = R::add(gy[oy], gz[oz]);
+            if (s == 0) { j = a; e = b; }
+            else {
+                rows.begin[s - 1][tid] = a;
+                rows.end[s - 1][tid] = b;
+                rows.bound[s - 1][tid] = R::add(gy[oy], gz[oz]);
+            }
         }
         int r = 0;
-        unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
         for (;;) {
             // Every trip first steps to the next row if the current run is exhausted (predicated; a pruned
             // row leaves the lane idle for this trip) and THEN evaluates candidates, so the lanes of a
@@ -168,8 +175,8 @@ __global__ void __launch_bounds__(kThreads) nn1_kernel(const __grid_constant__ C
             if (j >= e && r < 8) {
                 ++r;
                 // a row whose bound exceeds the current best only holds strictly farther points
-                const bool keep = !(rows.bound[r][tid] > best.d);
-                const unsigned nb = rows.begin[r][tid], ne = rows.end[r][tid];
+                const bool keep = !(rows.bound[r - 1][tid] > best.d);
+                const unsigned nb = rows.begin[r - 1][tid], ne = rows.end[r - 1][tid];
                 j = keep ? nb : 0u;
                 e = keep ? ne : 0u;
             }

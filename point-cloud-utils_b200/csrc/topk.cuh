@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const __grid_const
     const unsigned off_z[3] = {0u, 0u - slab, slab};
     const unsigned* __restrict__ cs = dc.cell_start;
     const unsigned first_x = (unsigned)xa, past_x = (unsigned)xb + 1u;
+    unsigned j = 0, e = 0;   // the own row's run; the other eight go to the table
 #pragma unroll
     for (int s = 0; s < 9; ++s) {
         const int oy = order_y[s], oz = order_z[s];
@@ -214,9 +215,12 @@ __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const __grid_const
             a = __ldg(cs + (base + first_x));
             b = __ldg(cs + (base + past_x));
         }
-        rows.begin[s][tid] = a;
-        rows.end[s][tid] = b;
-        rows.bound[s][tid] = R::add(gy[oy], gz[oz]);
+        if (s == 0) { j = a; e = b; }
+        else {
+            rows.begin[s - 1][tid] = a;
+            rows.end[s - 1][tid] = b;
+            rows.bound[s - 1][tid] = R::add(gy[oy], gz[oz]);
+        }
     }
     ListKey<T> list[K];
 #pragma unroll
@@ -255,7 +259,6 @@ __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const __grid_const
         if (__any_sync(__activemask(), parked == kPark)) insert_round();
     };
     int r = 0;
-    unsigned j = rows.begin[0][tid], e = rows.end[0][tid];
     for (;;) {
         if (j < e) {
             // two candidates per step: both loads are in flight before either distance is needed
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(kThreads) knn_thread_kernel(const __grid_const
         } else {
             if (++r >= 9) break;
             // skip a row only if all of it is strictly farther than the current k-th distance
-            if (!(rows.bound[r][tid] > list[K - 1].dist())) { j = rows.begin[r][tid]; e = rows.end[r][tid]; }
+            if (!(rows.bound[r - 1][tid] > list[K - 1].dist())) { j = rows.begin[r - 1][tid]; e = rows.end[r - 1][tid]; }
         }
     }
     while (parked > 0) insert_round();
