@@ -216,11 +216,17 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 6 : 4) nn1_kernel(c
 }
 
 template <typename T> __device__ void build_pyramid(const Cloud<T>& dc);   // pyramid.cuh
+template <typename T> struct Cloud;
+template <typename T> __device__ void conclude_sweep(const Sweep<T>& sw, const Cloud<T>& qc, const Cloud<T>& dc, int nparts);   // pyramid.cuh
+template <typename T> __device__ __forceinline__ SweepPartial<T> load_partial(const SweepPartial<T>* src);
 
 // Slow pass for the queries the 3 x 3 x 3 neighbourhood could not settle (empty surroundings): one
 // WARP per query (warp_ring_search); what even kMaxRing rings cannot settle goes to the very-far list.
-// The CTA that finishes last builds the dataset's occupancy pyramid if that list is not empty, so the
-// pyramid pass that follows needs no launch of its own for it.
+// Its CTAs also fold the main pass's per-block statistics partials into their own (slot s belongs to
+// CTA s mod gridDim), so the CTA that finishes last has only far_blocks partials left to combine: if the
+// very-far list is empty -- the rule on overlapping clouds -- it concludes the sweep right here
+// (statistics record, Hausdorff witness, Chamfer value; no further launch has anything to do);
+// otherwise it builds the dataset's occupancy pyramid and the pyramid pass concludes.
 // grid (sw.far_blocks, nsweeps), warp-stride loop over the far list.
 template <typename T, typename CS, typename SS, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
@@ -245,7 +251,16 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
             finish_query1<T, kOut, kStats>(sw, ok && lane == 0, best, (long long)q.i, qt, sum, sumsq, mc);
         }
     }
-    if (kStats) block_reduce_stats<T>(sum, sumsq, mc, sw.partial + sw.main_blocks + blockIdx.x);
+    if (kStats) {
+        const int main_used = (int)((qc.n + kThreads - 1) / kThreads);
+        for (int s = blockIdx.x + threadIdx.x * gridDim.x; s < main_used; s += gridDim.x * blockDim.x) {
+            const SweepPartial<T> p = load_partial<T>(sw.partial + s);
+            sum += p.sum; sumsq += p.sumsq;
+            MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.pos = p.arg_pos;
+            take_max<T>(mc, c);
+        }
+        block_reduce_stats<T>(sum, sumsq, mc, sw.partial + sw.main_blocks + blockIdx.x);
+    }
     __shared__ bool s_last;
     __syncthreads();   // every warp of this CTA has made its very-far appends before the CTA draws its ticket
     if (threadIdx.x == 0) {
@@ -256,6 +271,7 @@ __global__ void __launch_bounds__(kThreads) nn1_far_kernel(const __grid_constant
     if (s_last) {
         __threadfence();
         if (*(volatile unsigned*)(sw.counters + 2) > 0) build_pyramid<T>(dc);
+        else if (kStats) conclude_sweep<T>(sw, qc, dc, sw.far_blocks);
     }
 }
 
@@ -268,11 +284,10 @@ __device__ __forceinline__ SweepPartial<T> load_partial(const SweepPartial<T>* s
     return p;
 }
 
-// Combines the partials of the two slow passes (the pyramid pass has already folded the main pass's
-// partials into its own) into the sweep's pcu_b200_nn_stats.  Called by ONE CTA.
+// Combines the first `total` partials of the slow passes (far pass, which carries the main pass | pyramid
+// pass) into one.  Called by ONE CTA.
 template <typename T>
-__device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, SweepPartial<T>* result /* shared */) {
-    const int total = 2 * sw.far_blocks;   // far pass | pyramid pass (which carries the main pass)
+__device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, SweepPartial<T>* result /* shared */, int total) {
     double sum = 0.0, sumsq = 0.0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
     for (int s = threadIdx.x; s < total; s += blockDim.x) {

@@ -111,7 +111,64 @@ __device__ __forceinline__ void load_shapes(const Cloud<T>& dc, GridHeader<T>& g
     __syncthreads();
 }
 
-// k = 1: one thread per very-far query.
+// Last step of a statistics sweep, run by ONE CTA once every partial of the sweep is in memory: folds the
+// `nparts` per-CTA partials of the slow passes (which carry the main pass's partials, folded in by
+// nn1_far_kernel) into the caller's pcu_b200_nn_stats, recovers the Hausdorff witness -- the neighbour of
+// the one query that attains the maximum, and whether it was decided by tie order: a single warp repeats
+// that query's search with full bookkeeping -- and, for a bidirectional call, lets the sweep that
+// finishes second write the pair's Chamfer value.
+template <typename T>
+__device__ void conclude_sweep(const Sweep<T>& sw, const Cloud<T>& qc, const Cloud<T>& dc, int nparts) {
+    using R = Real<T>;
+    __shared__ SweepPartial<T> result;
+    finalize_sweep<T>(sw, &result, nparts);
+    __shared__ GridHeader<T> wg;
+    __shared__ PyramidShape wps;
+    if (threadIdx.x == 0) wg = *dc.grid;
+    __syncthreads();
+    if (threadIdx.x < 32 && result.max_d2 >= (T)0) {
+        const Pt<T> wq = load_pt<T>(qc.sorted + result.arg_pos);
+        Best1<T> wb; wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
+        const bool ok = warp_ring_search<T>(wg, dc, wq, threadIdx.x, wb);
+        if (!ok) {   // beyond the rings: the pyramid exists (this query was on the very-far list)
+            wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
+            for (int w = threadIdx.x; w < (int)(sizeof(PyramidShape) / sizeof(int)); w += 32)
+                reinterpret_cast<int*>(&wps)[w] = reinterpret_cast<const int*>(dc.shape)[w];
+            __syncwarp();
+            if (threadIdx.x == 0)
+                pyramid_descend<T>(wg, wps, dc, wq, [&]() { return wb.d; },
+                                   [&](unsigned a, unsigned b) { scan_run1<T>(dc.sorted, a, b, wq.x, wq.y, wq.z, wb); });
+        }
+        if (threadIdx.x == 0) {
+            pcu_b200_nn_stats st;
+            st.sum_dist = result.sum;
+            st.sum_sq_dist = result.sumsq;
+            st.max_sq_dist = (double)result.max_d2;
+            st.argmax_query = (long long)result.arg_q;
+            st.argmax_data = wb.i != no_index<T>() ? (long long)wb.i : -1;
+            st.n_queries = qc.n;
+            st.n_tied = -1;   // not tracked by the statistics-only sweep
+            st.n_far = (long long)sw.counters[0];
+            st.witness_tied = wb.tie ? 1 : 0;
+            *sw.stats = st;
+        }
+    }
+    __syncthreads();
+    if (sw.value_out != nullptr && threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(sw.pair_ticket, 1u) == 1u) {
+            __threadfence();
+            const volatile pcu_b200_nn_stats* ps = sw.pair_stats;
+            pcu_b200_nn_stats a, b;
+            a.sum_dist = ps[0].sum_dist; a.n_queries = ps[0].n_queries;
+            b.sum_dist = ps[1].sum_dist; b.n_queries = ps[1].n_queries;
+            *sw.value_out = chamfer_of<T>(a, b);
+        }
+    }
+}
+
+// k = 1: one thread per very-far query.  Nothing to do (and nothing done: the far pass has already
+// concluded the sweep) when the very-far list is empty, which is the rule on overlapping clouds.
 // grid (sw.far_blocks, nsweeps), thread-stride loop over the very-far list.
 template <typename T, typename CS, typename SS, bool kOut, bool kStats>
 __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constant__ CS clouds, const __grid_constant__ SS sweeps) {
@@ -119,11 +176,12 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
     using R = Real<T>;
     const Sweep<T> sw = sweeps[blockIdx.y];
     const unsigned n_vfar = sw.counters[2];
+    if (n_vfar == 0) return;
     const Cloud<T> qc = clouds[sw.qcloud];
     const Cloud<T> dc = clouds[sw.dcloud];
     double sum = 0.0, sumsq = 0.0;
     MaxCand<T> mc; mc.d2 = (T)-1; mc.q = 0xffffffffu; mc.pos = 0u;
-    if (n_vfar > 0) {
+    {
         __shared__ GridHeader<T> g;
         __shared__ PyramidShape ps;
         load_shapes<T>(dc, g, ps);
@@ -137,20 +195,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
         }
     }
     if (kStats) {
-        // every CTA of this pass first folds its share of the main pass's per-block partials (slot s
-        // belongs to CTA s mod gridDim) into its own accumulators, so the CTA that finishes last only
-        // has the 2 * far_blocks partials of the slow passes left to combine
-        const int main_used = (int)((qc.n + kThreads - 1) / kThreads);
-        for (int s = blockIdx.x + threadIdx.x * gridDim.x; s < main_used; s += gridDim.x * blockDim.x) {
-            const SweepPartial<T> p = load_partial<T>(sw.partial + s);
-            sum += p.sum; sumsq += p.sumsq;
-            MaxCand<T> c; c.d2 = p.max_d2; c.q = p.arg_q; c.pos = p.arg_pos;
-            take_max<T>(mc, c);
-        }
         block_reduce_stats<T>(sum, sumsq, mc, sw.partial + sw.main_blocks + sw.far_blocks + blockIdx.x);
-        // The CTA that finishes last folds all partials of this sweep (main pass + this pass) into the
-        // caller's statistics record; for a bidirectional call the sweep that finishes second also
-        // writes the Chamfer value.  No separate finalize launch.
         __shared__ bool s_last;
         if (threadIdx.x == 0) {
             __threadfence();
@@ -159,53 +204,7 @@ __global__ void __launch_bounds__(kThreads) nn1_vfar_kernel(const __grid_constan
         __syncthreads();
         if (s_last) {
             __threadfence();
-            __shared__ SweepPartial<T> result;
-            finalize_sweep<T>(sw, &result);
-            // Hausdorff witness: the neighbour of the one query that attains the maximum (and whether it
-            // was decided by tie order) -- a single warp repeats that query's search with full bookkeeping
-            __shared__ GridHeader<T> wg;
-            __shared__ PyramidShape wps;
-            if (threadIdx.x == 0) wg = *dc.grid;
-            __syncthreads();
-            if (threadIdx.x < 32 && result.max_d2 >= (T)0) {
-                const Pt<T> wq = load_pt<T>(qc.sorted + result.arg_pos);
-                Best1<T> wb; wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
-                const bool ok = warp_ring_search<T>(wg, dc, wq, threadIdx.x, wb);
-                if (!ok) {   // beyond the rings: the pyramid exists (this query was on the very-far list)
-                    wb.d = R::inf(); wb.i = no_index<T>(); wb.tie = false;
-                    for (int w = threadIdx.x; w < (int)(sizeof(PyramidShape) / sizeof(int)); w += 32)
-                        reinterpret_cast<int*>(&wps)[w] = reinterpret_cast<const int*>(dc.shape)[w];
-                    __syncwarp();
-                    if (threadIdx.x == 0)
-                        pyramid_descend<T>(wg, wps, dc, wq, [&]() { return wb.d; },
-                                           [&](unsigned a, unsigned b) { scan_run1<T>(dc.sorted, a, b, wq.x, wq.y, wq.z, wb); });
-                }
-                if (threadIdx.x == 0) {
-                    pcu_b200_nn_stats st;
-                    st.sum_dist = result.sum;
-                    st.sum_sq_dist = result.sumsq;
-                    st.max_sq_dist = (double)result.max_d2;
-                    st.argmax_query = (long long)result.arg_q;
-                    st.argmax_data = wb.i != no_index<T>() ? (long long)wb.i : -1;
-                    st.n_queries = qc.n;
-                    st.n_tied = -1;   // not tracked by the statistics-only sweep
-                    st.n_far = (long long)sw.counters[0];
-                    st.witness_tied = wb.tie ? 1 : 0;
-                    *sw.stats = st;
-                }
-            }
-            __syncthreads();
-            if (sw.value_out != nullptr && threadIdx.x == 0) {
-                __threadfence();
-                if (atomicAdd(sw.pair_ticket, 1u) == 1u) {
-                    __threadfence();
-                    const volatile pcu_b200_nn_stats* ps = sw.pair_stats;
-                    pcu_b200_nn_stats a, b;
-                    a.sum_dist = ps[0].sum_dist; a.n_queries = ps[0].n_queries;
-                    b.sum_dist = ps[1].sum_dist; b.n_queries = ps[1].n_queries;
-                    *sw.value_out = chamfer_of<T>(a, b);
-                }
-            }
+            conclude_sweep<T>(sw, qc, dc, 2 * sw.far_blocks);   // far pass (with the main pass folded in) | this pass
         }
     }
 }
