@@ -163,7 +163,7 @@ struct Cloud {
     T* wall_hi;             // 3 * stride
     T* bbox_partial;        // bbox_blocks * 6
     unsigned long long* scan_state;  // per scan tile: status | value (decoupled look-back), zeroed per call
-    unsigned* scan_ticket;           // tile ticket, zeroed per call
+    unsigned* scan_ticket;           // [0] scan tile ticket, [1] finished bbox CTAs; zeroed per call
     unsigned* occupied;     // number of non-empty cells (counted by the scan), zeroed per call
     unsigned* hint_out;     // host-mapped 8 words of feedback for the next call's grid sizing (grid.cuh), or null
     unsigned* pyramid;      // cell_cap + 64: point counts of the coarser levels (built only when needed)

@@ -71,17 +71,62 @@ __device__ __forceinline__ void block_bbox(const T* __restrict__ raw, long long 
     }
 }
 
-//    partial boxes of a large cloud: grid (max bbox_blocks, nclouds)
+//    partial boxes of a large cloud: grid (max bbox_blocks, nclouds).  The CTA of a cloud that finishes
+//    last (ticket in scan_ticket[1]) folds the partial boxes and sets up the grid (2. below), so the
+//    grid needs no launch of its own.
+template <typename T> __device__ void grid_setup_body(const Cloud<T>& c, const T* box, GridHeader<T>& hdr);
 template <typename T, typename CS>
 __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_constant__ CS clouds) {
     grid_dependency_wait();
     static_assert(kThreads % 3 == 1, "block_bbox relies on blockDim = 1 (mod 3)");
+    using R = Real<T>;
     const Cloud<T> c = clouds[blockIdx.y];
     if ((int)blockIdx.x >= c.bbox_blocks) return;
     block_bbox<T>(c.raw, 3 * c.n, blockIdx.x, c.bbox_blocks, c.bbox_partial + blockIdx.x * 6);
+    if (threadIdx.x < 6) __threadfence();   // the six writers publish their words before the CTA draws its ticket
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(c.scan_ticket + 1, 1u) == (unsigned)c.bbox_blocks - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ T box[6];
+    __shared__ T red[kThreads / 32][6];
+    __shared__ GridHeader<T> hdr;
+    {   // fold the partial boxes (written by other CTAs of this launch: read around L1)
+        T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
+        for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = R::vmin(lo[a], __ldcg(c.bbox_partial + i * 6 + a));
+                hi[a] = R::vmax(hi[a], __ldcg(c.bbox_partial + i * 6 + 3 + a));
+            }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+                hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+            }
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            T v = red[0][threadIdx.x];
+            for (int i = 1; i < kThreads / 32; ++i)
+                v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
+            box[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+    grid_setup_body<T>(c, box, hdr);
 }
 
-// ---------------------------------------------------------------------------------------------
 // 2. grid shape + wall tables.  grid_setup_body: block-wide; `box` (shared, 6 values, already visible to
 //    the block) -> `hdr` (shared) plus the header, pyramid shape and wall tables in device memory.
 template <typename T>
@@ -196,46 +241,6 @@ __device__ void grid_setup_body(const Cloud<T>& c, const T* box, GridHeader<T>& 
         c.wall_lo[a * stride + j] = wl;
         c.wall_hi[a * stride + j] = wh;
     }
-}
-
-//    grid (1, nclouds), kThreads threads: folds the partial boxes, then the body above
-template <typename T, typename CS>
-__global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_constant__ CS clouds) {
-    grid_dependency_wait();
-    using R = Real<T>;
-    const Cloud<T> c = clouds[blockIdx.y];
-    __shared__ T box[6];
-    __shared__ T red[kThreads / 32][6];
-    __shared__ GridHeader<T> hdr;
-    {   // fold the partial boxes: thread t takes partials t, t + blockDim, ...
-        T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
-        for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = R::vmin(lo[a], c.bbox_partial[i * 6 + a]);
-                hi[a] = R::vmax(hi[a], c.bbox_partial[i * 6 + 3 + a]);
-            }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-                hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-            }
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
-        __syncthreads();
-        if (threadIdx.x < 6) {
-            T v = red[0][threadIdx.x];
-            for (int i = 1; i < kThreads / 32; ++i)
-                v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
-            box[threadIdx.x] = v;
-        }
-        __syncthreads();
-    }
-    grid_setup_body<T>(c, box, hdr);
 }
 
 // ---------------------------------------------------------------------------------------------

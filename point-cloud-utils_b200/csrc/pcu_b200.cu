@@ -358,7 +358,7 @@ struct Plan {
             Cloud<T>& cl = args.cloud[s];
             cl.scan_state = take_strided<unsigned long long>(cv, ((size_t)cl.cell_cap + 1 + kScanTile - 1) / kScanTile + 1, B,
                                                              args.cs[s].scan_state);
-            cl.scan_ticket = take_strided<unsigned>(cv, 1, B, args.cs[s].scan_ticket);
+            cl.scan_ticket = take_strided<unsigned>(cv, 2, B, args.cs[s].scan_ticket);   // [0] scan tiles, [1] bbox CTAs
             cl.occupied = take_strided<unsigned>(cv, 1, B, args.cs[s].occupied);
         }
         // One CTA per cloud when the counters fit in shared memory and the clouds are small: five dependent
@@ -514,7 +514,6 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
     PCU_LAUNCH_C(bbox_partial_kernel, dim3(plan.max_bbox_blocks, nclouds), kThreads);
-    PCU_LAUNCH_C(grid_setup_kernel, dim3(1, nclouds), kThreads);
     mark(ws, 2, stream);
     const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     PCU_LAUNCH_C(cell_count_kernel, dim3(bin_blocks, nclouds), kThreads);
