@@ -71,18 +71,55 @@ __device__ __forceinline__ void block_bbox(const T* __restrict__ raw, long long 
     }
 }
 
-//    partial boxes of a large cloud: grid (max bbox_blocks, nclouds).  The CTA of a cloud that finishes
-//    last (ticket in scan_ticket[1]) folds the partial boxes and sets up the grid (2. below), so the
-//    grid needs no launch of its own.
+//    Folds the bbox_blocks partial boxes of a cloud into `box` (shared); block-wide, ends with a barrier.
+template <typename T>
+__device__ __forceinline__ void fold_partial_boxes(const Cloud<T>& c, T* box) {
+    using R = Real<T>;
+    __shared__ T red[kThreads / 32][6];
+    T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
+    for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)   // possibly written in this very launch: around L1
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = R::vmin(lo[a], __ldcg(c.bbox_partial + i * 6 + a));
+            hi[a] = R::vmax(hi[a], __ldcg(c.bbox_partial + i * 6 + 3 + a));
+        }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        T v = red[0][threadIdx.x];
+        for (int i = 1; i < kThreads / 32; ++i)
+            v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
+        box[threadIdx.x] = v;
+    }
+    __syncthreads();
+}
+
+//    partial boxes of a large cloud: grid (max bbox_blocks, nclouds).
+//    kSetup (single pairs): the CTA of a cloud that finishes last (ticket in scan_ticket[1]) folds the
+//    partial boxes and sets up the grid (2. below), so the grid needs no launch of its own -- one
+//    dependent launch less on the critical path of a call.  Batches keep the separate grid_setup_kernel:
+//    thousands of set-ups run side by side there instead of each holding a slot of this streaming kernel
+//    (C5: 0.58 vs 0.72 ms for this stage).
+//    The register budget is the streaming walk's (four CTAs per SM keep enough loads in flight).
 template <typename T> __device__ void grid_setup_body(const Cloud<T>& c, const T* box, GridHeader<T>& hdr);
-template <typename T, typename CS>
-__global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_constant__ CS clouds) {
+template <typename T, typename CS, bool kSetup>
+__global__ void __launch_bounds__(kThreads, 4) bbox_partial_kernel(const __grid_constant__ CS clouds) {
     grid_dependency_wait();
     static_assert(kThreads % 3 == 1, "block_bbox relies on blockDim = 1 (mod 3)");
-    using R = Real<T>;
     const Cloud<T> c = clouds[blockIdx.y];
     if ((int)blockIdx.x >= c.bbox_blocks) return;
     block_bbox<T>(c.raw, 3 * c.n, blockIdx.x, c.bbox_blocks, c.bbox_partial + blockIdx.x * 6);
+    if (!kSetup) return;
     if (threadIdx.x < 6) __threadfence();   // the six writers publish their words before the CTA draws its ticket
     __shared__ bool s_last;
     __syncthreads();
@@ -94,36 +131,19 @@ __global__ void __launch_bounds__(kThreads) bbox_partial_kernel(const __grid_con
     if (!s_last) return;
     __threadfence();
     __shared__ T box[6];
-    __shared__ T red[kThreads / 32][6];
     __shared__ GridHeader<T> hdr;
-    {   // fold the partial boxes (written by other CTAs of this launch: read around L1)
-        T lo[3] = {R::inf(), R::inf(), R::inf()}, hi[3] = {-R::inf(), -R::inf(), -R::inf()};
-        for (int i = threadIdx.x; i < c.bbox_blocks; i += blockDim.x)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                lo[a] = R::vmin(lo[a], __ldcg(c.bbox_partial + i * 6 + a));
-                hi[a] = R::vmax(hi[a], __ldcg(c.bbox_partial + i * 6 + 3 + a));
-            }
-#pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo[a] = R::vmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-                hi[a] = R::vmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-            }
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0)
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { red[w][a] = lo[a]; red[w][3 + a] = hi[a]; }
-        __syncthreads();
-        if (threadIdx.x < 6) {
-            T v = red[0][threadIdx.x];
-            for (int i = 1; i < kThreads / 32; ++i)
-                v = threadIdx.x < 3 ? R::vmin(v, red[i][threadIdx.x]) : R::vmax(v, red[i][threadIdx.x]);
-            box[threadIdx.x] = v;
-        }
-        __syncthreads();
-    }
+    fold_partial_boxes<T>(c, box);
+    grid_setup_body<T>(c, box, hdr);
+}
+
+//    grid (1, nclouds), kThreads threads: the grid set-up of batched calls
+template <typename T, typename CS>
+__global__ void __launch_bounds__(kThreads) grid_setup_kernel(const __grid_constant__ CS clouds) {
+    grid_dependency_wait();
+    const Cloud<T> c = clouds[blockIdx.y];
+    __shared__ T box[6];
+    __shared__ GridHeader<T> hdr;
+    fold_partial_boxes<T>(c, box);
     grid_setup_body<T>(c, box, hdr);
 }
 

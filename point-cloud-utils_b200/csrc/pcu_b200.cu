@@ -513,7 +513,12 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     }
     PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
     const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
-    PCU_LAUNCH_C(bbox_partial_kernel, dim3(plan.max_bbox_blocks, nclouds), kThreads);
+    if (plan.by_value) {
+        PCU_LAUNCH_PDL((bbox_partial_kernel<T, CloudsVal<T>, true>), dim3(plan.max_bbox_blocks, nclouds), kThreads, stream, plan.cv);
+    } else {
+        PCU_LAUNCH_PDL((bbox_partial_kernel<T, CloudsPtr<T>, false>), dim3(plan.max_bbox_blocks, nclouds), kThreads, stream, plan.cp);
+        PCU_LAUNCH_PDL((grid_setup_kernel<T, CloudsPtr<T>>), dim3(1, nclouds), kThreads, stream, plan.cp);
+    }
     mark(ws, 2, stream);
     const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
     PCU_LAUNCH_C(cell_count_kernel, dim3(bin_blocks, nclouds), kThreads);
