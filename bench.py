@@ -9,18 +9,26 @@ one pair, grid build included; value = (n + m) * pairs / time.
 
 * N = 1: one pair, inputs resident in HBM before the timed region (`value`), and the same call
   through the numpy-facing API from pinned host buffers with the H2D / D2H copies inside the timed
-  region (`e2e`).
+  region (`e2e`; `e2e.pageable` is the same call on ordinary numpy arrays).
 * N > 1 (torchrun, one rank per GPU): the path shards over independent pairs -- every rank owns one
-  pair of the same shape (weak scaling) and the only exchange is an NCCL all-reduce of the fp64 sum
-  of the per-pair Chamfer values.  Timing: CUDA events on the launching stream, max over ranks.
+  pair of the same shape (weak scaling) and the only exchange is the sum over ranks of one fp64 per
+  rank (the pair's Chamfer value, left in fp64 by the sweep's last CTA), all-reduced by NCCL on a
+  side stream so that step s's collective overlaps step s + 1's binning.  Timing: CUDA events on the
+  launching stream, max over ranks; the last step's interval ends after its collective.
+* `c5_strong` (every N, beside the C3 headline): BASELINE configs[4] -- the 1024-pair batch of
+  2 x 65536 points sharded over the N ranks (`shard_bounds`), one NCCL sum of the per-shard fp64
+  sums; fixed total work, so the driver's per-N records hold the strong-scaling curve.
 * L2: the 24 MB of inputs fit the 126 MB L2, so a 256 MiB buffer is overwritten before every timed
   step (outside the per-step event interval).
-* `roofline`: the dominant kernel (the fused search sweep) timed with CUDA events recorded inside the
-  library on the launching stream (pcu_b200_workspace_set_profiling), algorithmic bytes = 24 B per
-  query point, peak = MEASURED_PEAKS.json hbm_gbs.
+* `roofline`: the dominant kernel (the search sweep) timed with CUDA events recorded inside the
+  library on the launching stream (pcu_b200_workspace_set_profiling), algorithmic bytes per unit as
+  in SURVEY.md 8d, peak = MEASURED_PEAKS.json hbm_gbs; `traffic` = ncu dram bytes of that kernel from
+  the capture committed under profiles/ (profiles/dram_traffic.json).
 * `cpu_baseline` / `--impl reference`: the reference's own nanoflann path (oracle/_ref, compiled from
   /root/reference/external/nanoflann in place) driven like point_cloud_utils.chamfer_distance (three
-  tree builds per direction, OpenMP sweep, numpy norm/mean) on the box's host cores.
+  tree builds per direction, OpenMP sweep, numpy norm/mean) on the box's host cores;
+  `cpu_baseline.build_once` is the same sweep with ONE tree build per direction, so that the ratio
+  is not inflated by the reference's redundant builds.
 """
 import argparse
 import json
@@ -44,6 +52,12 @@ WORKLOADS = {
                batch=1024),
 }
 ALGO_BYTES_PER_QPT = {"c3": 24.0, "c2": 36.0, "c4": 205.2, "c5": 24.0}
+E2E_API = {
+    "c3": "pcu.chamfer_distance(numpy, numpy) -> pcu_b200_chamfer_host_f32",
+    "c2": "pcu.k_nearest_neighbors(numpy, numpy, 1) -> pcu_b200_knn_host_f32",
+    "c4": "pcu.k_nearest_neighbors(numpy, numpy, 16) -> pcu_b200_knn_host_f32",
+    "c5": "pcu.batched_chamfer_distance(numpy, numpy) -> pcu_b200_batched_chamfer_host_f32",
+}
 
 # Test hook (tests/test_bench_cpu.py): PCU_BENCH_SCALE=0.01 shrinks every cloud so that the reference arm's
 # JSON contract can be checked in seconds.  Never set for a measurement.
@@ -63,6 +77,26 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def committed_traffic(wl_key):
+    """ncu dram__bytes_read.sum + dram__bytes_write.sum of the workload's search kernel, per launch, from the
+    capture committed under profiles/ (None when no capture of this workload's kernel has been committed)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            rec = json.load(f).get(wl_key, {})
+        return rec.get("search_bytes_per_launch"), rec.get("kernel")
+    except Exception:
+        return None, None
+
+
+def search_kernel_name(wl_key, k):
+    if wl_key in ("c3", "c5"):
+        return "nn1_tile_kernel<float, ..., kOut=false, kStats=true> (fused search sweep, both directions in one launch)"
+    if k == 1:
+        return "nn1_tile_kernel<float, ..., kOut=true, kStats=false>"
+    cap = 4 if k <= 4 else 8 if k <= 8 else 16 if k <= 16 else 32
+    return "knn_thread_kernel<float, ..., %d> (thread-per-query register lists)" % cap if k <= 32 else "knn_descend_kernel"
 
 
 class ClockSampler:
@@ -123,7 +157,33 @@ def make_clouds(seed, n, m, batch=None):
     return rng.random((n, 3), dtype=np.float32), rng.random((m, 3), dtype=np.float32)
 
 
+def metric_name(wl_key):
+    return "chamfer_query_points_per_sec" if wl_key in ("c3", "c5") else "knn_queries_per_sec"
+
+
+def unit_name(wl_key):
+    return "query-points/s" if wl_key in ("c3", "c5") else "queries/s"
+
+
 # ------------------------------------------------------------------------------------------------
+def reference_sample(wl_key, total_steps):
+    """Bounded sample of the workload for the CPU arm: (n, m, pairs per step, note)."""
+    wl = WORKLOADS[wl_key]
+    n, m = wl["n"], wl["m"]
+    pairs = 1
+    note = "full size"
+    if wl_key == "c4":
+        n = min(n, 200000)
+        note = "%d of the %d queries against the full %d-point dataset" % (n, wl["n"], m)
+    elif wl_key == "c5":
+        pairs = 2
+        note = "2 of the %d pairs per step" % wl["batch"]
+    elif total_steps > 40:
+        n = m = max(16, n // 4)
+        note = "clouds shrunk to %d points each (more than 40 steps requested)" % n
+    return n, m, pairs, note
+
+
 def run_reference(args, wl_key):
     """The reference's CPU path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -131,19 +191,9 @@ def run_reference(args, wl_key):
         return 0
     from oracle import oracle as O
     O.build()
-    kind = "reference" if O.have_reference() else "port"
+    kind = O.resolve_impl(None)
     wl = WORKLOADS[wl_key]
-    n, m = wl["n"], wl["m"]
-    total_steps = args.steps + args.warmup
-    # bounded sample: the full C3 pair costs ~3 s per step on the reference path (six serial tree builds)
-    if wl_key == "c4":
-        n = 200000
-    if wl_key == "c5":
-        sample_pairs = 2
-    else:
-        sample_pairs = 1
-    if total_steps > 40 and wl_key in ("c3", "c2"):
-        n = m = 250000
+    n, m, sample_pairs, note = reference_sample(wl_key, args.steps + args.warmup)
     x, y = make_clouds(1234, n, m)
     cores = O.hardware_threads(kind)
 
@@ -151,9 +201,9 @@ def run_reference(args, wl_key):
         if wl_key in ("c3", "c5"):
             acc = 0.0
             for _ in range(sample_pairs):
-                acc += float(O.chamfer_distance(x, y, impl=kind))
+                acc += float(O.chamfer_distance(x, y, impl=kind, faithful_builds=True))
             return acc
-        d, i = O.k_nearest_neighbors(x, y, wl["k"], impl=kind)
+        d, i = O.k_nearest_neighbors(x, y, wl["k"], impl=kind, faithful_builds=True)
         return float(d.sum())
 
     for _ in range(args.warmup):
@@ -164,13 +214,17 @@ def run_reference(args, wl_key):
     dt = time.perf_counter() - t0
     units = ((n + m) if wl_key in ("c3", "c5") else n) * sample_pairs
     value = units * args.steps / dt
-    sample = "%d pair(s) of 2x(%dx3) fp32, reference-faithful (3 tree builds per direction, OpenMP sweep, numpy norm/mean)" \
-        % (sample_pairs, n) if wl_key in ("c3", "c5") else "%d queries vs %d points, k=%d" % (n, m, wl["k"])
+    if wl_key in ("c3", "c5"):
+        sample = "%d pair(s) of 2x(%dx3) fp32 per step, reference-faithful (3 tree builds per direction, OpenMP sweep, " \
+                 "numpy norm/mean); %s" % (sample_pairs, n, note)
+    else:
+        sample = "%d queries vs %d points, k=%d, per step (3 tree builds, OpenMP sweep); %s" % (n, m, wl["k"], note)
     line = {
         "impl": "reference", "metric": metric_name(wl_key), "value": value, "unit": unit_name(wl_key),
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "host": "CPU only (nanoflann kd-tree, %d threads)" % cores},
+        "config": {"workload": wl["name"], "host": "CPU only (nanoflann kd-tree, %d threads)" % cores,
+                   "sample": note},
         "cpu_baseline": {"value": value, "unit": unit_name(wl_key), "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": unit_name(wl_key), "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -179,15 +233,143 @@ def run_reference(args, wl_key):
     return 0
 
 
-def metric_name(wl_key):
-    return "chamfer_query_points_per_sec" if wl_key in ("c3", "c5") else "knn_queries_per_sec"
-
-
-def unit_name(wl_key):
-    return "query-points/s" if wl_key in ("c3", "c5") else "queries/s"
-
-
 # ------------------------------------------------------------------------------------------------
+class Bench:
+    """One rank of the GPU arm."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import pcu_b200 as pcu
+        from importlib import import_module
+        self.torch, self.dist, self.pcu = torch, dist, pcu
+        self.bmod = import_module("point-cloud-utils_b200._batched")
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available() or pcu.device_count() == 0:
+            raise SystemExit("bench.py needs a B200: the product has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self.exchange = self.bmod.ScalarSumExchange(self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def reduce_max(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # -- device-resident arm of one workload: (value, ms_per_step, launches per step, stage_ms, units/step all ranks)
+    def device_arm(self, wl_key, xd, yd, local_batch, steps, warmup, sample_clocks):
+        torch, pcu, bmod = self.torch, self.pcu, self.bmod
+        wl = WORKLOADS[wl_key]
+        n, m, k = wl["n"], wl["m"], wl["k"]
+        exchange = self.exchange
+
+        def device_step():
+            if wl_key == "c3":
+                if self.world > 1:   # the path's only exchange: one fp64 per rank, summed off the critical path
+                    return bmod.distributed_chamfer_sum(xd, yd, exchange)
+                return pcu.chamfer_distance(xd, yd)                     # 0-dim CUDA tensor, no synchronisation
+            if wl_key == "c5":
+                _, total = bmod.batched_chamfer(xd, yd, return_sum=True)   # fp64 sum of this rank's pairs
+                if self.world > 1:
+                    exchange.submit(total.reshape(1))
+                return total
+            pcu.k_nearest_neighbors(xd, yd, k)
+            return None
+
+        units_rank = ((n + m) if wl_key in ("c3", "c5") else n) * local_batch
+        for _ in range(warmup):
+            self.flush.fill_(1)
+            device_step()
+        exchange.wait()
+        self.barrier()
+        sampler = ClockSampler(self.local) if (sample_clocks and self.rank == 0) else None
+        if sampler:
+            sampler.start()
+        launches0 = pcu.launch_count()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        self.barrier()
+        for s in range(steps):
+            self.flush.fill_(s & 0xff)      # evict inputs / scratch from L2 (outside the interval)
+            starts[s].record()
+            device_step()
+            if s == steps - 1:
+                exchange.wait()             # the last interval ends after the last collective
+            stops[s].record()
+        self.barrier()
+        launches = pcu.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        total_ms = self.reduce_max(sum(a.elapsed_time(b) for a, b in zip(starts, stops)))
+        units = self.reduce_sum(units_rank)
+        ms_per_step = total_ms / steps
+        value = units / (ms_per_step * 1e-3)
+
+        # per-stage CUDA events inside the library, same workload
+        internal = pcu._pcu_internal
+        internal._set_profiling(self.local, self.stream, True)
+        stage_ms = {}
+        reps = min(steps, 30)
+        for s in range(reps):
+            self.flush.fill_(s & 0xff)
+            device_step()
+            exchange.wait()
+            torch.cuda.synchronize(self.dev)
+            for key, val in internal._last_profile(self.local, self.stream).items():
+                stage_ms[key] = stage_ms.get(key, 0.0) + val / reps
+        internal._set_profiling(self.local, self.stream, False)
+        return dict(value=value, ms_per_step=ms_per_step, launches=launches, stage_ms=stage_ms, units=units,
+                    units_rank=units_rank, clocks=clocks)
+
+    def host_arm(self, wl_key, xh, yh, steps, units_all):
+        """The numpy-facing API with host buffers: H2D + kernels + D2H + sync inside every call."""
+        pcu, bmod = self.pcu, self.bmod
+        k = WORKLOADS[wl_key]["k"]
+
+        def host_step(a, b):
+            if wl_key == "c3":
+                return float(pcu.chamfer_distance(a, b))
+            if wl_key == "c5":
+                return float(bmod.batched_chamfer(a, b, return_sum=True)[1])
+            d, i = pcu.k_nearest_neighbors(a, b, k)
+            return float(d[0].sum())
+
+        def timed(a, b, reps):
+            for _ in range(3):
+                host_step(a, b)
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                host_step(a, b)
+            self.torch.cuda.synchronize(self.dev)
+            return self.reduce_max(time.perf_counter() - t0) / reps
+
+        xp = self.torch.from_numpy(xh).pin_memory()
+        yp = self.torch.from_numpy(yh).pin_memory()
+        pinned_s = timed(xp.numpy(), yp.numpy(), steps)
+        del xp, yp
+        pageable_s = timed(np.array(xh, copy=True), np.array(yh, copy=True), max(3, steps // 4))
+        return pinned_s, pageable_s
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,176 +378,110 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the c5_strong object beside the headline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl_key = args.workload
     if args.impl == "reference":
         return run_reference(args, wl_key)
 
-    import torch
-    import torch.distributed as dist
-    import pcu_b200 as pcu
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available() or pcu.device_count() == 0:
-        raise SystemExit("bench.py needs a B200: the product has no CPU path")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    B = Bench(args)
+    torch, pcu, bmod = B.torch, B.pcu, B.bmod
+    rank, world, dev = B.rank, B.world, B.dev
     wl = WORKLOADS[wl_key]
     n, m, k = wl["n"], wl["m"], wl["k"]
     batch = wl.get("batch")
     if batch:
-        from importlib import import_module
-        bmod = import_module("point-cloud-utils_b200._batched")
         lo, hi = bmod.shard_bounds(batch, world, rank)
         local_batch = hi - lo
         xh, yh = make_clouds(1000 + rank, n, m, local_batch)
     else:
         local_batch = 1
         xh, yh = make_clouds(1000 + rank, n, m)
-    # pinned host copies (e2e path) and device-resident copies (value path)
-    xp = torch.from_numpy(xh).pin_memory()
-    yp = torch.from_numpy(yh).pin_memory()
-    xd, yd = xp.to(dev, non_blocking=True), yp.to(dev, non_blocking=True)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    xd = torch.from_numpy(xh).to(dev)
+    yd = torch.from_numpy(yh).to(dev)
 
-    def device_step():
-        if wl_key == "c3":
-            res = pcu.chamfer_distance(xd, yd)                       # 0-dim CUDA tensor, no synchronisation
-        elif wl_key == "c5":
-            _, res = bmod.batched_chamfer(xd, yd, return_sum=True)   # fp64 sum of this rank's pairs
-        else:
-            pcu.k_nearest_neighbors(xd, yd, k)
-            return None
-        if world > 1:   # the path's only exchange: one fp64 scalar per rank
-            res = res.to(torch.float64).reshape(1)
-            dist.all_reduce(res, op=dist.ReduceOp.SUM)
-        return res
-
-    def host_step():
-        if wl_key == "c3":
-            return float(pcu.chamfer_distance(xp.numpy(), yp.numpy()))
-        if wl_key == "c5":
-            return float(bmod.batched_chamfer(xp.numpy(), yp.numpy(), return_sum=True)[1])
-        d, i = pcu.k_nearest_neighbors(xp.numpy(), yp.numpy(), k)
-        return float(d[0].sum())
-
-    units_per_step_rank = ((n + m) if wl_key in ("c3", "c5") else n) * local_batch
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    # ---- device-resident arm ------------------------------------------------------------------
-    for _ in range(args.warmup):
-        flush.fill_(1)
-        device_step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = pcu.launch_count()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    barrier()
-    for s in range(args.steps):
-        flush.fill_(s & 0xff)          # evict the 24 MB of inputs / scratch from L2 (outside the interval)
-        starts[s].record()
-        device_step()
-        stops[s].record()
-    barrier()
-    launches = pcu.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, b in zip(starts, stops))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    units = torch.tensor([float(units_per_step_rank)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(units, op=dist.ReduceOp.SUM)
-    total_ms = float(t.item())
-    units_per_step = float(units.item())
-    ms_per_step = total_ms / args.steps
-    value = units_per_step / (ms_per_step * 1e-3)
-
-    # ---- roofline pass: per-stage CUDA events inside the library, same workload -----------------
-    pcu._pcu_internal._set_profiling(local, stream, True)
-    stage_ms = {}
-    reps = min(args.steps, 30)
-    for s in range(reps):
-        flush.fill_(s & 0xff)
-        device_step()
-        torch.cuda.synchronize(dev)
-        for key, val in pcu._pcu_internal._last_profile(local, stream).items():
-            stage_ms[key] = stage_ms.get(key, 0.0) + val / reps
-    pcu._pcu_internal._set_profiling(local, stream, False)
+    res = B.device_arm(wl_key, xd, yd, local_batch, args.steps, args.warmup, sample_clocks=True)
+    value, ms_per_step, stage_ms = res["value"], res["ms_per_step"], res["stage_ms"]
     peak, peak_src = measured_peak()
-    algo_bytes = ALGO_BYTES_PER_QPT[wl_key] * units_per_step_rank
+    algo_bytes = ALGO_BYTES_PER_QPT[wl_key] * res["units_rank"]
     search_ms = stage_ms.get("search", 0.0)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            traffic = json.load(f).get(wl_key, {}).get("search_bytes_per_launch")
-    except Exception:
-        pass
+    traffic, traffic_kernel = committed_traffic(wl_key)
     roofline = {
-        "bound": "hbm", "kernel": "nn1_kernel (fused search sweep, both directions in one launch)"
-        if wl_key in ("c3", "c5") else ("nn1_kernel" if k == 1 else "knn_warp_kernel"),
+        "bound": "hbm", "kernel": search_kernel_name(wl_key, k),
         "achieved": algo_bytes / (search_ms * 1e-3) / 1e9 if search_ms > 0 else None, "peak": peak, "unit": "GB/s",
         "frac": (algo_bytes / (search_ms * 1e-3) / 1e9 / peak) if search_ms > 0 else None, "traffic": traffic,
+        "traffic_kernel": traffic_kernel,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": search_ms,
         "stage_ms": {kk: round(v, 5) for kk, v in stage_ms.items()},
-        "step_frac": algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+        "step_frac": ALGO_BYTES_PER_QPT[wl_key] * res["units"] / world / (ms_per_step * 1e-3) / 1e9 / peak,
     }
 
-    # ---- end-to-end arm: numpy-facing API, pinned host buffers, copies inside the timed region ---
+    # ---- end-to-end arm: numpy-facing API, host buffers, copies inside the timed region ----------------
     e2e_steps = args.steps if wl_key in ("c3", "c2") else min(args.steps, 10)
-    for _ in range(3):
-        host_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        host_step()
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step / (float(te.item()) / e2e_steps)
+    pinned_s, pageable_s = B.host_arm(wl_key, xh, yh, e2e_steps, res["units"])
     h2d = int(xh.nbytes + yh.nbytes)
-    d2h = 2 * 72 + 4 if wl_key == "c3" else (4 * local_batch + 8 if wl_key == "c5" else int(n * k * 12 + 8))
+    d2h = 2 * 80 + 4 if wl_key == "c3" else (4 * local_batch + 8 if wl_key == "c5" else int(n * k * 12 + 8))
+    e2e = {"value": res["units"] / pinned_s, "unit": unit_name(wl_key), "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": pinned_s * 1e3, "steps": e2e_steps,
+           "api": E2E_API[wl_key] + " (pinned host buffers; every rank on its own GPU)",
+           "pageable": {"value": res["units"] / pageable_s, "ms_per_step": pageable_s * 1e3,
+                        "note": "same call on ordinary (pageable) numpy arrays"}}
+    del xd, yd
+
+    # ---- C5 strong scaling beside the headline (BASELINE configs[4]) -----------------------------------
+    c5 = None
+    if wl_key == "c3" and not args.no_c5:
+        w5 = WORKLOADS["c5"]
+        lo, hi = bmod.shard_bounds(w5["batch"], world, rank)
+        g = torch.Generator(device=dev).manual_seed(5000 + rank)
+        x5 = torch.rand((hi - lo, w5["n"], 3), generator=g, device=dev)
+        y5 = torch.rand((hi - lo, w5["m"], 3), generator=g, device=dev)
+        r5 = B.device_arm("c5", x5, y5, hi - lo, min(args.steps, 10), 3, sample_clocks=False)
+        c5 = {"workload": w5["name"], "value": r5["value"], "unit": "query-points/s", "ms_per_step": r5["ms_per_step"],
+              "steps": min(args.steps, 10), "pairs_total": w5["batch"], "pairs_per_gpu": hi - lo, "scaling": "strong",
+              "exchange": "one NCCL all-reduce of the per-shard fp64 sum per step (side stream)" if world > 1 else "none (1 GPU)",
+              "stage_ms": {kk: round(v, 5) for kk, v in r5["stage_ms"].items()},
+              "gpu_launches": int(r5["launches"]), "data": "torch.rand on the device, seed 5000 + rank"}
+        del x5, y5
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
-        kind = "reference" if O.have_reference() else "port"
+        kind = O.resolve_impl(None)
         cores = O.hardware_threads(kind)
         if wl_key in ("c3", "c5"):
-            cn = 1000000 if wl_key == "c3" else 65536
+            cn = wl["n"]
             reps_cpu = 1 if wl_key == "c3" else 8
             cx, cy = make_clouds(4321, cn, cn)
-            t0 = time.perf_counter()
-            for _ in range(reps_cpu):
-                O.chamfer_distance(cx, cy, impl=kind)
-            dt = time.perf_counter() - t0
+
+            def timed_cpu(faithful):
+                t0 = time.perf_counter()
+                for _ in range(reps_cpu):
+                    O.chamfer_distance(cx, cy, impl=kind, faithful_builds=faithful)
+                return time.perf_counter() - t0
+            dt = timed_cpu(True)
+            dt1 = timed_cpu(False)
             cpu = {"value": 2 * cn * reps_cpu / dt, "unit": "query-points/s", "cores": cores, "kind": kind,
                    "sample": "%d x chamfer_distance on 2x(%dx3) fp32 exactly as point_cloud_utils does it (three kd-tree "
-                             "builds per direction, OpenMP query sweep, numpy gather/norm/mean): %.2f s" % (reps_cpu, cn, dt)}
+                             "builds per direction, OpenMP query sweep, numpy gather/norm/mean): %.2f s" % (reps_cpu, cn, dt),
+                   "build_once": {"value": 2 * cn * reps_cpu / dt1, "unit": "query-points/s",
+                                  "sample": "same, ONE kd-tree build per direction: %.2f s" % dt1}}
         else:
-            cn = 1000000 if wl_key == "c2" else 300000
+            cn = min(n, 1000000 if wl_key == "c2" else 300000)
             cx, cy = make_clouds(4321, cn, m)
-            t0 = time.perf_counter()
-            O.k_nearest_neighbors(cx, cy, k, impl=kind)
-            dt = time.perf_counter() - t0
+
+            def timed_cpu(faithful):
+                t0 = time.perf_counter()
+                O.k_nearest_neighbors(cx, cy, k, impl=kind, faithful_builds=faithful)
+                return time.perf_counter() - t0
+            dt = timed_cpu(True)
+            dt1 = timed_cpu(False)
             cpu = {"value": cn / dt, "unit": "queries/s", "cores": cores, "kind": kind,
-                   "sample": "%d of the queries vs the full %d-point dataset, k=%d: %.2f s" % (cn, m, k, dt)}
+                   "sample": "%d of the queries vs the full %d-point dataset, k=%d, three tree builds: %.2f s" % (cn, m, k, dt),
+                   "build_once": {"value": cn / dt1, "unit": "queries/s", "sample": "same, ONE tree build: %.2f s" % dt1}}
 
     if rank == 0:
         line = {
@@ -374,22 +490,24 @@ def main():
             "scaling": "weak" if wl_key != "c5" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
                 "workload": wl["name"], "pairs_per_gpu": local_batch, "seed": 1000,
-                "parallelism": "pair-sharded, one rank per GPU, NCCL all-reduce of one fp64 sum" if world > 1 else "1 GPU",
+                "parallelism": ("pair-sharded, one rank per GPU; per step one NCCL sum of one fp64 per rank on a side "
+                                "stream (overlaps the next step's binning)") if world > 1 else "1 GPU",
                 "l2": "inputs (24 MB) < L2: a 256 MiB buffer is overwritten before every timed step, outside the interval",
                 "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
+                "ratio_note": "N GPUs process N pairs per step; the reference arm is one CPU process: a throughput ratio",
             },
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": unit_name(wl_key), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(te.item()) / e2e_steps * 1e3, "steps": e2e_steps,
-                    "api": "pcu.chamfer_distance(numpy, numpy) -> pcu_b200_chamfer_host_f32 (pinned host buffers)"},
-            "gpu_launches": int(launches),
+            "clocks": res["clocks"],
+            "e2e": e2e,
+            "gpu_launches": int(res["launches"]),
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if c5 is not None:
+            line["c5_strong"] = c5
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        B.dist.barrier()
+        B.dist.destroy_process_group()
     return 0
 
 

@@ -27,8 +27,12 @@
  *     workspace serves one stream at a time.
  *   - "device" entry points take DEVICE pointers, enqueue work on `stream` and return without
  *     synchronising; results are valid once the stream reaches that point.  "host" entry points
- *     take HOST pointers, stage through the workspace's pinned buffers (H2D, kernels, D2H) on the
- *     workspace's own stream and return after the results have landed.
+ *     take HOST pointers (pinned or pageable), copy them to device staging owned by the workspace
+ *     on the workspace's own streams -- the copy of the second cloud overlaps the first kernels --
+ *     and return after the results have landed in the caller's buffers.
+ *   - Scratch grows with stream-ordered allocation (cudaMallocAsync): no entry point synchronises
+ *     the device.  A workspace serves one stream at a time; a call on another stream than the
+ *     previous one is ordered after it on the device.
  *   - Results follow the reference bit for bit: squared distance is ((qx-px)^2+(qy-py)^2)+(qz-pz)^2,
  *     every operation rounded in the input precision, no FMA (nanoflann.hpp:496-507); indices are
  *     int64 (ptrdiff_t in the reference); rows are ascending by distance; queries whose answer
@@ -46,7 +50,7 @@
 extern "C" {
 #endif
 
-#define PCU_B200_ABI_VERSION 2
+#define PCU_B200_ABI_VERSION 3
 
 typedef enum pcu_b200_status {
     PCU_B200_OK = 0,
@@ -73,6 +77,10 @@ typedef struct pcu_b200_nn_stats {
                           /* is the lowest such index, not necessarily the reference's pick; the  */
                           /* host entry points resolve this themselves, device callers use        */
                           /* pcu_b200_resolve_witness_* (value, sums and argmax_query are final)   */
+    double pair_value;    /* bidirectional calls (pcu_b200_chamfer_*): the pair's Chamfer value in fp64,  */
+                          /* sum_dist[x->y] / n + sum_dist[y->x] / m, written to BOTH records by the sweep */
+                          /* that finishes second (what a multi-GPU caller sums across ranks);            */
+                          /* one-directional calls: sum_dist / n_queries                                  */
 } pcu_b200_nn_stats;
 
 /* Tunables; zero-initialise and override what you need.  0 always means "library default". */
@@ -91,12 +99,21 @@ int pcu_b200_abi_version(void);
 const char* pcu_b200_last_error(void);
 /* Number of CUDA devices this build can run on (compute capability 10.x); 0 if none. */
 int pcu_b200_device_count(void);
+/* The device a call that names none runs on.  The reference's interface (src/point_cloud_distance.cpp:123-131,
+ * :186-193) has no device argument, so the replacement has to pick one: the environment variable
+ * PCU_B200_DEVICE if set; else the CUDA runtime's current device of the calling thread when that is not 0
+ * (torch.cuda.set_device / `with torch.cuda.device(i)`); else LOCAL_RANK when a launcher (torchrun) set it
+ * and that many devices are visible; else 0. */
+int pcu_b200_current_device(void);
 /* Kernels launched by this library on the calling process since load (bench.py's gpu_launches). */
 int64_t pcu_b200_launch_count(void);
 
 /* ---- workspace ---------------------------------------------------------------------------- */
 int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws);
 int pcu_b200_workspace_destroy(pcu_b200_workspace* ws);
+/* The device the workspace was created on (-1 for NULL).  Every entry point runs there and leaves the
+ * calling thread's current device as it found it. */
+int pcu_b200_workspace_device(const pcu_b200_workspace* ws);
 /* Bytes of device scratch currently held. */
 int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws);
 int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_options* opts);

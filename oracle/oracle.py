@@ -6,6 +6,8 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 
 Two back ends with one interface:
 
+``impl=None`` (the default everywhere) means "reference" where ``oracle/_ref`` exists, else "port".
+
 * ``impl="port"``       ``oracle/libpcu_oracle.so`` -- our own restatement of the kd-tree build and
                         search (``oracle/kdtree_oracle.cpp``), available everywhere.
 * ``impl="reference"``  ``oracle/_ref/libpcu_ref.so`` -- the reference's *own* vendored
@@ -31,6 +33,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _PORT_PATH = os.path.join(_HERE, "libpcu_oracle.so")
 _REF_PATH = os.path.join(_HERE, "_ref", "libpcu_ref.so")
 _libs = {}
+# Default of `faithful_builds` (reference back end only): True = three tree builds per call like the reference
+# (what bench.py times); tests set it to False through the conftest fixture -- the three builds produce the same
+# tree, so results are identical and the CPU side of the big parity tests is three builds shorter.
+DEFAULT_FAITHFUL_BUILDS = True
 
 _c_i64 = ctypes.c_int64
 _c_int = ctypes.c_int
@@ -50,7 +56,16 @@ def have_reference():
     return os.path.exists(_REF_PATH)
 
 
+def resolve_impl(impl=None):
+    """None -> the reference's own nanoflann path when oracle/_ref is present (this container, and the GPU
+    box as a prebuilt file), else the restatement.  Tests that pin one against the other name them explicitly."""
+    if impl is None:
+        return "reference" if have_reference() else "port"
+    return impl
+
+
 def _lib(impl):
+    impl = resolve_impl(impl)
     if impl in _libs:
         return _libs[impl]
     if impl == "port":
@@ -79,7 +94,7 @@ def _lib(impl):
     return _libs[impl]
 
 
-def hardware_threads(impl="port"):
+def hardware_threads(impl=None):
     lib, prefix = _lib(impl)
     return int(getattr(lib, prefix + "_hardware_threads")())
 
@@ -102,11 +117,12 @@ def _check_pair(a, b, name_a, name_b):
 
 
 def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False, max_points_per_leaf=10,
-                        num_threads=-1, impl="port", faithful_builds=True):
+                        num_threads=-1, impl=None, faithful_builds=None):
     """point_cloud_distance.cpp:123-164."""
     if k <= 0:
         raise ValueError("Invalid value for k (%d) must be greater than 0." % k)
     q, d = _check_pair(query_points, dataset_points, "query_points", "dataset_points")
+    impl = resolve_impl(impl)
     lib, prefix = _lib(impl)
     n, m = q.shape[0], d.shape[0]
     dists = np.empty((n, k), dtype=q.dtype)
@@ -116,7 +132,7 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
     args = [q.ctypes.data, n, d.ctypes.data, m, int(k), int(bool(squared_distances)), int(max_points_per_leaf),
             int(num_threads)]
     if impl == "reference":
-        args.append(int(bool(faithful_builds)))
+        args.append(int(bool(DEFAULT_FAITHFUL_BUILDS if faithful_builds is None else faithful_builds)))
     rc = fn(*args, dists.ctypes.data, corrs.ctypes.data)
     if rc != 0:
         raise RuntimeError("oracle call failed (rc=%d)" % rc)
@@ -126,7 +142,7 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
 
 
 def one_sided_hausdorff_distance(source, target, return_index=True, squared_distances=False, max_points_per_leaf=10,
-                                 impl="port"):
+                                 impl=None):
     """point_cloud_distance.cpp:186-234 (note: return_index defaults to True here)."""
     s, t = _check_pair(source, target, "source", "target")
     lib, prefix = _lib(impl)
@@ -145,7 +161,7 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
     return value
 
 
-def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_points_per_leaf=10, impl="port"):
+def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_points_per_leaf=10, impl=None):
     """point_cloud_utils/__init__.py:52-81."""
     h_xy, ix1, iy1 = one_sided_hausdorff_distance(x, y, True, squared_distances, max_points_per_leaf, impl=impl)
     h_yx, iy2, ix2 = one_sided_hausdorff_distance(y, x, True, squared_distances, max_points_per_leaf, impl=impl)
@@ -157,7 +173,7 @@ def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_po
     return h
 
 
-def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10, impl="port", faithful_builds=True):
+def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10, impl=None, faithful_builds=None):
     """point_cloud_utils/__init__.py:84-120 (distances are recomputed from the indices with numpy)."""
     x = np.asarray(x)
     y = np.asarray(y)

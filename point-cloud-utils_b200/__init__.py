@@ -37,14 +37,43 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
         "There is no pure-Python or CPU fallback for this package." % (_e,)) from _e
 
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
-           "batched_chamfer_distance", "device_count", "launch_count"]
+           "batched_chamfer_distance", "device_count", "current_device", "launch_count"]
 
-_STATS_WORDS = 9   # sizeof(pcu_b200_nn_stats) / 8
+_STATS_WORDS = 10  # sizeof(pcu_b200_nn_stats) / 8
 
 
 def device_count():
     """Number of visible GPUs this build can run on (compute capability 10.x)."""
     return _pcu_internal._device_count()
+
+
+def current_device():
+    """The GPU a numpy-input call runs on when no ``device=`` is given: ``PCU_B200_DEVICE`` if set, else the CUDA
+    runtime's current device when it is not 0 (``torch.cuda.set_device`` / ``with torch.cuda.device(i)``), else
+    ``LOCAL_RANK`` (torchrun) when that many devices are visible, else 0.  CUDA tensors always run where they live."""
+    return _pcu_internal._current_device()
+
+
+def _dev(device):
+    """``device=`` keyword -> ordinal for the native layer (-1: let the library choose, see current_device)."""
+    if device is None:
+        return -1
+    if isinstance(device, int):
+        d = device
+    elif isinstance(device, str):
+        name = device.strip().lower()
+        if name == "cuda":
+            return -1
+        if not name.startswith("cuda:") or not name[5:].isdigit():
+            raise ValueError("device must be an int, None, 'cuda' or 'cuda:<i>' (got %r)" % (device,))
+        d = int(name[5:])
+    elif getattr(device, "type", None) == "cuda":           # torch.device
+        d = -1 if device.index is None else int(device.index)
+    else:
+        raise ValueError("device must be an int, None, 'cuda', 'cuda:<i>' or a CUDA torch.device (got %r)" % (device,))
+    if d >= device_count() or d < -1:
+        raise ValueError("device %d out of range: %d usable GPU(s) visible" % (d, device_count()))
+    return d
 
 
 def launch_count():
@@ -88,6 +117,13 @@ def _check_tensor_pair(a, b, name_a, name_b):
     return a.detach().contiguous(), b.detach().contiguous()
 
 
+def _same_device(t, device):
+    """CUDA tensors run where they live; a contradicting device= is an argument error."""
+    d = _dev(device)
+    if d >= 0 and d != (t.device.index or 0):
+        raise ValueError("device=%r contradicts the inputs, which live on %s" % (device, t.device))
+
+
 def _stream_of(t):
     torch = _torch()
     return torch.cuda.current_stream(t.device).cuda_stream
@@ -101,7 +137,8 @@ def _stats_from_tensor(buf, which):
     o = _STATS_WORDS * which
     return {"sum_dist": float(f[o]), "sum_sq_dist": float(f[o + 1]), "max_sq_dist": float(f[o + 2]),
             "argmax_query": int(i[o + 3]), "argmax_data": int(i[o + 4]), "n_queries": int(i[o + 5]),
-            "n_tied": int(i[o + 6]), "n_far": int(i[o + 7]), "witness_tied": int(i[o + 8])}
+            "n_tied": int(i[o + 6]), "n_far": int(i[o + 7]), "witness_tied": int(i[o + 8]),
+            "pair_value": float(f[o + 9])}
 
 
 def _resolved_stats(buf, which, q, d, leaf):
@@ -119,7 +156,7 @@ def _resolved_stats(buf, which, q, d, leaf):
 def _stats_device(a, b, both, leaf):
     torch = _torch()
     assert _pcu_internal._stats_nbytes() == 8 * _STATS_WORDS
-    buf = torch.empty(2 * _STATS_WORDS, dtype=torch.int64, device=a.device)
+    buf = torch.empty(2 * _STATS_WORDS, dtype=torch.int64, device=a.device)   # every record is written by the sweep
     val = torch.empty((), dtype=a.dtype, device=a.device)
     _pcu_internal._stats_device(a.dtype == torch.float64, both, a.data_ptr(), a.shape[0], b.data_ptr(), b.shape[0],
                                 buf.data_ptr(), val.data_ptr() if both else 0, int(leaf), a.device.index or 0,
@@ -134,7 +171,7 @@ def _metric_value(max_sq, squared, dtype):
 
 # ---------------------------------------------------------------------------------------------
 def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False, max_points_per_leaf=10,
-                        num_threads=-1):
+                        num_threads=-1, *, device=None):
     """
     Compute the k nearest neighbors (L2 distance) from each point in the query point cloud to the dataset point cloud.
 
@@ -146,6 +183,8 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
         max_points_per_leaf : The maximum number of points per leaf node in the KD tree of the reference. Here it
                               only decides how exactly-equal distances are ordered (identically to the reference).
         num_threads : CPU thread count of the reference implementation; accepted and ignored.
+        device : (keyword only, not in the reference) GPU for numpy / CPU-tensor inputs: an ordinal, 'cuda:<i>' or a
+                 torch.device; None = `current_device()`.  CUDA tensors run on the device they live on.
 
     Returns:
         dists : An (n, k)-shaped array such that `dists[i,k]` contains the k^th shortest L2 distance from the point
@@ -164,8 +203,9 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
         q, d = _check_tensor_pair(query_points, dataset_points, "query_points", "dataset_points")
         if not q.is_cuda:
             dn, cn = _pcu_internal.k_nearest_neighbors(q.numpy(), d.numpy(), int(k), bool(squared_distances),
-                                                       int(max_points_per_leaf), int(num_threads))
+                                                       int(max_points_per_leaf), int(num_threads), _dev(device))
             return torch.from_numpy(_np.asarray(dn)), torch.from_numpy(_np.asarray(cn))
+        _same_device(q, device)
         n = q.shape[0]
         dists = torch.empty((n, int(k)), dtype=q.dtype, device=q.device)
         corrs = torch.empty((n, int(k)), dtype=torch.int64, device=q.device)
@@ -174,10 +214,12 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
                                   int(max_points_per_leaf), q.device.index or 0, _stream_of(q))
         return dists.squeeze(), corrs.squeeze()
     return _pcu_internal.k_nearest_neighbors(_np.asarray(query_points), _np.asarray(dataset_points), int(k),
-                                             bool(squared_distances), int(max_points_per_leaf), int(num_threads))
+                                             bool(squared_distances), int(max_points_per_leaf), int(num_threads),
+                                             _dev(device))
 
 
-def one_sided_hausdorff_distance(source, target, return_index=True, squared_distances=False, max_points_per_leaf=10):
+def one_sided_hausdorff_distance(source, target, return_index=True, squared_distances=False, max_points_per_leaf=10,
+                                 *, device=None):
     """
     Compute the one sided Hausdorff distance from source to target
 
@@ -189,6 +231,7 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
                        reference binding).
         squared_distances : If set to True, then return squared L2 distances.
         max_points_per_leaf : see `k_nearest_neighbors`.
+        device : see `k_nearest_neighbors` (keyword only).
 
     Returns:
         d : The largest shortest distance, `d` between each point in `source` and the points in `target` (a float).
@@ -203,7 +246,9 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
         s, t = _check_tensor_pair(source, target, "source", "target")
         if not s.is_cuda:
             return _pcu_internal.one_sided_hausdorff_distance(s.numpy(), t.numpy(), bool(return_index),
-                                                              bool(squared_distances), int(max_points_per_leaf))
+                                                              bool(squared_distances), int(max_points_per_leaf),
+                                                              _dev(device))
+        _same_device(s, device)
         buf, _ = _stats_device(s, t, False, max_points_per_leaf)
         st = _resolved_stats(buf, 0, s, t, max_points_per_leaf)
         value = _metric_value(st["max_sq_dist"], squared_distances,
@@ -212,24 +257,25 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
             return value, st["argmax_query"], st["argmax_data"]
         return value
     return _pcu_internal.one_sided_hausdorff_distance(_np.asarray(source), _np.asarray(target), bool(return_index),
-                                                      bool(squared_distances), int(max_points_per_leaf))
+                                                      bool(squared_distances), int(max_points_per_leaf), _dev(device))
 
 
-def _both_stats(x, y, max_points_per_leaf):
+def _both_stats(x, y, max_points_per_leaf, device=None):
     """(dtype, chamfer value, stats x->y, stats y->x) from ONE fused bidirectional launch sequence."""
     if _is_tensor(x) or _is_tensor(y):
         if not _is_tensor(x):
             raise ValueError("x and y must both be torch tensors or both be numpy arrays")
         xs, ys = _check_tensor_pair(x, y, "x", "y")
         if xs.is_cuda:
+            _same_device(xs, device)
             buf, val = _stats_device(xs, ys, True, max_points_per_leaf)
             return ("cuda", xs.dtype, val, (buf, xs, ys))
         x, y = xs.numpy(), ys.numpy()
-    val, sxy, syx = _pcu_internal._chamfer_stats(_np.asarray(x), _np.asarray(y), int(max_points_per_leaf))
+    val, sxy, syx = _pcu_internal._chamfer_stats(_np.asarray(x), _np.asarray(y), int(max_points_per_leaf), _dev(device))
     return ("host", _np.asarray(x).dtype.type, val, (sxy, syx))
 
 
-def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_points_per_leaf=10):
+def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_points_per_leaf=10, *, device=None):
     """
     Compute the Hausdorff distance between x and y
 
@@ -250,7 +296,7 @@ def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_po
     Mirrors /root/reference/point_cloud_utils/__init__.py:52-81 (two one-sided passes, `>` / `<=` branch rule);
     both directions come from one fused launch sequence over the two binned clouds.
     """
-    where, dtype, _, st = _both_stats(x, y, max_points_per_leaf)
+    where, dtype, _, st = _both_stats(x, y, max_points_per_leaf, device)
     if where == "cuda":
         buf, xs, ys = st
         sxy = _resolved_stats(buf, 0, xs, ys, max_points_per_leaf)
@@ -269,7 +315,7 @@ def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_po
     return hausdorff
 
 
-def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10):
+def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10, *, device=None):
     """
     Compute the chamfer distance between two point clouds x, and y
 
@@ -291,12 +337,12 @@ def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10)
     whole computation is one fused bidirectional sweep (no index or distance array is materialised).
     """
     if p_norm == 2 and not return_index:
-        where, _, val, _ = _both_stats(x, y, max_points_per_leaf)
+        where, _, val, _ = _both_stats(x, y, max_points_per_leaf, device)
         return val
     dists_x_to_y, corrs_x_to_y = k_nearest_neighbors(x, y, k=1, squared_distances=False,
-                                                     max_points_per_leaf=max_points_per_leaf)
+                                                     max_points_per_leaf=max_points_per_leaf, device=device)
     dists_y_to_x, corrs_y_to_x = k_nearest_neighbors(y, x, k=1, squared_distances=False,
-                                                     max_points_per_leaf=max_points_per_leaf)
+                                                     max_points_per_leaf=max_points_per_leaf, device=device)
     if _is_tensor(x):
         torch = _torch()
         if p_norm == 2:
@@ -315,7 +361,7 @@ def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10)
     return cham
 
 
-def batched_chamfer_distance(x, y, max_points_per_leaf=10):
+def batched_chamfer_distance(x, y, max_points_per_leaf=10, *, device=None):
     """
     Chamfer distance of B independent pairs.
 
@@ -329,4 +375,4 @@ def batched_chamfer_distance(x, y, max_points_per_leaf=10):
     /root/reference/point_cloud_utils/__init__.py:89-90, was never implemented by the 2-D-only binding).
     """
     from ._batched import batched_chamfer  # noqa: WPS433 (kept separate: multi-GPU plumbing lives there too)
-    return batched_chamfer(x, y, max_points_per_leaf)
+    return batched_chamfer(x, y, max_points_per_leaf, device=_dev(device))

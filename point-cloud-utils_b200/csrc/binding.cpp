@@ -15,6 +15,7 @@
 
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <sstream>
 #include <stdexcept>
@@ -38,34 +39,43 @@ namespace {
 inline void check(int status) { if (status != PCU_B200_OK) raise_status(status); }
 
 // One workspace per (device, stream): a workspace serves one stream at a time.  Calls that share a
-// workspace (several Python threads on the same stream) are serialised by `busy`: enqueueing is what
-// must not interleave, the work itself is ordered by the stream.
+// workspace (several Python threads on the same stream) are serialised by that workspace's own mutex:
+// enqueueing is what must not interleave, the work itself is ordered by the stream.  Calls on different
+// devices or streams never wait for each other.
+// The numpy (host-pointer) entry points run on the workspace's private stream; they get workspaces of
+// their own under the key kHostKey, so they never share scratch with a device-pointer call that may still
+// be queued on one of the caller's streams (stream handle 0 is torch's default stream, not "host").
+constexpr uintptr_t kHostKey = ~(uintptr_t)0;
+struct Slot {
+    pcu_b200_workspace* ws = nullptr;
+    std::mutex busy;
+};
 struct Pool {
     std::mutex mu;
-    std::mutex busy;
-    std::map<std::pair<int, uintptr_t>, pcu_b200_workspace*> items;
-    pcu_b200_workspace* get(int device, uintptr_t stream) {
+    std::map<std::pair<int, uintptr_t>, std::unique_ptr<Slot>> items;
+    Slot& get(int device, uintptr_t stream) {
         std::lock_guard<std::mutex> lock(mu);
         auto key = std::make_pair(device, stream);
         auto it = items.find(key);
-        if (it != items.end()) return it->second;
-        pcu_b200_workspace* ws = nullptr;
-        check(pcu_b200_workspace_create(device, &ws));
-        items[key] = ws;
-        return ws;
+        if (it != items.end()) return *it->second;
+        std::unique_ptr<Slot> slot(new Slot());
+        check(pcu_b200_workspace_create(device, &slot->ws));
+        Slot& ref = *slot;
+        items[key] = std::move(slot);
+        return ref;
     }
     void clear() {
         std::lock_guard<std::mutex> lock(mu);
-        for (auto& kv : items) pcu_b200_workspace_destroy(kv.second);
+        for (auto& kv : items) pcu_b200_workspace_destroy(kv.second->ws);
         items.clear();
     }
 };
 Pool& pool() { static Pool p; return p; }
-// Released GIL + exclusive use of the native library for the duration of one call.
+// Released GIL + exclusive use of one workspace for the duration of one call.
 struct CallScope {
     py::gil_scoped_release nogil;
     std::lock_guard<std::mutex> lock;
-    CallScope() : nogil(), lock(pool().busy) {}
+    explicit CallScope(Slot& slot) : nogil(), lock(slot.busy) {}
 };
 
 struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; int binning = 0; };
@@ -138,7 +148,9 @@ py::array_t<T, py::array::c_style> dense(const py::array& a) {
     return py::array_t<T, py::array::c_style | py::array::forcecast>::ensure(a);
 }
 
-int current_device_or_default(int device) { return device < 0 ? 0 : device; }
+// device < 0: the caller named none (the reference's interface has no such argument) -> the library's rule
+// (PCU_B200_DEVICE, the CUDA runtime's current device, LOCAL_RANK, 0; see pcu_b200_current_device)
+int current_device_or_default(int device) { return device < 0 ? pcu_b200_current_device() : device; }
 
 template <typename T>
 py::tuple knn_numpy(const py::array& q_in, const py::array& d_in, int k, bool squared, int leaf, int device) {
@@ -147,12 +159,13 @@ py::tuple knn_numpy(const py::array& q_in, const py::array& d_in, int k, bool sq
     const int64_t n = q.shape(0), m = d.shape(0);
     py::array_t<T> dists({(py::ssize_t)n, (py::ssize_t)k});
     py::array_t<int64_t> corrs({(py::ssize_t)n, (py::ssize_t)k});
-    pcu_b200_workspace* ws = pool().get(device, 0);
+    Slot& slot = pool().get(device, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(leaf);
     int status;
     int64_t tied = 0;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         if (sizeof(T) == 4)
             status = pcu_b200_knn_host_f32(ws, (const float*)q.data(), n, (const float*)d.data(), m, k, squared,
@@ -189,6 +202,7 @@ py::dict stats_to_dict(const pcu_b200_nn_stats& s) {
     d["n_tied"] = s.n_tied;
     d["n_far"] = s.n_far;
     d["witness_tied"] = s.witness_tied;
+    d["pair_value"] = s.pair_value;
     return d;
 }
 
@@ -196,12 +210,13 @@ template <typename T>
 pcu_b200_nn_stats one_sided_numpy(const py::array& s_in, const py::array& t_in, int leaf, int device) {
     auto s = dense<T>(s_in);
     auto t = dense<T>(t_in);
-    pcu_b200_workspace* ws = pool().get(device, 0);
+    Slot& slot = pool().get(device, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(leaf);
     pcu_b200_nn_stats st{};
     int status;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         if (sizeof(T) == 4)
             status = pcu_b200_nn_stats_host_f32(ws, (const float*)s.data(), s.shape(0), (const float*)t.data(), t.shape(0), &st);
@@ -236,7 +251,8 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
     const Dt dt = common_dtype(x_in, y_in, "x", "y");
     check_shapes(x_in, y_in, "x", "y");
     const int dev = current_device_or_default(device);
-    pcu_b200_workspace* ws = pool().get(dev, 0);
+    Slot& slot = pool().get(dev, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(max_points_per_leaf);
     pcu_b200_nn_stats st[2] = {};
     int status;
@@ -245,7 +261,7 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
         auto x = dense<float>(x_in);
         auto y = dense<float>(y_in);
         float v = 0.f;
-        { CallScope scope; pcu_b200_workspace_set_options(ws, &opts);
+        { CallScope scope(slot); pcu_b200_workspace_set_options(ws, &opts);
           status = pcu_b200_chamfer_host_f32(ws, x.data(), x.shape(0), y.data(), y.shape(0), st, &v); }
         check(status);
         value = py::module_::import("numpy").attr("float32")(v);
@@ -253,7 +269,7 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
         auto x = dense<double>(x_in);
         auto y = dense<double>(y_in);
         double v = 0.0;
-        { CallScope scope; pcu_b200_workspace_set_options(ws, &opts);
+        { CallScope scope(slot); pcu_b200_workspace_set_options(ws, &opts);
           status = pcu_b200_chamfer_host_f64(ws, x.data(), x.shape(0), y.data(), y.shape(0), st, &v); }
         check(status);
         value = py::module_::import("numpy").attr("float64")(v);
@@ -266,11 +282,12 @@ void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int6
                 uintptr_t out_dist, uintptr_t out_idx, uintptr_t out_n_tied, int max_points_per_leaf, int device,
                 uintptr_t stream) {
     if (k <= 0) throw py::value_error("Invalid value for k (" + std::to_string(k) + ") must be greater than 0.");
-    pcu_b200_workspace* ws = pool().get(device, stream);
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         status = is_f64 ? pcu_b200_knn_f64(ws, (const double*)query, n, (const double*)dataset, m, k, squared,
                                            (double*)out_dist, (int64_t*)out_idx, (int64_t*)out_n_tied, (void*)stream)
@@ -282,11 +299,12 @@ void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int6
 
 void stats_device(bool is_f64, bool both, uintptr_t a, int64_t n, uintptr_t b, int64_t m, uintptr_t out_stats,
                   uintptr_t out_value, int max_points_per_leaf, int device, uintptr_t stream) {
-    pcu_b200_workspace* ws = pool().get(device, stream);
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         auto* st = (pcu_b200_nn_stats*)out_stats;
         if (both)
@@ -313,14 +331,15 @@ py::tuple batched_chamfer_numpy(const py::array& x_in, const py::array& y_in, in
     py::array_t<float> out({(py::ssize_t)B});
     double sum = 0.0;
     const int dev = current_device_or_default(device);
-    pcu_b200_workspace* ws = pool().get(dev, 0);
+    Slot& slot = pool().get(dev, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         status = pcu_b200_batched_chamfer_host_f32(ws, x.data(), y.data(), B, n, m, out.mutable_data(),
-                                                   B <= 16384 ? &sum : nullptr);
+                                                   &sum);
     }
     check(status);
     return py::make_tuple(out, sum);
@@ -328,11 +347,12 @@ py::tuple batched_chamfer_numpy(const py::array& x_in, const py::array& y_in, in
 
 void batched_chamfer_device(uintptr_t x, uintptr_t y, int64_t B, int64_t n, int64_t m, uintptr_t out_per_pair,
                             uintptr_t out_sum, int max_points_per_leaf, int device, uintptr_t stream) {
-    pcu_b200_workspace* ws = pool().get(device, stream);
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         status = pcu_b200_batched_chamfer_f32(ws, (const float*)x, (const float*)y, B, n, m, (float*)out_per_pair,
                                               (double*)out_sum, (void*)stream);
@@ -348,7 +368,8 @@ py::dict debug_kd_tree_t(const py::array& pts_in, int leaf, int device) {
     py::array_t<int32_t> order(m), feat(cap), first(cap), last(cap), kid0(cap), kid1(cap);
     py::array_t<T> lo(cap), hi(cap);
     int64_t nn = 0;
-    pcu_b200_workspace* ws = pool().get(device, 0);
+    Slot& slot = pool().get(device, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
     int status;
     if (sizeof(T) == 4)
         status = pcu_b200_debug_kd_tree_f32(ws, (const float*)pts.data(), m, leaf, order.mutable_data(), cap,
@@ -377,11 +398,12 @@ py::dict debug_kd_tree(const py::array& pts, int leaf, int device) {
 
 void resolve_witness_device(bool is_f64, uintptr_t q, int64_t n, uintptr_t d, int64_t m, uintptr_t stats,
                             int max_points_per_leaf, int device, uintptr_t stream) {
-    pcu_b200_workspace* ws = pool().get(device, stream);
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(max_points_per_leaf);
     int status;
     {
-        CallScope scope;
+        CallScope scope(slot);
         pcu_b200_workspace_set_options(ws, &opts);
         status = is_f64 ? pcu_b200_resolve_witness_f64(ws, (const double*)q, n, (const double*)d, m,
                                                        (pcu_b200_nn_stats*)stats, (void*)stream)
@@ -418,20 +440,28 @@ PYBIND11_MODULE(_pcu_internal, mod) {
     mod.def("_device_count", []() { return pcu_b200_device_count(); });
     mod.def("_launch_count", []() { return (int64_t)pcu_b200_launch_count(); });
     mod.def("_abi_version", []() { return pcu_b200_abi_version(); });
-    mod.def("_grid_refinement", [](int device, uintptr_t stream) {
+    // diagnostics address a workspace by (device, stream); stream None = the numpy path's own workspace,
+    // device < 0 = the device a call that names none would use
+    auto key_of = [](const py::object& stream) { return stream.is_none() ? kHostKey : stream.cast<uintptr_t>(); };
+    mod.def("_current_device", []() { return pcu_b200_current_device(); });
+    mod.def("_grid_refinement", [key_of](int device, py::object stream) {
         float m[2] = {1.f, 1.f};
-        pcu_b200_workspace_grid_refinement(pool().get(device, stream), m);
+        pcu_b200_workspace_grid_refinement(pool().get(current_device_or_default(device), key_of(stream)).ws, m);
         return py::make_tuple(m[0], m[1]);
-    }, py::arg("device") = 0, py::arg("stream") = 0);
-    mod.def("_workspace_bytes", [](int device, uintptr_t stream) {
-        return (int64_t)pcu_b200_workspace_bytes(pool().get(device, stream));
+    }, py::arg("device") = -1, py::arg("stream") = py::none());
+    mod.def("_workspace_bytes", [key_of](int device, py::object stream) {
+        return (int64_t)pcu_b200_workspace_bytes(pool().get(current_device_or_default(device), key_of(stream)).ws);
+    }, py::arg("device") = -1, py::arg("stream") = py::none());
+    mod.def("_workspace_exists", [key_of](int device, py::object stream) {
+        std::lock_guard<std::mutex> lock(pool().mu);
+        return pool().items.count(std::make_pair(current_device_or_default(device), key_of(stream))) != 0;
+    }, py::arg("device") = -1, py::arg("stream") = py::none());
+    mod.def("_set_profiling", [key_of](int device, py::object stream, bool on) {
+        check(pcu_b200_workspace_set_profiling(pool().get(current_device_or_default(device), key_of(stream)).ws, on ? 1 : 0));
     });
-    mod.def("_set_profiling", [](int device, uintptr_t stream, bool on) {
-        check(pcu_b200_workspace_set_profiling(pool().get(device, stream), on ? 1 : 0));
-    });
-    mod.def("_last_profile", [](int device, uintptr_t stream) {
+    mod.def("_last_profile", [key_of](int device, py::object stream) {
         float ms[8];
-        const int n = pcu_b200_workspace_last_profile(pool().get(device, stream), ms, 8);
+        const int n = pcu_b200_workspace_last_profile(pool().get(current_device_or_default(device), key_of(stream)).ws, ms, 8);
         py::dict d;
         for (int i = 0; i < n; ++i) d[py::str(pcu_b200_profile_stage_name(i))] = ms[i];
         return d;

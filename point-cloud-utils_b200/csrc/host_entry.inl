@@ -10,7 +10,7 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid value for k (%d) must be greater than 0.", k);
     PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
     if (!out_dist || !out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
     Carver measure(nullptr);
     auto carve = [&](Carver& cv, T*& dq, T*& dd, T*& od, long long*& oi, long long*& nt) {
         dq = cv.take<T>((size_t)3 * n);
@@ -21,7 +21,7 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     };
     T *dq, *dd, *od; long long *oi, *nt;
     carve(measure, dq, dd, od, oi, nt);
-    PCU_TRY(ensure_io(ws, measure.off));
+    PCU_TRY(ensure_io(ws, measure.off, ws->own_stream));
     Carver cv(ws->io);
     carve(cv, dq, dd, od, oi, nt);
     cudaStream_t st = ws->own_stream;
@@ -31,9 +31,15 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     PCU_CUDA(cudaMemcpyAsync(out_dist, od, sizeof(T) * n * k, cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaMemcpyAsync(out_idx, oi, sizeof(long long) * n * k, cudaMemcpyDeviceToHost, st));
     long long tied = 0;
+    unsigned overflows = 0;
     PCU_CUDA(cudaMemcpyAsync(&tied, nt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    if (ws->replay_overflows)
+        PCU_CUDA(cudaMemcpyAsync(&overflows, ws->replay_overflows, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
     if (out_n_tied) *out_n_tied = tied;
+    if (tied > 0 && overflows > 0)
+        return fail(PCU_B200_INTERNAL, "tie replay: the reference kd-tree of this dataset is deeper than the %d-frame walk "
+                    "stack (%u walks affected); neighbour order among exactly equidistant points is not guaranteed", kKdStack, overflows);
     return PCU_B200_OK;
 }
 
@@ -43,7 +49,7 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     PCU_TRY(check_cloud_args<T>(a, n, b, m));
     if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
     Carver measure(nullptr);
     auto carve = [&](Carver& cv, T*& da, T*& db, pcu_b200_nn_stats*& ds, T*& dv) {
         da = cv.take<T>((size_t)3 * n);
@@ -53,7 +59,7 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     };
     T *da, *db, *dv; pcu_b200_nn_stats* ds;
     carve(measure, da, db, ds, dv);
-    PCU_TRY(ensure_io(ws, measure.off));
+    PCU_TRY(ensure_io(ws, measure.off, ws->own_stream));
     Carver cv(ws->io);
     carve(cv, da, db, ds, dv);
     cudaStream_t st = ws->own_stream;
@@ -84,7 +90,7 @@ int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long lo
     if (batch <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "batch must be positive (got %lld)", batch);
     PCU_TRY(check_cloud_args<T>(x, n, y, m));
     if (!out_per_pair) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
     Carver measure(nullptr);
     auto carve = [&](Carver& cv, T*& dx, T*& dy, T*& dv, double*& dsum) {
         dx = cv.take<T>((size_t)3 * n * batch);
@@ -94,7 +100,7 @@ int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long lo
     };
     T *dx, *dy, *dv; double* dsum;
     carve(measure, dx, dy, dv, dsum);
-    PCU_TRY(ensure_io(ws, measure.off));
+    PCU_TRY(ensure_io(ws, measure.off, ws->own_stream));
     Carver cv(ws->io);
     carve(cv, dx, dy, dv, dsum);
     cudaStream_t st = ws->own_stream;
@@ -112,14 +118,13 @@ int debug_kd_tree(pcu_b200_workspace* ws, const T* points, long long m, int leaf
                   int32_t* feat, T* div_lo, T* div_hi, int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1,
                   int64_t* out_nodes) {
     if (!ws || !points || m <= 0 || leaf <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "bad argument");
-    PCU_CUDA(cudaSetDevice(ws->device));
-    PCU_CUDA(cudaDeviceSynchronize());
+    PCU_ON_DEVICE(ws);
     KdReplayBuffers<T> rb;
     T* dpts;
     Carver measure(nullptr);
     rb.carve(measure, m);
     dpts = measure.take<T>((size_t)3 * m);
-    PCU_TRY(ensure_arena(ws, measure.off));
+    PCU_TRY(ensure_arena(ws, measure.off, ws->own_stream));
     Carver cv(ws->arena);
     rb.carve(cv, m);
     dpts = cv.take<T>((size_t)3 * m);

@@ -71,6 +71,7 @@ struct KdReplayBuffers {
     KdNode<T>* nodes = nullptr;       // 2 * capacity
     KdCounters* counters = nullptr;
     unsigned* stub_hits = nullptr;    // searches that ran into a stub of the pruned build (-> full rebuild)
+    unsigned* overflows = nullptr;    // searches whose walk was deeper than kKdStack (adversarially deep trees): reported
     long long* one_row = nullptr;     // scratch for the single-query (witness) replay
     T* one_dist = nullptr;
     long long* one_idx = nullptr;
@@ -86,6 +87,7 @@ struct KdReplayBuffers {
         nodes = cv.take<KdNode<T>>((size_t)2 * points + 2);
         counters = cv.take<KdCounters>(1);
         stub_hits = cv.take<unsigned>(1);
+        overflows = cv.take<unsigned>(1);
         one_row = cv.take<long long>(1);
         one_dist = cv.take<T>(1);
         one_idx = cv.take<long long>(1);
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
     const unsigned gate_value = gate != nullptr ? *gate : 1u;
     // the pruned build opens a call's replay: it clears the stub counter (even when it has nothing to do)
     if (pr.enabled && blockIdx.x == 0 && threadIdx.x == 0) *b.stub_hits = 0u;
+    if (gate != b.stub_hits && blockIdx.x == 0 && threadIdx.x == 0) *b.overflows = 0u;   // first build of a replay
     if (gate_value == 0u) return;   // uniform over the grid
     unsigned n_flagged = 0u;   // 0: full build
     if (pr.enabled) {
@@ -601,6 +604,7 @@ __device__ bool kd_search_one(const KdReplayBuffers<T>& b, const T* __restrict__
             g.off[ft] = cut;
             g.far = true;
             if (top < kKdStack) stack[top++] = g;
+            else atomicAdd(b.overflows, 1u);   // never silently: the host entry points turn this into an error
             f.node = near_kid;
         }
     }
@@ -630,8 +634,9 @@ __global__ void kd_replay_kernel(KdReplayBuffers<T> b, const T* __restrict__ que
 // single query taken from a stats record (the Hausdorff witness)
 template <typename T>
 __global__ void kd_witness_kernel(KdReplayBuffers<T> b, const T* __restrict__ query, const T* __restrict__ pts,
-                                  pcu_b200_nn_stats* stats) {
+                                  long long n_queries, pcu_b200_nn_stats* stats) {
     const long long row = stats->argmax_query;
+    if (row < 0 || row >= n_queries) { stats->witness_tied = 0; return; }   // a record without a witness
     const T q[3] = {query[3 * row], query[3 * row + 1], query[3 * row + 2]};
     (void)kd_search_one<T>(b, pts, q, 1, true, b.one_dist, b.one_idx);   // full tree: no stubs
     stats->argmax_data = *b.one_idx;
@@ -653,15 +658,21 @@ int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int le
                      KdPrune<T> prune, cudaStream_t stream, std::atomic<long long>& launches) {
     if (m_ll > b.capacity || m_ll >= 0x7fffffffLL) return PCU_B200_INTERNAL;
     int m = (int)m_ll;
-    static int blocks_per_sm = 0, sms = 0;
-    if (blocks_per_sm == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+    // co-residency limits of the cooperative launch, cached per device (a process may drive several GPUs)
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> cached_blocks[kMaxDevices], cached_sms[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+    const int slot = dev >= 0 && dev < kMaxDevices ? dev : 0;
+    int blocks_per_sm = cached_blocks[slot].load(std::memory_order_acquire), sms = cached_sms[slot].load(std::memory_order_acquire);
+    if (blocks_per_sm == 0 || slot != dev) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return PCU_B200_CUDA_ERROR;
         int f32 = 0, f64 = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f32, kd_build_kernel<float>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f64, kd_build_kernel<double>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
         blocks_per_sm = std::max(1, std::min(8, std::min(f32, f64)));   // enough threads to cover the latency of the element passes
+        cached_sms[slot].store(sms, std::memory_order_release);
+        cached_blocks[slot].store(blocks_per_sm, std::memory_order_release);
     }
     const long long want = (m_ll + kThreads - 1) / kThreads;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, (long long)blocks_per_sm * sms));
@@ -703,11 +714,11 @@ int enqueue_tie_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, 
 
 // Replays the single query stats->argmax_query (already known to be tie-dependent).
 template <typename T>
-int enqueue_witness_replay(KdReplayBuffers<T>& b, const T* query, const T* dataset, long long m, int leaf_cap,
+int enqueue_witness_replay(KdReplayBuffers<T>& b, const T* query, long long n, const T* dataset, long long m, int leaf_cap,
                            pcu_b200_nn_stats* stats, cudaStream_t stream, std::atomic<long long>& launches) {
     const int st = build_kd_replica<T>(b, dataset, m, leaf_cap, nullptr, KdPrune<T>{}, stream, launches);
     if (st != PCU_B200_OK) return st;
-    KD_LAUNCH(kd_witness_kernel<T>, 1, 1, stream, b, query, dataset, stats);
+    KD_LAUNCH(kd_witness_kernel<T>, 1, 1, stream, b, query, dataset, n, stats);
     return PCU_B200_OK;
 }
 

@@ -301,9 +301,12 @@ __device__ __forceinline__ void finalize_sweep(const Sweep<T>& sw, SweepPartial<
 }
 
 // chamfer = mean_x |x - NN_y(x)| + mean_y |y - NN_x(y)|  (point_cloud_utils/__init__.py:112-115)
+__device__ __forceinline__ double chamfer_of64(const pcu_b200_nn_stats& a, const pcu_b200_nn_stats& b) {
+    return a.sum_dist / (double)a.n_queries + b.sum_dist / (double)b.n_queries;
+}
 template <typename T>
 __device__ __forceinline__ T chamfer_of(const pcu_b200_nn_stats& a, const pcu_b200_nn_stats& b) {
-    return (T)(a.sum_dist / (double)a.n_queries + b.sum_dist / (double)b.n_queries);
+    return (T)chamfer_of64(a, b);
 }
 
 // stats: 2 per pair ([2p] = x->y, [2p+1] = y->x).  One block; pairs strided over its threads.
@@ -311,7 +314,7 @@ __device__ __forceinline__ T chamfer_of(const pcu_b200_nn_stats& a, const pcu_b2
 template <typename T>
 __global__ void __launch_bounds__(kThreads) chamfer_value_kernel(const pcu_b200_nn_stats* __restrict__ stats,
                                                                  long long npairs, T* __restrict__ out_value,
-                                                                 double* __restrict__ out_sum) {
+                                                                 double* __restrict__ out_sum, int accumulate) {
     double acc = 0.0;
     for (long long p = threadIdx.x; p < npairs; p += blockDim.x) {
         const T vt = chamfer_of<T>(stats[2 * p], stats[2 * p + 1]);
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(kThreads) chamfer_value_kernel(const pcu_b200_
         if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out_sum = s[0];
+    if (threadIdx.x == 0) *out_sum = accumulate ? *out_sum + s[0] : s[0];   // later slices of one call add up (stream order)
 }
 
 }  // namespace pcu

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -199,6 +200,10 @@ struct pcu_b200_workspace {
     long long hint_key[5] = {0, 0, 0, 0, 0};   // n, m, k, sizeof(T), batch of the call the hints belong to
     float cell_mult[2] = {1.f, 1.f};           // current refinement of the two clouds' grids (cells per point x this)
     float cell_mult_ceiling[2] = {32.f, 32.f}; // lowered when a refinement left too many queries unsettled
+    const unsigned* replay_overflows = nullptr;   // device counter of the last KNN call's tie replay (null: none ran)
+    cudaStream_t last_stream = nullptr;  // stream of the previous call (see adopt_stream)
+    bool has_last_stream = false;
+    cudaEvent_t handover = nullptr;
     bool profiling = false;
     cudaEvent_t marks[9] = {};
     int marks_used = 0;
@@ -208,40 +213,70 @@ struct pcu_b200_workspace {
 
 namespace {
 
-int ensure_arena(pcu_b200_workspace* ws, size_t bytes) {
-    if (bytes <= ws->arena_bytes) return PCU_B200_OK;
-    if (ws->arena) {
-        PCU_CUDA(cudaDeviceSynchronize());  // earlier calls may still be using the old arena
-        PCU_CUDA(cudaFree(ws->arena));
-        ws->arena = nullptr;
-        ws->arena_bytes = 0;
+// Makes ws->device current for the duration of an entry point and puts the caller's device back on every
+// exit path (a torch program with cuda:0 current that passes cuda:1 tensors keeps cuda:0 current).
+struct DeviceGuard {
+    int previous = -1;
+    bool switched = false;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        status = cudaGetDevice(&previous);
+        if (status == cudaSuccess && previous != device) {
+            status = cudaSetDevice(device);
+            switched = status == cudaSuccess;
+        }
     }
-    const size_t want = align_up(bytes + bytes / 8, 1 << 20);
-    cudaError_t e = cudaMalloc(&ws->arena, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(PCU_B200_OUT_OF_MEMORY, "cudaMalloc of %zu bytes of scratch failed: %s", want, cudaGetErrorString(e));
+    ~DeviceGuard() { if (switched) cudaSetDevice(previous); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define PCU_ON_DEVICE(ws)                                                                              \
+    DeviceGuard device_guard__((ws)->device);                                                          \
+    if (device_guard__.status != cudaSuccess)                                                          \
+        return fail(PCU_B200_CUDA_ERROR, "cudaSetDevice(%d) failed: %s", (ws)->device, cudaGetErrorString(device_guard__.status))
+
+// A workspace serves one stream at a time.  When a call arrives on another stream than the previous one,
+// the new stream is made to wait (on the device) for everything the previous call enqueued: the scratch is shared.
+int adopt_stream(pcu_b200_workspace* ws, cudaStream_t stream) {
+    if (ws->has_last_stream && ws->last_stream != stream) {
+        if (!ws->handover) PCU_CUDA(cudaEventCreateWithFlags(&ws->handover, cudaEventDisableTiming));
+        PCU_CUDA(cudaEventRecord(ws->handover, ws->last_stream));
+        PCU_CUDA(cudaStreamWaitEvent(stream, ws->handover, 0));
     }
-    ws->arena_bytes = want;
+    ws->last_stream = stream;
+    ws->has_last_stream = true;
     return PCU_B200_OK;
 }
 
-int ensure_io(pcu_b200_workspace* ws, size_t bytes) {
-    if (bytes <= ws->io_bytes) return PCU_B200_OK;
-    if (ws->io) {
-        PCU_CUDA(cudaDeviceSynchronize());
-        PCU_CUDA(cudaFree(ws->io));
-        ws->io = nullptr;
-        ws->io_bytes = 0;
+// Scratch grows with stream-ordered allocation: the old block is released and the new one obtained in the
+// order of `stream`, so earlier calls still queued there keep their memory until they are done and neither
+// the host nor the rest of the device is synchronised.
+int grow_block(unsigned char*& block, size_t& have, size_t bytes, cudaStream_t stream, const char* what) {
+    if (bytes <= have) return PCU_B200_OK;
+    if (block) {
+        PCU_CUDA(cudaFreeAsync(block, stream));
+        block = nullptr;
+        have = 0;
     }
     const size_t want = align_up(bytes + bytes / 8, 1 << 20);
-    cudaError_t e = cudaMalloc(&ws->io, want);
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, want, stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return fail(PCU_B200_OUT_OF_MEMORY, "cudaMalloc of %zu bytes of staging failed: %s", want, cudaGetErrorString(e));
+        return fail(PCU_B200_OUT_OF_MEMORY, "cudaMallocAsync of %zu bytes of %s failed: %s", want, what, cudaGetErrorString(e));
     }
-    ws->io_bytes = want;
+    block = (unsigned char*)p;
+    have = want;
     return PCU_B200_OK;
+}
+
+int ensure_arena(pcu_b200_workspace* ws, size_t bytes, cudaStream_t stream) {
+    PCU_TRY(adopt_stream(ws, stream));
+    return grow_block(ws->arena, ws->arena_bytes, bytes, stream, "scratch");
+}
+
+int ensure_io(pcu_b200_workspace* ws, size_t bytes, cudaStream_t stream) {
+    return grow_block(ws->io, ws->io_bytes, bytes, stream, "staging");
 }
 
 void mark(pcu_b200_workspace* ws, int index, cudaStream_t stream) {
@@ -482,10 +517,10 @@ void apply_grid_feedback(pcu_b200_workspace* ws, PlanSpec<T>& spec) {
 }
 
 template <typename T>
-int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, PlanSpec<T>& spec) {
+int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, PlanSpec<T>& spec, cudaStream_t stream) {
     apply_grid_feedback(ws, spec);
     plan.layout(nullptr, spec);
-    PCU_TRY(ensure_arena(ws, plan.total));
+    PCU_TRY(ensure_arena(ws, plan.total, stream));
     plan.layout(ws->arena, spec);
     return PCU_B200_OK;
 }
@@ -537,8 +572,10 @@ int check_cloud_args(const void* a, long long n, const void* b, long long m) {
         return fail(PCU_B200_INVALID_ARGUMENT,
                     "Invalid input set with zero elements: both clouds must have shape (n, 3) with n > 0 "
                     "(got %lld and %lld rows)", n, m);
-    const long long lim = sizeof(T) == 4 ? 0x7fffffffLL : (1LL << 40);
-    if (n >= lim || m >= lim) return fail(PCU_B200_INVALID_ARGUMENT, "point cloud too large (%lld, %lld rows)", n, m);
+    // rows, cell prefixes and list entries are 32-bit throughout the pipeline, whatever the coordinate type
+    const long long lim = 0x7fffffffLL;
+    if (n >= lim || m >= lim)
+        return fail(PCU_B200_INVALID_ARGUMENT, "point cloud too large (%lld, %lld rows; at most 2^31 - 2 are supported)", n, m);
     return PCU_B200_OK;
 }
 
@@ -551,7 +588,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
     if (!out_dist || !out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     if ((double)n * (double)k >= 9e18) return fail(PCU_B200_INVALID_ARGUMENT, "n * k overflows");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
 
     PlanSpec<T> spec;
     spec.a = query; spec.n = n; spec.b = dataset; spec.m = m;
@@ -561,7 +598,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     spec.out_dist = out_dist; spec.out_idx = out_idx;
     spec.replay_points = ws->opts.disable_tie_replay == 1 ? 0 : m;
     Plan<T> plan;
-    PCU_TRY(prepare_plan(ws, plan, spec));
+    PCU_TRY(prepare_plan(ws, plan, spec, stream));
     mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
     mark(ws, 1, stream);
@@ -595,6 +632,9 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         const int rs = enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
                                              plan.args.sweep[0].counters + 1, n, out_dist, out_idx, ws->opts.disable_tie_replay, stream, g_launches);
         if (rs != PCU_B200_OK) return fail(rs, "tie replay failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ws->replay_overflows = plan.replay.overflows;
+    } else {
+        ws->replay_overflows = nullptr;
     }
     if (out_n_tied) {
         PCU_LAUNCH(widen_counter_kernel, 1, 1, stream, plan.args.sweep[0].counters + 1, out_n_tied);
@@ -611,7 +651,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     PCU_TRY(check_cloud_args<T>(a, n, b, m));
     if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
     const int ns = both ? 2 : 1;
     PlanSpec<T> spec;
     spec.a = a; spec.n = n; spec.b = b; spec.m = m;
@@ -621,7 +661,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     spec.stats = out_stats;
     spec.value_out = both ? out_value : nullptr;
     Plan<T> plan;
-    PCU_TRY(prepare_plan(ws, plan, spec));
+    PCU_TRY(prepare_plan(ws, plan, spec, stream));
     mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
     mark(ws, 1, stream);
@@ -643,16 +683,16 @@ int resolve_witness_device(pcu_b200_workspace* ws, const T* query, long long n, 
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
     if (!stats) return fail(PCU_B200_INVALID_ARGUMENT, "null stats pointer");
-    PCU_CUDA(cudaSetDevice(ws->device));
-    PCU_CUDA(cudaStreamSynchronize(stream));   // the arena is about to be re-carved
+    PCU_ON_DEVICE(ws);
+    // the arena is re-carved in stream order: the sweep that produced `stats` has been enqueued before us
     KdReplayBuffers<T> rb;
     Carver measure(nullptr);
     rb.carve(measure, m);
-    PCU_TRY(ensure_arena(ws, measure.off));
+    PCU_TRY(ensure_arena(ws, measure.off, stream));
     Carver cv(ws->arena);
     rb.carve(cv, m);
     const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
-    const int rs = enqueue_witness_replay<T>(rb, query, dataset, m, leaf, stats, stream, g_launches);
+    const int rs = enqueue_witness_replay<T>(rb, query, n, dataset, m, leaf, stats, stream, g_launches);
     if (rs != PCU_B200_OK) return fail(rs, "witness replay failed: %s", cudaGetErrorString(cudaGetLastError()));
     return PCU_B200_OK;
 }
@@ -665,11 +705,9 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
     if (batch <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "batch must be positive (got %lld)", batch);
     PCU_TRY(check_cloud_args<T>(x, n, y, m));
     if (!out_per_pair && !out_sum) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
     // gridDim.y carries the cloud / sweep index: at most 65535, i.e. 32767 pairs per slice
     const long long slice = 16384;
-    if (batch > slice && out_sum)
-        return fail(PCU_B200_INVALID_ARGUMENT, "out_sum is only supported for batches of at most %lld pairs", slice);
     for (long long first = 0; first < batch; first += slice) {
         const long long B = std::min(slice, batch - first);
         PlanSpec<T> spec;
@@ -679,7 +717,7 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         spec.occupancy = occupancy_for(ws, 1);
         spec.binning = ws->opts.binning;
         Plan<T> plan;
-        PCU_TRY(prepare_plan(ws, plan, spec));
+        PCU_TRY(prepare_plan(ws, plan, spec, stream));
         mark(ws, 0, stream);
         PCU_TRY(upload_descriptors(plan, stream));
         mark(ws, 1, stream);
@@ -691,7 +729,7 @@ int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long 
         PCU_LAUNCH_CS(nn1_vfar_kernel, dim3(plan.far_blocks, plan.nsweeps_total), kThreads, false, true);
         mark(ws, 7, stream);
         PCU_LAUNCH(chamfer_value_kernel<T>, 1, kThreads, stream, plan.d_stats, B,
-                   out_per_pair ? out_per_pair + first : (T*)nullptr, out_sum);
+                   out_per_pair ? out_per_pair + first : (T*)nullptr, out_sum, first > 0 ? 1 : 0);
         mark(ws, 8, stream);
     }
     return PCU_B200_OK;
@@ -717,6 +755,31 @@ int pcu_b200_device_count(void) {
     return usable;
 }
 
+// Which device a call that names none should run on (the reference's interface has no device argument):
+// PCU_B200_DEVICE if set; else the CUDA runtime's current device when the caller has chosen one other than 0
+// (torch.cuda.set_device / torch.cuda.device(...) in this thread); else LOCAL_RANK when a launcher such as
+// torchrun set it and that many devices are visible; else device 0.
+int pcu_b200_current_device(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return 0; }
+    auto from_env = [&](const char* name) {
+        const char* v = std::getenv(name);
+        if (!v || !*v) return -1;
+        char* end = nullptr;
+        const long d = std::strtol(v, &end, 10);
+        return (end && *end == '\0' && d >= 0 && d < count) ? (int)d : -1;
+    };
+    int d = from_env("PCU_B200_DEVICE");
+    if (d >= 0) return d;
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; }
+    if (cur > 0) return cur;
+    d = from_env("LOCAL_RANK");
+    return d >= 0 ? d : 0;
+}
+
+int pcu_b200_workspace_device(const pcu_b200_workspace* ws) { return ws ? ws->device : -1; }
+
 int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
     if (!out_ws) return fail(PCU_B200_INVALID_ARGUMENT, "null out_ws");
     *out_ws = nullptr;
@@ -736,7 +799,8 @@ int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
     if (!ws) return fail(PCU_B200_OUT_OF_MEMORY, "out of host memory");
     ws->device = device;
     ws->sm_count = sms;
-    PCU_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    if (guard.status != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.status)); }
     cudaError_t e = cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     void* hint = nullptr;
@@ -759,10 +823,11 @@ int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
 
 int pcu_b200_workspace_destroy(pcu_b200_workspace* ws) {
     if (!ws) return PCU_B200_OK;
-    cudaSetDevice(ws->device);
+    DeviceGuard guard(ws->device);
     cudaDeviceSynchronize();
     if (ws->arena) cudaFree(ws->arena);
     if (ws->io) cudaFree(ws->io);
+    if (ws->handover) cudaEventDestroy(ws->handover);
     if (ws->hint_host) cudaFreeHost((void*)ws->hint_host);
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
     for (auto& e : ws->marks) if (e) cudaEventDestroy(e);
@@ -776,7 +841,7 @@ int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws) {
 
 int pcu_b200_workspace_set_profiling(pcu_b200_workspace* ws, int enabled) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
-    PCU_CUDA(cudaSetDevice(ws->device));
+    PCU_ON_DEVICE(ws);
     if (enabled && !ws->marks[0])
         for (auto& e : ws->marks) PCU_CUDA(cudaEventCreate(&e));
     ws->profiling = enabled != 0;

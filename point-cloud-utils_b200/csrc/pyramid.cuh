@@ -150,19 +150,38 @@ __device__ void conclude_sweep(const Sweep<T>& sw, const Cloud<T>& qc, const Clo
             st.n_tied = -1;   // not tracked by the statistics-only sweep
             st.n_far = (long long)sw.counters[0];
             st.witness_tied = wb.tie ? 1 : 0;
+            st.pair_value = result.sum / (double)qc.n;   // overwritten by the pair's value in bidirectional calls
             *sw.stats = st;
         }
+    } else if (threadIdx.x == 0 && !(result.max_d2 >= (T)0)) {
+        // no query produced a comparable distance (non-finite coordinates): the record is still written, with
+        // no witness, so that callers never decode uninitialised memory
+        pcu_b200_nn_stats st;
+        st.sum_dist = result.sum;
+        st.sum_sq_dist = result.sumsq;
+        st.max_sq_dist = (double)result.max_d2;
+        st.argmax_query = -1;
+        st.argmax_data = -1;
+        st.n_queries = qc.n;
+        st.n_tied = -1;
+        st.n_far = (long long)sw.counters[0];
+        st.witness_tied = 0;
+        st.pair_value = result.sum / (double)qc.n;
+        *sw.stats = st;
     }
     __syncthreads();
-    if (sw.value_out != nullptr && threadIdx.x == 0) {
+    if (sw.pair_stats != nullptr && sw.pair_ticket != nullptr && threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(sw.pair_ticket, 1u) == 1u) {
+        if (atomicAdd(sw.pair_ticket, 1u) == 1u) {   // the sweep of the pair that finishes second
             __threadfence();
-            const volatile pcu_b200_nn_stats* ps = sw.pair_stats;
+            volatile pcu_b200_nn_stats* ps = sw.pair_stats;
             pcu_b200_nn_stats a, b;
             a.sum_dist = ps[0].sum_dist; a.n_queries = ps[0].n_queries;
             b.sum_dist = ps[1].sum_dist; b.n_queries = ps[1].n_queries;
-            *sw.value_out = chamfer_of<T>(a, b);
+            const double v = chamfer_of64(a, b);
+            ps[0].pair_value = v;
+            ps[1].pair_value = v;
+            if (sw.value_out != nullptr) *sw.value_out = (T)v;
         }
     }
 }

@@ -24,13 +24,13 @@ def test_library_exports_every_declared_symbol(pcu):
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     lib.pcu_b200_abi_version.restype = ctypes.c_int
-    assert lib.pcu_b200_abi_version() == 2
+    assert lib.pcu_b200_abi_version() == 3
     lib.pcu_b200_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.pcu_b200_last_error(), bytes)
 
 
 def test_stats_struct_layout(pcu):
-    assert pcu._pcu_internal._stats_nbytes() == 72
+    assert pcu._pcu_internal._stats_nbytes() == 80
 
 
 def test_no_cpu_fallback_without_gpu(pcu):
@@ -66,19 +66,57 @@ def test_argument_errors_are_value_errors(pcu):
         pcu.chamfer_distance(a[:, :2], b)
 
 
-def test_signatures_match_the_reference(pcu):
+def _reference_parameters(fn):
+    """Positional parameters (the reference's) and keyword-only extras of a public function."""
     import inspect
-    sig = inspect.signature(pcu.k_nearest_neighbors)
-    assert list(sig.parameters) == ["query_points", "dataset_points", "k", "squared_distances", "max_points_per_leaf",
-                                    "num_threads"]
+    sig = inspect.signature(fn)
+    positional = [p for p in sig.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+    extras = [p for p in sig.parameters.values() if p.kind == p.KEYWORD_ONLY]
+    assert len(positional) + len(extras) == len(sig.parameters)
+    return sig, [p.name for p in positional], [p.name for p in extras]
+
+
+def test_signatures_match_the_reference(pcu):
+    """Names, order and defaults of the reference's parameters; the only addition is the keyword-only
+    `device` (the reference is CPU code and has no such notion), which never shifts a positional argument."""
+    sig, names, extras = _reference_parameters(pcu.k_nearest_neighbors)
+    assert names == ["query_points", "dataset_points", "k", "squared_distances", "max_points_per_leaf", "num_threads"]
+    assert extras == ["device"] and sig.parameters["device"].default is None
     assert sig.parameters["squared_distances"].default is False
     assert sig.parameters["max_points_per_leaf"].default == 10 and sig.parameters["num_threads"].default == -1
-    sig = inspect.signature(pcu.one_sided_hausdorff_distance)
-    assert list(sig.parameters) == ["source", "target", "return_index", "squared_distances", "max_points_per_leaf"]
+    sig, names, extras = _reference_parameters(pcu.one_sided_hausdorff_distance)
+    assert names == ["source", "target", "return_index", "squared_distances", "max_points_per_leaf"]
+    assert extras == ["device"]
     assert sig.parameters["return_index"].default is True     # point_cloud_distance.cpp:189
-    sig = inspect.signature(pcu.hausdorff_distance)
-    assert list(sig.parameters) == ["x", "y", "return_index", "squared_distances", "max_points_per_leaf"]
+    sig, names, extras = _reference_parameters(pcu.hausdorff_distance)
+    assert names == ["x", "y", "return_index", "squared_distances", "max_points_per_leaf"] and extras == ["device"]
     assert sig.parameters["return_index"].default is False    # __init__.py:52
-    sig = inspect.signature(pcu.chamfer_distance)
-    assert list(sig.parameters) == ["x", "y", "return_index", "p_norm", "max_points_per_leaf"]
+    sig, names, extras = _reference_parameters(pcu.chamfer_distance)
+    assert names == ["x", "y", "return_index", "p_norm", "max_points_per_leaf"] and extras == ["device"]
     assert sig.parameters["p_norm"].default == 2
+
+
+def test_device_argument_is_validated_on_the_host(pcu):
+    a = np.random.rand(10, 3)
+    for bad in ("cpu", "cuda:x", 1.5, -2):
+        with pytest.raises(ValueError, match="device"):
+            pcu.chamfer_distance(a, a, device=bad)
+    with pytest.raises(ValueError, match="out of range"):
+        pcu.k_nearest_neighbors(a, a, 1, device=pcu.device_count() + 7)
+
+
+def test_current_device_rule(pcu):
+    """PCU_B200_DEVICE / LOCAL_RANK only count when they name a visible device; with no GPU the answer is 0."""
+    import os
+    old = {k: os.environ.pop(k, None) for k in ("PCU_B200_DEVICE", "LOCAL_RANK")}
+    try:
+        assert pcu.current_device() == 0 or pcu.device_count() > 1
+        os.environ["LOCAL_RANK"] = "5"
+        os.environ["PCU_B200_DEVICE"] = "not-a-number"
+        d = pcu.current_device()
+        assert d == (5 if pcu.device_count() > 5 else d) and 0 <= d < max(1, pcu.device_count())
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v

@@ -1,0 +1,228 @@
+"""GPU: BASELINE.json configs[3] (C4: k = 16, 1e7 queries vs 1e6 points) and configs[4] (C5: 1024 pairs of
+2 x 65536 points) at their FULL sizes, the C-ABI compute entry points driven through ctypes exactly as
+INTEGRATION.md section 3 binds them, and the device-selection / stream-ordering rules of the host API.
+
+Full-size checks use size-independent properties on the device plus the reference's own nanoflann path
+(oracle/_ref through the `oracle` fixture) on random subsets that the host finishes in seconds."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+REL = 1e-6
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _reference_d2(q, p):
+    """((qx-px)^2 + (qy-py)^2) + (qz-pz)^2 with every operation rounded separately (eager torch ops do not fuse)."""
+    diff = q - p
+    sq = diff * diff
+    return (sq[..., 0] + sq[..., 1]) + sq[..., 2]
+
+
+def test_c4_full_size_k16(pcu, oracle):
+    """k_nearest_neighbors k = 16 on 1e7 x 3 queries vs 1e6 x 3 points, fp32 (1.92 GB of results)."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, m, k = 10_000_000, 1_000_000, 16
+    q = torch.rand((n, 3), generator=g, device="cuda")
+    d = torch.rand((m, 3), generator=g, device="cuda")
+    dist, idx = pcu.k_nearest_neighbors(q, d, k)
+    assert dist.shape == (n, k) and idx.shape == (n, k) and idx.dtype == torch.int64
+    assert int(idx.min()) >= 0 and int(idx.max()) < m
+    # (a) every returned distance is the distance to the returned index, in the reference's rounding, and
+    # (b) rows ascend; checked over all 1.6e8 entries, a slab of rows at a time
+    step = 1_000_000
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        d2 = _reference_d2(q[lo:hi, None, :], d[idx[lo:hi]])
+        assert torch.equal(dist[lo:hi], torch.sqrt(d2)), "distance != distance to the returned index (rows %d..%d)" % (lo, hi)
+        assert bool((dist[lo:hi, 1:] >= dist[lo:hi, :-1]).all()), "row not ascending"
+        same = idx[lo:hi, 1:] == idx[lo:hi, :-1]
+        assert not bool(same.any()), "an index appears twice in a row"
+    # (c) nothing nearer was missed: brute force in fp64 on random rows (the 16 smallest of 1e6 distances)
+    rows = torch.randperm(n, generator=g, device="cuda")[:1024]
+    brute = torch.cdist(q[rows].double(), d.double()).topk(k, dim=1, largest=False).values
+    assert bool(((dist[rows].double() - brute).abs() <= 1e-6).all())
+    # (d) the reference itself (nanoflann, same dataset) on a random 50 000-row subset: every index and distance
+    sub = torch.randperm(n, generator=g, device="cuda")[:50_000]
+    ref_d, ref_i = oracle.k_nearest_neighbors(q[sub].cpu().numpy(), d.cpu().numpy(), k)
+    assert np.array_equal(idx[sub].cpu().numpy(), ref_i)
+    assert np.array_equal(dist[sub].cpu().numpy(), ref_d)
+    # rows at the very end of the output (row * k indexing beyond 2^27 elements)
+    tail = torch.arange(n - 2000, n, device="cuda")
+    ref_d, ref_i = oracle.k_nearest_neighbors(q[tail].cpu().numpy(), d.cpu().numpy(), k)
+    assert np.array_equal(idx[tail].cpu().numpy(), ref_i) and np.array_equal(dist[tail].cpu().numpy(), ref_d)
+
+
+def test_c5_full_size_batched_chamfer(pcu, oracle):
+    """batched Chamfer on 1024 pairs of 2 x (65536 x 3) fp32: 1.6 GB of input, descriptor strides beyond 4 GB."""
+    import importlib
+    import torch
+    bmod = importlib.import_module("point-cloud-utils_b200._batched")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, n = 1024, 65536
+    x = torch.rand((B, n, 3), generator=g, device="cuda")
+    y = torch.rand((B, n, 3), generator=g, device="cuda")
+    vals, total = bmod.batched_chamfer(x, y, return_sum=True)
+    assert vals.shape == (B,) and vals.dtype == torch.float32 and total.dtype == torch.float64
+    vh = vals.cpu().numpy()
+    assert np.all(np.isfinite(vh)) and np.all(vh > 0)
+    # per-pair value against the reference for 16 pairs, the first and the last among them
+    rng = np.random.default_rng(55)
+    pairs = sorted(set([0, B - 1] + [int(p) for p in rng.choice(B, 14, replace=False)]))
+    for p in pairs:
+        ref = float(oracle.chamfer_distance(x[p].cpu().numpy(), y[p].cpu().numpy()))
+        assert abs(float(vh[p]) - ref) <= REL * ref, (p, float(vh[p]), ref)
+        one = float(pcu.chamfer_distance(x[p], y[p]))
+        assert abs(float(vh[p]) - one) <= 1e-7 * ref, (p, float(vh[p]), one)
+    # the device-side fp64 sum (what a multi-GPU caller all-reduces) is the sum of the per-pair values
+    expect = float(vh.astype(np.float64).sum())
+    assert abs(float(total) - expect) <= 1e-12 * expect
+
+
+def test_batched_sum_over_more_than_one_slice(pcu, oracle):
+    """More pairs than one launch addresses (gridDim.y): the batch is cut in slices and the fp64 sum runs on."""
+    import importlib
+    import torch
+    bmod = importlib.import_module("point-cloud-utils_b200._batched")
+    g = torch.Generator(device="cuda").manual_seed(6)
+    B = 20_000
+    x = torch.rand((B, 24, 3), generator=g, device="cuda")
+    y = torch.rand((B, 17, 3), generator=g, device="cuda")
+    vals, total = bmod.batched_chamfer(x, y, return_sum=True)
+    vh = vals.cpu().numpy()
+    assert abs(float(total) - float(vh.astype(np.float64).sum())) <= 1e-12 * float(total)
+    for p in (0, 16383, 16384, B - 1):
+        ref = float(oracle.chamfer_distance(x[p].cpu().numpy(), y[p].cpu().numpy()))
+        assert abs(float(vh[p]) - ref) <= REL * ref
+
+
+# ---- the C ABI through ctypes, exactly as INTEGRATION.md section 3 shows it ---------------------------------
+class NNStats(ctypes.Structure):
+    _fields_ = [("sum_dist", ctypes.c_double), ("sum_sq_dist", ctypes.c_double), ("max_sq_dist", ctypes.c_double),
+                ("argmax_query", ctypes.c_int64), ("argmax_data", ctypes.c_int64), ("n_queries", ctypes.c_int64),
+                ("n_tied", ctypes.c_int64), ("n_far", ctypes.c_int64), ("witness_tied", ctypes.c_int64),
+                ("pair_value", ctypes.c_double)]
+
+
+def test_ctypes_binding_of_the_host_entry_points(pcu):
+    from conftest import load_golden
+    lib = ctypes.CDLL(os.path.join(ROOT, "point-cloud-utils_b200", "libpcu_b200.so"))
+    lib.pcu_b200_last_error.restype = ctypes.c_char_p
+    ws = ctypes.c_void_p()
+    assert lib.pcu_b200_workspace_create(0, ctypes.byref(ws)) == 0, lib.pcu_b200_last_error()
+    try:
+        g = load_golden("metrics_f32_20k_15k")
+        x = np.ascontiguousarray(g["x"], np.float32)
+        y = np.ascontiguousarray(g["y"], np.float32)
+        st = (NNStats * 2)()
+        val = ctypes.c_float()
+        rc = lib.pcu_b200_chamfer_host_f32(ws, x.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(x)),
+                                           y.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(y)), st,
+                                           ctypes.byref(val))
+        assert rc == 0, lib.pcu_b200_last_error()
+        ref = float(g["chamfer_f64"])
+        assert abs(val.value - ref) <= REL * ref
+        # the two records carry the one-sided Hausdorff results of both directions (squared distances)
+        d_xy, i_xy, j_xy = g["one_sided_xy_sq1"]
+        d_yx, i_yx, j_yx = g["one_sided_yx_sq1"]
+        assert (np.float32(st[0].max_sq_dist), st[0].argmax_query, st[0].argmax_data) == (np.float32(d_xy), int(i_xy), int(j_xy))
+        assert (np.float32(st[1].max_sq_dist), st[1].argmax_query, st[1].argmax_data) == (np.float32(d_yx), int(i_yx), int(j_yx))
+        assert st[0].n_queries == len(x) and st[1].n_queries == len(y)
+        # k nearest neighbours through the same handle
+        g = load_golden("uniform_f32_5k_50k")
+        q = np.ascontiguousarray(g["query"], np.float32)
+        d = np.ascontiguousarray(g["dataset"], np.float32)
+        k = int(g["ks"][-1])
+        leaf = int(g["leafs"][0])
+        dist = np.empty((len(q), k), np.float32)
+        idx = np.empty((len(q), k), np.int64)
+        tied = ctypes.c_int64(-1)
+
+        class Options(ctypes.Structure):
+            _fields_ = [("max_points_per_leaf", ctypes.c_int), ("cell_occupancy", ctypes.c_float),
+                        ("disable_tie_replay", ctypes.c_int), ("binning", ctypes.c_int)]
+        opt = Options(leaf, 0.0, 0, 0)
+        assert lib.pcu_b200_workspace_set_options(ws, ctypes.byref(opt)) == 0
+        rc = lib.pcu_b200_knn_host_f32(ws, q.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(q)),
+                                       d.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(d)), k, 0,
+                                       dist.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p),
+                                       ctypes.byref(tied))
+        assert rc == 0, lib.pcu_b200_last_error()
+        tag = "k%d_leaf%d_sq0" % (k, leaf)
+        assert np.array_equal(idx.squeeze(), g["idx_" + tag]) and np.array_equal(dist.squeeze(), g["dist_" + tag])
+        assert tied.value >= 0
+        # argument errors come back as status 1 with a message, never as a crash
+        rc = lib.pcu_b200_knn_host_f32(ws, q.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(q)),
+                                       d.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(d)), 0, 0,
+                                       dist.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p), None)
+        assert rc == 1 and b"Invalid value for k" in lib.pcu_b200_last_error()
+        lib.pcu_b200_workspace_device.restype = ctypes.c_int
+        assert lib.pcu_b200_workspace_device(ws) == 0
+    finally:
+        assert lib.pcu_b200_workspace_destroy(ws) == 0
+
+
+# ---- which GPU the numpy path runs on; what a call leaves behind ------------------------------------------
+def test_numpy_path_follows_the_current_device(pcu, oracle):
+    """The reference's interface has no device argument: numpy calls run on torch's current device (or the one
+    named by the keyword-only `device=`), never silently on GPU 0."""
+    import torch
+    internal = pcu._pcu_internal
+    rng = np.random.default_rng(17)
+    x = rng.random((30000, 3), dtype=np.float32)
+    y = rng.random((20000, 3), dtype=np.float32)
+    ref = float(oracle.chamfer_distance(x, y))
+    ref_knn = oracle.k_nearest_neighbors(x, y, 3)
+    ndev = pcu.device_count()
+    target = 1 if ndev >= 2 else 0
+    internal._release_workspaces()
+    with torch.cuda.device(target):
+        assert pcu.current_device() == target
+        c = pcu.chamfer_distance(x, y)
+        assert abs(float(c) - ref) <= REL * ref
+        assert internal._workspace_exists(target) and internal._workspace_bytes(target) > 0
+        if ndev >= 2:
+            assert not internal._workspace_exists(0), "the numpy path ran on GPU 0 although cuda:1 is current"
+    assert torch.cuda.current_device() == 0
+    # explicit keyword, whatever is current
+    internal._release_workspaces()
+    got = pcu.k_nearest_neighbors(x, y, 3, device=target)
+    assert np.array_equal(got[1], ref_knn[1]) and np.array_equal(got[0], ref_knn[0])
+    assert internal._workspace_exists(target) and (ndev < 2 or not internal._workspace_exists(0))
+    assert pcu.hausdorff_distance(x, y, return_index=True, device="cuda:%d" % target) == \
+        oracle.hausdorff_distance(x, y, return_index=True)
+    assert abs(float(pcu.batched_chamfer_distance(x[None], y[None], device=torch.device("cuda", target))[0]) - ref) <= REL * ref
+    if ndev >= 2:
+        # tensors on cuda:1 while cuda:0 is current: runs on cuda:1 and leaves cuda:0 current
+        xt, yt = torch.from_numpy(x).to("cuda:1"), torch.from_numpy(y).to("cuda:1")
+        d, i = pcu.k_nearest_neighbors(xt, yt, 3)
+        assert d.device.index == 1 and torch.cuda.current_device() == 0
+        assert np.array_equal(i.cpu().numpy(), ref_knn[1])
+        with pytest.raises(ValueError, match="contradicts"):
+            pcu.k_nearest_neighbors(xt, yt, 3, device=0)
+
+
+def test_device_call_then_numpy_call_without_synchronising(pcu, oracle):
+    """A CUDA-tensor call returns without synchronising; a numpy call issued right behind it uses a workspace
+    of its own (its stream does not order against the caller's), so neither disturbs the other's scratch."""
+    import torch
+    rng = np.random.default_rng(23)
+    x = rng.random((400000, 3), dtype=np.float32)
+    y = rng.random((300000, 3), dtype=np.float32)
+    a = rng.random((50000, 3), dtype=np.float32)
+    b = rng.random((60000, 3), dtype=np.float32)
+    ref_big = oracle.k_nearest_neighbors(x, y, 8)
+    ref_small = oracle.hausdorff_distance(a, b, return_index=True)
+    ref_cham = float(oracle.chamfer_distance(a, b))
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        d, i = pcu.k_nearest_neighbors(xt, yt, 8)          # enqueued on torch's default stream, still running ...
+        h = pcu.hausdorff_distance(a, b, return_index=True)  # ... while the numpy path copies, bins and sweeps
+        c = pcu.chamfer_distance(a, b)
+        assert h == ref_small and abs(float(c) - ref_cham) <= REL * ref_cham
+        assert np.array_equal(i.cpu().numpy(), ref_big[1]) and np.array_equal(d.cpu().numpy(), ref_big[0])
