@@ -92,9 +92,9 @@ def committed_traffic(wl_key):
 
 def search_kernel_name(wl_key, k):
     if wl_key in ("c3", "c5"):
-        return "nn1_tile_kernel<float, ..., kOut=false, kStats=true> (fused search sweep, both directions in one launch)"
+        return "nn1_kernel<float, ..., kOut=false, kStats=true> (fused search sweep, both directions in one launch)"
     if k == 1:
-        return "nn1_tile_kernel<float, ..., kOut=true, kStats=false>"
+        return "nn1_kernel<float, ..., kOut=true, kStats=false>"
     cap = 4 if k <= 4 else 8 if k <= 8 else 16 if k <= 16 else 32
     return "knn_thread_kernel<float, ..., %d> (thread-per-query register lists)" % cap if k <= 32 else "knn_descend_kernel"
 

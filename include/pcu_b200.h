@@ -108,6 +108,13 @@ int pcu_b200_current_device(void);
 /* Kernels launched by this library on the calling process since load (bench.py's gpu_launches). */
 int64_t pcu_b200_launch_count(void);
 
+/* Page-locked host memory (cudaHostAlloc / cudaFreeHost), for callers that want their big result buffers to
+ * be copy targets the DMA engines can write directly: the numpy-facing binding backs k-NN results of 1 MiB and
+ * more with such blocks (recycled through a small pool), because a device-to-host copy into freshly allocated
+ * pageable memory runs at ~3 GB/s -- the page faults, not PCIe -- against ~50 GB/s into pinned memory. */
+int pcu_b200_host_alloc(void** out_ptr, int64_t bytes);
+int pcu_b200_host_free(void* ptr);
+
 /* ---- workspace ---------------------------------------------------------------------------- */
 int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws);
 int pcu_b200_workspace_destroy(pcu_b200_workspace* ws);
@@ -125,7 +132,9 @@ int pcu_b200_workspace_grid_refinement(const pcu_b200_workspace* ws, float out_m
 /* Per-stage device timing (diagnostic; bench.py's roofline pass).  When enabled, every device entry
  * point records CUDA events on the launching stream between its stages; after that stream has been
  * synchronised, last_profile() returns the milliseconds of the LAST call's 8 stages (descriptors,
- * bbox+grid, histogram, scan, scatter, search, search_far, finalize) and their count (0 if none). */
+ * bbox+grid, histogram, scan, scatter, search, search_far, finalize) and their count (0 if none); after a
+ * host entry point and with capacity >= 10, two more: the host-to-device copies in front of the first stage
+ * and the device-to-host copies behind the last ("h2d", "d2h"). */
 int pcu_b200_workspace_set_profiling(pcu_b200_workspace* ws, int enabled);
 int pcu_b200_workspace_last_profile(pcu_b200_workspace* ws, float* out_ms, int capacity);
 const char* pcu_b200_profile_stage_name(int stage);
@@ -179,6 +188,20 @@ int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, con
 int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
                                  int64_t m, float* out_per_pair, double* out_sum, void* stream);
 
+/* ---- point-cloud normals from k nearest neighbours ----------------------
+ * Replaces estimate_point_cloud_normals_knn_internal (src/point_cloud_normals.cpp:375-411, estimator :115-173):
+ * for every point its k nearest points of the same cloud (itself included), the unit normal of the plane
+ * fitted to them, and -- when view_dirs (n, 3) is not NULL -- orientation towards the view direction and
+ * dropping of points whose normal makes an angle above drop_angle_threshold (radians) with it.
+ * out_idx (capacity n) / out_normals (capacity n x 3): the kept points in ascending row order; out_count: how
+ * many.  The neighbour sets are the reference's bit for bit (same exact k-NN, same tie order); the plane fit is
+ * the smallest eigenvector of the fp64 scatter matrix, equal to the reference's JacobiSVD vector up to rounding
+ * and, without view directions, up to sign.  DEVICE pointers; out_count is a device int64. */
+int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs, int k,
+                             double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count, void* stream);
+int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
+                             double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
+
 /* ---- HOST-pointer conveniences (H2D + kernels + D2H, synchronous) --------------------------
  * The calls the numpy-facing binding makes; these are what `e2e` in bench.py times.              */
 int pcu_b200_knn_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m,
@@ -195,6 +218,10 @@ int pcu_b200_chamfer_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n
                               pcu_b200_nn_stats* out_stats, double* out_value);
 int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
                                       int64_t n, int64_t m, float* out_per_pair, double* out_sum);
+int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs, int k,
+                                  double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count);
+int pcu_b200_normals_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
+                                  double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count);
 
 /* ---- diagnostics ----------------------------------------------------------------------------
  * Builds the kd-tree replica used by the tie replay for HOST points and copies it out, so tests can

@@ -187,6 +187,44 @@ def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10,
     return cham
 
 
+def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None, drop_angle_threshold=np.deg2rad(90.0),
+                                     max_points_per_leaf=10, impl=None):
+    """src/point_cloud_normals.cpp:115-173 + :375-411 restated: the k-NN part is the pinned oracle above (self-query,
+    the point itself is neighbour 0); the plane fit follows the reference operation for operation -- offsets
+    subtracted in the cloud's precision, widened to fp64, right singular vector of the smallest singular value --
+    with numpy's LAPACK SVD standing in for Eigen's JacobiSVD, which is not in the reference tree.
+    PARITY UNPINNED for the normal vector itself (no golden vector of the reference exists and its SVD cannot be
+    built here): same subspace up to rounding, sign arbitrary unless view directions are given."""
+    points = np.asarray(points)
+    if num_neighbors <= 0:
+        raise ValueError("Invalid number of neighbors (%d) must be greater than 0." % num_neighbors)
+    if points.ndim != 2 or points.shape[0] == 0 or points.shape[1] != 3:
+        raise ValueError("Invalid point set with zero elements: points must have shape (n, 3)")
+    n = points.shape[0]
+    has_dirs = view_directions is not None and np.asarray(view_directions).shape[0] != 0
+    if has_dirs and np.asarray(view_directions).shape != points.shape:
+        raise ValueError("Invalid view directions does not match the number of points.")
+    _, idx = k_nearest_neighbors(points, points, num_neighbors, True, max_points_per_leaf, impl=impl, faithful_builds=False)
+    idx = idx.reshape(n, num_neighbors)
+    found = idx[:, -1] >= 0                                   # :139-142
+    safe = np.where(idx >= 0, idx, 0)
+    offsets = (points[safe] - points[:, None, :]).astype(np.float64)     # (n, k, 3): subtraction in the cloud's dtype
+    _, _, vt = np.linalg.svd(offsets, full_matrices=False)               # V(:, 2) == vt[:, 2, :]  (k >= 3)
+    if vt.shape[1] < 3:                                                  # fewer than 3 rows: thin V has no third column
+        vt = np.concatenate([vt, np.zeros((n, 3 - vt.shape[1], 3))], axis=1)
+    normal = vt[:, 2, :].copy()
+    keep = found.copy()
+    if has_dirs:
+        dirs = np.asarray(view_directions).astype(np.float64)
+        sgn = np.sign(np.einsum("ij,ij->i", normal, dirs))
+        normal *= sgn[:, None]
+        with np.errstate(invalid="ignore"):
+            angle = np.arccos(np.einsum("ij,ij->i", normal, dirs))
+        keep &= ~(angle > drop_angle_threshold)
+    kept = np.nonzero(keep)[0].astype(np.int64)
+    return kept, normal[kept].astype(points.dtype)
+
+
 def kd_tree(dataset_points, max_points_per_leaf=10):
     """The restatement's built tree (order[] = nanoflann's vAcc, plus the node table), for checking
     GPU-side replicas of the build."""

@@ -37,7 +37,7 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
         "There is no pure-Python or CPU fallback for this package." % (_e,)) from _e
 
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
-           "batched_chamfer_distance", "device_count", "current_device", "launch_count"]
+           "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "device_count", "current_device", "launch_count"]
 
 _STATS_WORDS = 10  # sizeof(pcu_b200_nn_stats) / 8
 
@@ -359,6 +359,84 @@ def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10,
     if return_index:
         return cham, corrs_x_to_y, corrs_y_to_x
     return cham
+
+
+def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None, drop_angle_threshold=_np.deg2rad(90.0),
+                                     max_points_per_leaf=10, num_threads=-1, *, device=None):
+    """
+    Estimate normals for a point cloud by locally fitting a plane to the k nearest neighbors of each point.
+
+    This function can optionally consider directions to the sensor for each point to align the final normal
+    directions and to drop points whose normal deviates too much from the view direction.
+
+    Args:
+        points : (n, 3)-shaped NumPy array (or CUDA tensor) of point positions (each row is a point)
+        num_neighbors : Integer number of neighbors to use in each neighborhood (the point itself counts as its own
+                        nearest neighbor, as in the reference).
+        view_directions : (n, 3)-shaped array or None, the unit direction to the sensor for each point.
+        drop_angle_threshold : If view_directions is passed in, drop points whose angle between the normal and view
+                               direction exceeds drop_angle_threshold (in radians).
+        max_points_per_leaf : see `k_nearest_neighbors` (decides the neighbour set only among exactly equidistant points).
+        num_threads : CPU thread count of the reference implementation; accepted and ignored.
+        device : see `k_nearest_neighbors` (keyword only).
+
+    Returns:
+        idx : an (m,)-shaped int64 array of indices into points (the points that were kept, ascending)
+        n : an (m, 3)-shaped array of unit normals for those points
+
+    Mirrors /root/reference/point_cloud_utils/_pointcloud_normals.py:4-54 and
+    /root/reference/src/point_cloud_normals.cpp:115-173, :375-411.  Neighbour sets are the reference's; the normal is the
+    same plane-fit direction up to rounding (1e-6 in the dot product for well-separated singular values) and, when no
+    view directions are given, up to sign -- the reference's sign is whatever Eigen's JacobiSVD returns.
+    """
+    if _is_tensor(points):
+        torch = _torch()
+        if points.dtype not in (torch.float32, torch.float64):
+            raise ValueError("Invalid scalar type (%s) for argument 'points'. Expected one of ['float32', 'float64']." % points.dtype)
+        if points.dim() != 2 or points.shape[-1] != 3:
+            raise ValueError("Invalid shape for points, must be (n, 3) but got " + str(tuple(points.shape)))
+        if points.shape[0] == 0:
+            raise ValueError("Invalid point set with zero elements: points must have shape (n, 3)")
+        if int(num_neighbors) <= 0:
+            raise ValueError("Invalid number of neighbors (%d) must be greater than 0." % int(num_neighbors))
+        dirs = None
+        if view_directions is not None:
+            if not _is_tensor(view_directions) or view_directions.dtype != points.dtype or \
+                    view_directions.device != points.device or tuple(view_directions.shape) != tuple(points.shape):
+                raise ValueError("Invalid view directions does not match the number of points. If view directions are passed "
+                                 "in, they must be a tensor with the dtype, device and shape of points.")
+            dirs = view_directions.detach().contiguous()
+        pts = points.detach().contiguous()
+        if not pts.is_cuda:
+            i, nrm = estimate_point_cloud_normals_knn(pts.numpy(), num_neighbors, None if dirs is None else dirs.numpy(),
+                                                      drop_angle_threshold, max_points_per_leaf, num_threads, device=device)
+            return torch.from_numpy(i), torch.from_numpy(nrm)
+        _same_device(pts, device)
+        n = pts.shape[0]
+        idx = torch.empty(n, dtype=torch.int64, device=pts.device)
+        nrm = torch.empty((n, 3), dtype=pts.dtype, device=pts.device)
+        count = torch.empty(1, dtype=torch.int64, device=pts.device)
+        _pcu_internal._normals_knn_device(pts.dtype == torch.float64, pts.data_ptr(), n, 0 if dirs is None else dirs.data_ptr(),
+                                          int(num_neighbors), float(drop_angle_threshold), idx.data_ptr(), nrm.data_ptr(),
+                                          count.data_ptr(), int(max_points_per_leaf), pts.device.index or 0, _stream_of(pts))
+        if dirs is None and n >= int(num_neighbors):
+            return idx, nrm          # every point is kept: no need to wait for the count
+        m = int(count.item())
+        return idx[:m], nrm[:m]
+    if type(points) != _np.ndarray:
+        raise ValueError("Invalid type for points, must be a NumPy array, but got " + str(type(points)) + ".")
+    if view_directions is None:
+        view_directions = _np.zeros([0, 3], dtype=points.dtype)
+    if type(view_directions) != _np.ndarray:
+        raise ValueError("Invalid type for view_directions, must be None or a NumPy array, but got " +
+                         str(type(view_directions)) + ".")
+    if len(points.shape) != 2 or points.shape[-1] != 3:
+        raise ValueError("Invalid shape for points, must be (n, 3) but got " + str(points.shape))
+    if len(view_directions.shape) != 2:
+        raise ValueError("Invalid shape for view_directions, must be (n, 3) but got " + str(view_directions.shape))
+    return _pcu_internal.estimate_point_cloud_normals_knn_internal(points, view_directions, int(num_neighbors),
+                                                                   int(max_points_per_leaf), float(drop_angle_threshold),
+                                                                   int(num_threads), -1, _dev(device))
 
 
 def batched_chamfer_distance(x, y, max_points_per_leaf=10, *, device=None):

@@ -78,6 +78,91 @@ struct CallScope {
     explicit CallScope(Slot& slot) : nogil(), lock(slot.busy) {}
 };
 
+// Result arrays of 1 MiB and more are backed by page-locked host memory: the device-to-host copy of a large
+// k-NN result into a fresh pageable numpy array is bound by page faults (~3 GB/s measured, 0.6 s for the
+// 1.9 GB of BASELINE configs[3]), into pinned memory by PCIe.  Page-locking is slow itself, so blocks are
+// recycled: when the numpy array that owns one is garbage-collected the block returns to this pool (at most
+// kKeepBytes stay cached; anything beyond is unpinned and released).  Allocation failure or a pool over its
+// budget of outstanding blocks falls back to an ordinary numpy array.
+class PinnedPool {
+public:
+    static constexpr size_t kMinBytes = size_t(1) << 20;
+    static constexpr size_t kKeepBytes = size_t(6) << 30;
+    static constexpr size_t kMaxOutstanding = size_t(24) << 30;
+    void* take(size_t bytes, size_t& capacity) {
+        capacity = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = free_.lower_bound(capacity);
+            if (it != free_.end() && it->first <= capacity + capacity / 4) {
+                void* p = it->second;
+                capacity = it->first;
+                cached_ -= it->first;
+                free_.erase(it);
+                outstanding_ += capacity;
+                return p;
+            }
+            if (outstanding_ + capacity > kMaxOutstanding) return nullptr;
+            outstanding_ += capacity;
+        }
+        void* p = nullptr;
+        if (pcu_b200_host_alloc(&p, (int64_t)capacity) != PCU_B200_OK) {
+            std::lock_guard<std::mutex> lock(mu_);
+            outstanding_ -= capacity;
+            return nullptr;
+        }
+        return p;
+    }
+    void give(void* p, size_t capacity) {
+        bool release = false;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            outstanding_ -= capacity;
+            if (closed_ || cached_ + capacity > kKeepBytes) release = true;
+            else { free_.emplace(capacity, p); cached_ += capacity; }
+        }
+        if (release) pcu_b200_host_free(p);
+    }
+    void clear(bool close) {
+        std::multimap<size_t, void*> drop;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            drop.swap(free_);
+            cached_ = 0;
+            if (close) closed_ = true;
+        }
+        for (auto& kv : drop) pcu_b200_host_free(kv.second);
+    }
+private:
+    std::mutex mu_;
+    std::multimap<size_t, void*> free_;
+    size_t cached_ = 0, outstanding_ = 0;
+    bool closed_ = false;
+};
+PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; }   // outlives late array destructors
+
+struct PinnedBlock { void* ptr; size_t capacity; };
+
+// A C-contiguous (rows, cols) array of T: page-locked and pool-backed when it is large, ordinary otherwise.
+template <typename T>
+py::array_t<T> result_array(py::ssize_t rows, py::ssize_t cols) {
+    const size_t bytes = (size_t)rows * (size_t)cols * sizeof(T);
+    if (bytes >= PinnedPool::kMinBytes) {
+        size_t capacity = 0;
+        void* p = pinned_pool().take(bytes, capacity);
+        if (p != nullptr) {
+            auto* block = new PinnedBlock{p, capacity};
+            py::capsule owner(block, [](void* b) {
+                auto* blk = static_cast<PinnedBlock*>(b);
+                pinned_pool().give(blk->ptr, blk->capacity);
+                delete blk;
+            });
+            return py::array_t<T>({rows, cols}, {(py::ssize_t)(cols * sizeof(T)), (py::ssize_t)sizeof(T)}, static_cast<T*>(p), owner);
+        }
+    }
+    return py::array_t<T>({rows, cols});
+}
+
 struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; int binning = 0; };
 Options& defaults() { static Options o; return o; }
 
@@ -157,8 +242,8 @@ py::tuple knn_numpy(const py::array& q_in, const py::array& d_in, int k, bool sq
     auto q = dense<T>(q_in);
     auto d = dense<T>(d_in);
     const int64_t n = q.shape(0), m = d.shape(0);
-    py::array_t<T> dists({(py::ssize_t)n, (py::ssize_t)k});
-    py::array_t<int64_t> corrs({(py::ssize_t)n, (py::ssize_t)k});
+    py::array_t<T> dists = result_array<T>((py::ssize_t)n, (py::ssize_t)k);
+    py::array_t<int64_t> corrs = result_array<int64_t>((py::ssize_t)n, (py::ssize_t)k);
     Slot& slot = pool().get(device, kHostKey);
     pcu_b200_workspace* ws = slot.ws;
     const pcu_b200_options opts = make_options(leaf);
@@ -275,6 +360,82 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
         value = py::module_::import("numpy").attr("float64")(v);
     }
     return py::make_tuple(value, stats_to_dict(st[0]), stats_to_dict(st[1]));
+}
+
+// estimate_point_cloud_normals_knn_internal (src/point_cloud_normals.cpp:375-411): (indices of the kept points,
+// their unit normals).  view_dirs is a (0, 3) array when no view directions are given, as in the reference's wrapper.
+template <typename T>
+py::tuple normals_knn_numpy(const py::array& p_in, const py::array& v_in, int k, int leaf, double drop_angle, int device) {
+    auto pts = dense<T>(p_in);
+    auto dirs = dense<T>(v_in);
+    const int64_t n = pts.shape(0);
+    const bool has_dirs = dirs.shape(0) != 0;
+    py::array_t<int64_t> idx({(py::ssize_t)n});
+    py::array_t<T> normals({(py::ssize_t)n, (py::ssize_t)3});
+    int64_t kept = 0;
+    Slot& slot = pool().get(device, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
+    const pcu_b200_options opts = make_options(leaf);
+    int status;
+    {
+        CallScope scope(slot);
+        pcu_b200_workspace_set_options(ws, &opts);
+        if (sizeof(T) == 4)
+            status = pcu_b200_normals_knn_host_f32(ws, (const float*)pts.data(), n, has_dirs ? (const float*)dirs.data() : nullptr, k,
+                                                   drop_angle, idx.mutable_data(), (float*)normals.mutable_data(), &kept);
+        else
+            status = pcu_b200_normals_knn_host_f64(ws, (const double*)pts.data(), n, has_dirs ? (const double*)dirs.data() : nullptr, k,
+                                                   drop_angle, idx.mutable_data(), (double*)normals.mutable_data(), &kept);
+    }
+    check(status);
+    idx.resize({(py::ssize_t)kept});
+    normals.resize({(py::ssize_t)kept, (py::ssize_t)3});
+    return py::make_tuple(idx, normals);
+}
+
+py::tuple estimate_point_cloud_normals_knn_internal(const py::array& points, const py::array& view_dirs, int num_neighbors,
+                                                    int max_points_per_leaf, double drop_angle_threshold, int num_threads,
+                                                    int random_seed, int device) {
+    (void)num_threads; (void)random_seed;   // CPU threading / rand() seeding of the reference: no effect on the k-NN variant
+    if (num_neighbors <= 0)
+        throw py::value_error("Invalid number of neighbors (" + std::to_string(num_neighbors) + ") must be greater than 0.");
+    const Dt dt = common_dtype(points, view_dirs, "points", "view_dirs");
+    auto shape_of = [](const py::array& a) {
+        std::ostringstream ss;
+        ss << "(";
+        for (py::ssize_t i = 0; i < a.ndim(); ++i) ss << (i ? ", " : "") << a.shape(i);
+        ss << ")";
+        return ss.str();
+    };
+    if (points.ndim() != 2 || points.shape(0) == 0 || points.shape(1) != 3)      // validate_input, :25-33
+        throw py::value_error("Invalid point set with zero elements: points must have shape (n, 3), but got points.shape = " +
+                              shape_of(points) + ".");
+    if (view_dirs.ndim() != 2 || (view_dirs.shape(0) != 0 && (view_dirs.shape(0) != points.shape(0) || view_dirs.shape(1) != 3)))
+        throw py::value_error("Invalid view directions does not match the number of points. If view directions are passed in, "
+                              "they must have the same shape as points. Got points.shape = " + shape_of(points) +
+                              ", and view_dirs.shape = " + shape_of(view_dirs) + ".");   // :34-42
+    const int dev = current_device_or_default(device);
+    return dt == Dt::f32 ? normals_knn_numpy<float>(points, view_dirs, num_neighbors, max_points_per_leaf, drop_angle_threshold, dev)
+                         : normals_knn_numpy<double>(points, view_dirs, num_neighbors, max_points_per_leaf, drop_angle_threshold, dev);
+}
+
+void normals_knn_device(bool is_f64, uintptr_t points, int64_t n, uintptr_t view_dirs, int k, double drop_angle,
+                        uintptr_t out_idx, uintptr_t out_normals, uintptr_t out_count, int max_points_per_leaf, int device,
+                        uintptr_t stream) {
+    if (k <= 0) throw py::value_error("Invalid number of neighbors (" + std::to_string(k) + ") must be greater than 0.");
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_workspace* ws = slot.ws;
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
+    int status;
+    {
+        CallScope scope(slot);
+        pcu_b200_workspace_set_options(ws, &opts);
+        status = is_f64 ? pcu_b200_normals_knn_f64(ws, (const double*)points, n, (const double*)view_dirs, k, drop_angle,
+                                                   (int64_t*)out_idx, (double*)out_normals, (int64_t*)out_count, (void*)stream)
+                        : pcu_b200_normals_knn_f32(ws, (const float*)points, n, (const float*)view_dirs, k, drop_angle,
+                                                   (int64_t*)out_idx, (float*)out_normals, (int64_t*)out_count, (void*)stream);
+    }
+    check(status);
 }
 
 // ---- raw device-pointer entry points (CUDA torch tensors) --------------------------------------
@@ -426,6 +587,12 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("return_index") = true, py::arg("squared_distances") = false, py::arg("max_points_per_leaf") = 10,
             py::arg("device") = -1,
             "Compute the one sided Hausdorff distance from source to target.  Returns d or (d, i, j).");
+    mod.def("estimate_point_cloud_normals_knn_internal", &estimate_point_cloud_normals_knn_internal, py::arg("points"),
+            py::arg("view_dirs"), py::arg("num_neighbors"), py::arg("max_points_per_leaf") = 10,
+            py::arg("drop_angle_threshold") = 1.5707963267948966, py::arg("num_threads") = 0, py::arg("random_seed") = -1,
+            py::arg("device") = -1,
+            "Indices of the kept points and their unit normals (plane fit to the k nearest neighbours of each point).");
+    mod.def("_normals_knn_device", &normals_knn_device);
     mod.def("_chamfer_stats", &chamfer_stats, py::arg("x"), py::arg("y"), py::arg("max_points_per_leaf") = 10,
             py::arg("device") = -1);
     mod.def("_batched_chamfer", &batched_chamfer_numpy, py::arg("x"), py::arg("y"), py::arg("max_points_per_leaf") = 10,
@@ -460,8 +627,8 @@ PYBIND11_MODULE(_pcu_internal, mod) {
         check(pcu_b200_workspace_set_profiling(pool().get(current_device_or_default(device), key_of(stream)).ws, on ? 1 : 0));
     });
     mod.def("_last_profile", [key_of](int device, py::object stream) {
-        float ms[8];
-        const int n = pcu_b200_workspace_last_profile(pool().get(current_device_or_default(device), key_of(stream)).ws, ms, 8);
+        float ms[10];
+        const int n = pcu_b200_workspace_last_profile(pool().get(current_device_or_default(device), key_of(stream)).ws, ms, 10);
         py::dict d;
         for (int i = 0; i < n; ++i) d[py::str(pcu_b200_profile_stage_name(i))] = ms[i];
         return d;
@@ -474,6 +641,7 @@ PYBIND11_MODULE(_pcu_internal, mod) {
         defaults().binning = binning;
     }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = 0, py::arg("binning") = 0);
     mod.def("_release_workspaces", []() { pool().clear(); });
-    // destroy workspaces before the CUDA context goes away at interpreter exit
-    py::module_::import("atexit").attr("register")(py::cpp_function([]() { pool().clear(); }));
+    mod.def("_release_pinned_results", []() { pinned_pool().clear(false); });
+    // destroy workspaces and cached pinned blocks before the CUDA context goes away at interpreter exit
+    py::module_::import("atexit").attr("register")(py::cpp_function([]() { pool().clear(); pinned_pool().clear(true); }));
 }

@@ -25,6 +25,7 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     Carver cv(ws->io);
     carve(cv, dq, dd, od, oi, nt);
     cudaStream_t st = ws->own_stream;
+    mark(ws, 9, st);
     PCU_CUDA(cudaMemcpyAsync(dq, query, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
     PCU_CUDA(cudaMemcpyAsync(dd, dataset, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
     PCU_TRY(knn_device<T>(ws, dq, n, dd, m, k, squared, od, oi, nt, st));
@@ -33,6 +34,7 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     long long tied = 0;
     unsigned overflows = 0;
     PCU_CUDA(cudaMemcpyAsync(&tied, nt, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    mark(ws, 10, st);
     if (ws->replay_overflows)
         PCU_CUDA(cudaMemcpyAsync(&overflows, ws->replay_overflows, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
@@ -43,6 +45,13 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     return PCU_B200_OK;
 }
 
+// Device-side results of one fused call, contiguous so that ONE copy brings them to the pinned slot.
+template <typename T>
+struct StatsResult {
+    pcu_b200_nn_stats stats[2];
+    T value;
+};
+
 template <typename T>
 int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
                pcu_b200_nn_stats* out_stats, T* out_value) {
@@ -51,35 +60,47 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     PCU_ON_DEVICE(ws);
     Carver measure(nullptr);
-    auto carve = [&](Carver& cv, T*& da, T*& db, pcu_b200_nn_stats*& ds, T*& dv) {
+    auto carve = [&](Carver& cv, T*& da, T*& db, StatsResult<T>*& dr) {
         da = cv.take<T>((size_t)3 * n);
         db = cv.take<T>((size_t)3 * m);
-        ds = cv.take<pcu_b200_nn_stats>(2);
-        dv = cv.take<T>(1);
+        dr = cv.take<StatsResult<T>>(1);
     };
-    T *da, *db, *dv; pcu_b200_nn_stats* ds;
-    carve(measure, da, db, ds, dv);
-    PCU_TRY(ensure_io(ws, measure.off, ws->own_stream));
-    Carver cv(ws->io);
-    carve(cv, da, db, ds, dv);
+    T *da, *db; StatsResult<T>* dr;
+    carve(measure, da, db, dr);
     cudaStream_t st = ws->own_stream;
-    PCU_CUDA(cudaMemcpyAsync(da, a, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
-    PCU_CUDA(cudaMemcpyAsync(db, b, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
-    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, ds, (both && out_value) ? dv : nullptr, st));
-    PCU_CUDA(cudaMemcpyAsync(out_stats, ds, sizeof(pcu_b200_nn_stats) * (both ? 2 : 1), cudaMemcpyDeviceToHost, st));
-    if (both && out_value) PCU_CUDA(cudaMemcpyAsync(out_value, dv, sizeof(T), cudaMemcpyDeviceToHost, st));
-    PCU_CUDA(cudaStreamSynchronize(st));
+    PCU_TRY(ensure_io(ws, measure.off, st));
+    Carver cv(ws->io);
+    carve(cv, da, db, dr);
+    // the copies run on their own stream: the first cloud is binned while the second is still in flight.
+    // (the staging block may have just been re-allocated in the order of `st`: the copies wait for that)
+    PCU_CUDA(cudaEventRecord(ws->arrived[0], st));
+    PCU_CUDA(cudaStreamWaitEvent(ws->copy_stream, ws->arrived[0], 0));
+    mark(ws, 9, st);
+    PCU_CUDA(cudaMemcpyAsync(da, a, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, ws->copy_stream));
+    PCU_CUDA(cudaEventRecord(ws->arrived[0], ws->copy_stream));
+    PCU_CUDA(cudaMemcpyAsync(db, b, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, ws->copy_stream));
+    PCU_CUDA(cudaEventRecord(ws->arrived[1], ws->copy_stream));
+    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, dr->stats, both ? &dr->value : nullptr, st, ws->arrived));
+    StatsResult<T>* hr = reinterpret_cast<StatsResult<T>*>(ws->host_slot);
+    auto fetch = [&]() -> int {
+        PCU_CUDA(cudaMemcpyAsync(hr, dr, sizeof(StatsResult<T>), cudaMemcpyDeviceToHost, st));
+        mark(ws, 10, st);
+        PCU_CUDA(cudaStreamSynchronize(st));
+        return PCU_B200_OK;
+    };
+    PCU_TRY(fetch());
     // Hausdorff witnesses whose neighbour was decided by tie order: replay with the reference's tree
     if (ws->opts.disable_tie_replay != 1) {
         for (int s = 0; s < (both ? 2 : 1); ++s) {
-            if (!out_stats[s].witness_tied) continue;
+            if (!hr->stats[s].witness_tied) continue;
             const T* qs = s == 0 ? da : db;
             const T* dsrc = s == 0 ? db : da;
-            PCU_TRY(resolve_witness_device<T>(ws, qs, s == 0 ? n : m, dsrc, s == 0 ? m : n, ds + s, st));
-            PCU_CUDA(cudaMemcpyAsync(out_stats + s, ds + s, sizeof(pcu_b200_nn_stats), cudaMemcpyDeviceToHost, st));
-            PCU_CUDA(cudaStreamSynchronize(st));
+            PCU_TRY(resolve_witness_device<T>(ws, qs, s == 0 ? n : m, dsrc, s == 0 ? m : n, dr->stats + s, st));
+            PCU_TRY(fetch());
         }
     }
+    for (int s = 0; s < (both ? 2 : 1); ++s) out_stats[s] = hr->stats[s];
+    if (both && out_value) *out_value = hr->value;
     return PCU_B200_OK;
 }
 
@@ -110,6 +131,45 @@ int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long lo
     PCU_CUDA(cudaMemcpyAsync(out_per_pair, dv, sizeof(T) * batch, cudaMemcpyDeviceToHost, st));
     if (out_sum) PCU_CUDA(cudaMemcpyAsync(out_sum, dsum, sizeof(double), cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, int k,
+                     double drop_angle_threshold, long long* out_idx, T* out_normals, long long* out_count) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid number of neighbors (%d) must be greater than 0.", k);
+    if (!points || n <= 0)
+        return fail(PCU_B200_INVALID_ARGUMENT, "Invalid point set with zero elements: points must have shape (n, 3) (got %lld rows)", n);
+    if (!out_idx || !out_normals || !out_count) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_ON_DEVICE(ws);
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& dp, T*& dv, long long*& di, T*& dn, long long*& dc) {
+        dp = cv.take<T>((size_t)3 * n);
+        dv = cv.take<T>(view_dirs ? (size_t)3 * n : 1);
+        di = cv.take<long long>((size_t)n);
+        dn = cv.take<T>((size_t)3 * n);
+        dc = cv.take<long long>(1);
+    };
+    T *dp, *dv, *dn; long long *di, *dc;
+    carve(measure, dp, dv, di, dn, dc);
+    cudaStream_t st = ws->own_stream;
+    PCU_TRY(ensure_io(ws, measure.off, st));
+    Carver cv(ws->io);
+    carve(cv, dp, dv, di, dn, dc);
+    PCU_CUDA(cudaMemcpyAsync(dp, points, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    if (view_dirs) PCU_CUDA(cudaMemcpyAsync(dv, view_dirs, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    PCU_TRY(normals_knn_device<T>(ws, dp, n, view_dirs ? dv : (const T*)nullptr, k, drop_angle_threshold, di, dn, dc, st));
+    long long* hc = reinterpret_cast<long long*>(ws->host_slot);
+    PCU_CUDA(cudaMemcpyAsync(hc, dc, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    const long long kept = *hc;
+    if (kept > 0) {
+        PCU_CUDA(cudaMemcpyAsync(out_idx, di, sizeof(long long) * kept, cudaMemcpyDeviceToHost, st));
+        PCU_CUDA(cudaMemcpyAsync(out_normals, dn, sizeof(T) * 3 * kept, cudaMemcpyDeviceToHost, st));
+        PCU_CUDA(cudaStreamSynchronize(st));
+    }
+    *out_count = kept;
     return PCU_B200_OK;
 }
 
@@ -186,6 +246,14 @@ int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int
                                int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes) {
     return debug_kd_tree<double>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
                                  kid0, kid1, out_nodes);
+}
+int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs, int k,
+                                  double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count) {
+    return normals_knn_host<float>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals, (long long*)out_count);
+}
+int pcu_b200_normals_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
+                                  double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count) {
+    return normals_knn_host<double>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals, (long long*)out_count);
 }
 int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
                                       int64_t n, int64_t m, float* out_per_pair, double* out_sum) {

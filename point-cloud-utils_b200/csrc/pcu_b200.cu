@@ -24,6 +24,7 @@
 #include "topk.cuh"
 #include "pyramid.cuh"
 #include "kdreplay.cuh"
+#include "normals.cuh"
 
 using namespace pcu;
 
@@ -188,6 +189,8 @@ struct pcu_b200_workspace {
     size_t arena_bytes = 0;
     unsigned char* io = nullptr;         // device copies of host inputs / outputs (host entry points)
     size_t io_bytes = 0;
+    unsigned char* aux = nullptr;        // intermediate results that outlive a nested call's re-carving of the arena (normals)
+    size_t aux_bytes = 0;
     pcu_b200_options opts{};
     int sm_count = 148;
     // optional per-stage timing (bench.py's roofline pass): events recorded on the launching stream
@@ -200,16 +203,20 @@ struct pcu_b200_workspace {
     long long hint_key[5] = {0, 0, 0, 0, 0};   // n, m, k, sizeof(T), batch of the call the hints belong to
     float cell_mult[2] = {1.f, 1.f};           // current refinement of the two clouds' grids (cells per point x this)
     float cell_mult_ceiling[2] = {32.f, 32.f}; // lowered when a refinement left too many queries unsettled
+    cudaStream_t copy_stream = nullptr;  // host entry points: the H2D copies run here, the kernels on own_stream
+    cudaEvent_t arrived[2] = {};         // recorded on copy_stream behind each cloud's copy
+    unsigned char* host_slot = nullptr;  // 4 KB of pinned host memory: small results land here, then in the caller's buffers
     const unsigned* replay_overflows = nullptr;   // device counter of the last KNN call's tie replay (null: none ran)
     cudaStream_t last_stream = nullptr;  // stream of the previous call (see adopt_stream)
     bool has_last_stream = false;
     cudaEvent_t handover = nullptr;
     bool profiling = false;
-    cudaEvent_t marks[9] = {};
+    cudaEvent_t marks[11] = {};   // 0 .. 8: stage boundaries of a device call; 9 / 10: before the H2D / after the D2H of a host call
     int marks_used = 0;
+    bool host_marks = false;      // marks 9 and 10 belong to the last call
 };
 
-#define PCU_STAGE_NAMES "descriptors", "bbox+grid", "histogram", "scan", "scatter", "search", "search_far", "finalize"
+#define PCU_STAGE_NAMES "descriptors", "bbox+grid", "histogram", "scan", "scatter", "search", "search_far", "finalize", "h2d", "d2h"
 
 namespace {
 
@@ -282,7 +289,9 @@ int ensure_io(pcu_b200_workspace* ws, size_t bytes, cudaStream_t stream) {
 void mark(pcu_b200_workspace* ws, int index, cudaStream_t stream) {
     if (!ws->profiling) return;
     cudaEventRecord(ws->marks[index], stream);
-    ws->marks_used = index + 1;
+    if (index <= 8) ws->marks_used = index + 1;
+    if (index == 0) ws->host_marks = false;
+    if (index == 10) ws->host_marks = true;
 }
 
 int cell_cap_for(long long n, double occupancy) {
@@ -294,7 +303,9 @@ int cell_cap_for(long long n, double occupancy) {
 
 float occupancy_for(const pcu_b200_workspace* ws, int k) {
     if (ws->opts.cell_occupancy > 0.f) return ws->opts.cell_occupancy;
-    if (k <= 1) return 2.0f;
+    // k = 1: 1.5 points per cell (measured on C3, profiles/r2d_occ.log: the sweep visits fewer candidates -- 139 -> 124 us --
+    // while the scan over more cells and the far pass grow by less; 1.25 and 1.75 are within 1 % of it, 1.0 loses 8 %)
+    if (k <= 1) return 1.5f;
     return std::max(2.0f, 0.5f * (float)k);
 }
 
@@ -526,9 +537,36 @@ int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, PlanSpec<T>& spec, cudaS
 }
 
 // bbox -> grid -> histogram -> scan -> scatter for every cloud of the plan
+// `ready` (host entry points, single pairs): two events, recorded on the copy stream when the first / the second
+// cloud has arrived on the device.  The first cloud is then binned -- all five passes -- while the second is
+// still crossing PCIe, and only the second cloud's passes follow its copy.
 template <typename T>
-int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream) {
+int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream, const cudaEvent_t* ready = nullptr) {
     const int nclouds = plan.nclouds;
+    if (ready != nullptr && plan.by_value && !plan.one_cta_binning) {
+        PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
+        const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
+        const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
+        for (int s = 0; s < 2; ++s) {
+            PCU_CUDA(cudaStreamWaitEvent(stream, ready[s], 0));
+            CloudsVal<T> one;
+            one.v[0] = plan.cv.v[s];
+            one.v[1] = plan.cv.v[s];
+            PCU_LAUNCH_PDL((bbox_partial_kernel<T, CloudsVal<T>, true>), dim3(plan.max_bbox_blocks, 1), kThreads, stream, one);
+            mark(ws, 2, stream);
+            PCU_LAUNCH_PDL((cell_count_kernel<T, CloudsVal<T>>), dim3(bin_blocks, 1), kThreads, stream, one);
+            mark(ws, 3, stream);
+            PCU_LAUNCH_PDL((scan_lookback_kernel<T, CloudsVal<T>>), dim3(scan_blocks, 1), kScanThreads, stream, one);
+            mark(ws, 4, stream);
+            PCU_LAUNCH_PDL((scatter_kernel<T, CloudsVal<T>>), dim3(bin_blocks, 1), kThreads, stream, one);
+            mark(ws, 5, stream);
+        }
+        return PCU_B200_OK;
+    }
+    if (ready != nullptr) {
+        PCU_CUDA(cudaStreamWaitEvent(stream, ready[0], 0));
+        PCU_CUDA(cudaStreamWaitEvent(stream, ready[1], 0));
+    }
     if (plan.one_cta_binning) {
         PCU_CUDA(cudaMemsetAsync(plan.zero_begin + plan.zero_cells_bytes, 0, plan.zero_bytes - plan.zero_cells_bytes, stream));
         const size_t smem = ((size_t)plan.max_cap + 1) * sizeof(unsigned);
@@ -647,7 +685,7 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
 // nsweeps == 1: query -> dataset.  nsweeps == 2: x -> y and y -> x over the same two binned clouds.
 template <typename T>
 int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
-                 pcu_b200_nn_stats* out_stats, T* out_value, cudaStream_t stream) {
+                 pcu_b200_nn_stats* out_stats, T* out_value, cudaStream_t stream, const cudaEvent_t* ready = nullptr) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     PCU_TRY(check_cloud_args<T>(a, n, b, m));
     if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
@@ -665,7 +703,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
     mark(ws, 1, stream);
-    PCU_TRY(enqueue_binning(ws, plan, stream));
+    PCU_TRY(enqueue_binning(ws, plan, stream, ready));
     const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
     PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, ns), kThreads, false, true);
     mark(ws, 6, stream);
@@ -694,6 +732,42 @@ int resolve_witness_device(pcu_b200_workspace* ws, const T* query, long long n, 
     const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
     const int rs = enqueue_witness_replay<T>(rb, query, n, dataset, m, leaf, stats, stream, g_launches);
     if (rs != PCU_B200_OK) return fail(rs, "witness replay failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PCU_B200_OK;
+}
+
+// ---- normals from k nearest neighbours -------------------------------------------
+// Self-query top-k (the point itself is its own first neighbour, as in the reference), plane fit, optional
+// orientation / filtering by view directions, order-preserving compaction of the kept points.
+template <typename T>
+int normals_knn_device(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, int k,
+                       double drop_angle_threshold, long long* out_idx, T* out_normals, long long* out_count,
+                       cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid number of neighbors (%d) must be greater than 0.", k);
+    if (!points || n <= 0)
+        return fail(PCU_B200_INVALID_ARGUMENT, "Invalid point set with zero elements: points must have shape (n, 3) (got %lld rows)", n);
+    if (!out_idx || !out_normals || !out_count) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_ON_DEVICE(ws);
+    const long long nblocks = (n + kThreads - 1) / kThreads;
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, long long*& nn_idx, T*& nn_dist, T*& dense, unsigned char*& keep, unsigned*& counts) {
+        nn_idx = cv.take<long long>((size_t)n * k);
+        nn_dist = cv.take<T>((size_t)n * k);
+        dense = cv.take<T>((size_t)3 * n);
+        keep = cv.take<unsigned char>((size_t)n);
+        counts = cv.take<unsigned>((size_t)nblocks);
+    };
+    long long* nn_idx; T *nn_dist, *dense; unsigned char* keep; unsigned* counts;
+    carve(measure, nn_idx, nn_dist, dense, keep, counts);
+    PCU_TRY(adopt_stream(ws, stream));
+    PCU_TRY(grow_block(ws->aux, ws->aux_bytes, measure.off, stream, "neighbour scratch"));
+    Carver cv(ws->aux);
+    carve(cv, nn_idx, nn_dist, dense, keep, counts);
+    PCU_TRY(knn_device<T>(ws, points, n, points, n, k, 1, nn_dist, nn_idx, nullptr, stream));
+    PCU_LAUNCH((normals_knn_kernel<T>), (unsigned)nblocks, kThreads, stream, points, n, nn_idx, k, view_dirs, drop_angle_threshold, dense, keep);
+    PCU_LAUNCH(keep_count_kernel, (unsigned)nblocks, kThreads, stream, keep, n, counts);
+    PCU_LAUNCH(keep_offsets_kernel, 1, 1024, stream, counts, nblocks, out_count);
+    PCU_LAUNCH((keep_scatter_kernel<T>), (unsigned)nblocks, kThreads, stream, keep, n, counts, dense, out_idx, out_normals);
     return PCU_B200_OK;
 }
 
@@ -780,6 +854,25 @@ int pcu_b200_current_device(void) {
 
 int pcu_b200_workspace_device(const pcu_b200_workspace* ws) { return ws ? ws->device : -1; }
 
+int pcu_b200_host_alloc(void** out_ptr, int64_t bytes) {
+    if (!out_ptr || bytes <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "bad argument");
+    *out_ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(out_ptr, (size_t)bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out_ptr = nullptr;
+        return fail(PCU_B200_OUT_OF_MEMORY, "cudaHostAlloc of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+    }
+    return PCU_B200_OK;
+}
+
+int pcu_b200_host_free(void* ptr) {
+    if (!ptr) return PCU_B200_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(PCU_B200_CUDA_ERROR, "cudaFreeHost failed: %s", cudaGetErrorString(e)); }
+    return PCU_B200_OK;
+}
+
 int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
     if (!out_ws) return fail(PCU_B200_INVALID_ARGUMENT, "null out_ws");
     *out_ws = nullptr;
@@ -802,7 +895,14 @@ int pcu_b200_workspace_create(int device, pcu_b200_workspace** out_ws) {
     DeviceGuard guard(device);
     if (guard.status != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaSetDevice(%d): %s", device, cudaGetErrorString(guard.status)); }
     cudaError_t e = cudaStreamCreateWithFlags(&ws->own_stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ws; return fail(PCU_B200_CUDA_ERROR, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ws->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ws->arrived[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ws->host_slot, 4096, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        pcu_b200_workspace_destroy(ws);
+        return fail(PCU_B200_CUDA_ERROR, "workspace streams / events / pinned slot: %s", cudaGetErrorString(e));
+    }
     void* hint = nullptr;
     if (cudaHostAlloc(&hint, 16 * sizeof(unsigned), cudaHostAllocMapped) == cudaSuccess) {
         std::memset(hint, 0, 16 * sizeof(unsigned));
@@ -827,16 +927,20 @@ int pcu_b200_workspace_destroy(pcu_b200_workspace* ws) {
     cudaDeviceSynchronize();
     if (ws->arena) cudaFree(ws->arena);
     if (ws->io) cudaFree(ws->io);
+    if (ws->aux) cudaFree(ws->aux);
     if (ws->handover) cudaEventDestroy(ws->handover);
     if (ws->hint_host) cudaFreeHost((void*)ws->hint_host);
     if (ws->own_stream) cudaStreamDestroy(ws->own_stream);
+    if (ws->copy_stream) cudaStreamDestroy(ws->copy_stream);
+    for (auto& e : ws->arrived) if (e) cudaEventDestroy(e);
+    if (ws->host_slot) cudaFreeHost(ws->host_slot);
     for (auto& e : ws->marks) if (e) cudaEventDestroy(e);
     delete ws;
     return PCU_B200_OK;
 }
 
 int64_t pcu_b200_workspace_bytes(const pcu_b200_workspace* ws) {
-    return ws ? (int64_t)(ws->arena_bytes + ws->io_bytes) : 0;
+    return ws ? (int64_t)(ws->arena_bytes + ws->io_bytes + ws->aux_bytes) : 0;
 }
 
 int pcu_b200_workspace_set_profiling(pcu_b200_workspace* ws, int enabled) {
@@ -852,19 +956,27 @@ int pcu_b200_workspace_set_profiling(pcu_b200_workspace* ws, int enabled) {
 int pcu_b200_workspace_last_profile(pcu_b200_workspace* ws, float* out_ms, int capacity) {
     if (!ws || !out_ms) return -1;
     if (!ws->profiling || ws->marks_used < 9) return 0;
-    if (cudaEventSynchronize(ws->marks[8]) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cudaEvent_t last = ws->host_marks ? ws->marks[10] : ws->marks[8];
+    if (cudaEventSynchronize(last) != cudaSuccess) { cudaGetLastError(); return -1; }
     int n = 0;
     for (; n < 8 && n < capacity; ++n) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ws->marks[n], ws->marks[n + 1]) != cudaSuccess) { cudaGetLastError(); return -1; }
         out_ms[n] = ms;
     }
+    if (ws->host_marks && capacity >= 10) {   // host entry points: the copies either side of the device call
+        float h2d = 0.f, d2h = 0.f;
+        if (cudaEventElapsedTime(&h2d, ws->marks[9], ws->marks[0]) != cudaSuccess ||
+            cudaEventElapsedTime(&d2h, ws->marks[8], ws->marks[10]) != cudaSuccess) { cudaGetLastError(); return -1; }
+        out_ms[8] = h2d; out_ms[9] = d2h;
+        n = 10;
+    }
     return n;
 }
 
 const char* pcu_b200_profile_stage_name(int stage) {
     static const char* names[] = {PCU_STAGE_NAMES};
-    return stage >= 0 && stage < 8 ? names[stage] : "";
+    return stage >= 0 && stage < 10 ? names[stage] : "";
 }
 
 int pcu_b200_workspace_grid_refinement(const pcu_b200_workspace* ws, float out_mult[2]) {
@@ -918,6 +1030,17 @@ int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, cons
 int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
                          pcu_b200_nn_stats* out_stats, double* out_value, void* stream) {
     return stats_device<double>(ws, x, n, y, m, true, out_stats, out_value, (cudaStream_t)stream);
+}
+
+int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs, int k,
+                             double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count, void* stream) {
+    return normals_knn_device<float>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals,
+                                     (long long*)out_count, (cudaStream_t)stream);
+}
+int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
+                             double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream) {
+    return normals_knn_device<double>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals,
+                                      (long long*)out_count, (cudaStream_t)stream);
 }
 
 int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
