@@ -202,6 +202,22 @@ int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_
 int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                              double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
 
+/* ---- 64-bit 3-D Morton codes --------------------------------------------
+ * Replace MortonCode64 (src/common/morton_code.cpp:43-163) and the bindings morton_encode / morton_decode /
+ * morton_add / morton_subtract / morton_knn (src/morton.cpp:185-239, :253-310, :26-103, :106-183, :324-414).
+ * Integer work: bit-identical.  pts: (n, 3) int32 (or int64, truncated to int32 as the reference does);
+ * coordinates in [-2^20, 2^20).  morton_knn: `codes` ascending; out_idx (m, k) = the k consecutive positions
+ * around the lower bound of each query code (k <= n: the binding clamps like morton.cpp:351); sort_dist != 0
+ * orders each row by squared distance to the query point -- an order the reference leaves undefined (its
+ * comparator reads uninitialised variables, :381-398); the set of positions is the reference's.  DEVICE pointers. */
+int pcu_b200_morton_encode_i32(pcu_b200_workspace* ws, const int32_t* pts, int64_t n, uint64_t* out_codes, void* stream);
+int pcu_b200_morton_encode_i64(pcu_b200_workspace* ws, const int64_t* pts, int64_t n, uint64_t* out_codes, void* stream);
+int pcu_b200_morton_decode(pcu_b200_workspace* ws, const uint64_t* codes, int64_t n, int32_t* out_pts, void* stream);
+int pcu_b200_morton_add(pcu_b200_workspace* ws, const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out, void* stream);
+int pcu_b200_morton_subtract(pcu_b200_workspace* ws, const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out, void* stream);
+int pcu_b200_morton_knn(pcu_b200_workspace* ws, const uint64_t* codes, int64_t n, const uint64_t* qcodes, int64_t m, int k,
+                        int sort_dist, int64_t* out_idx, void* stream);
+
 /* ---- HOST-pointer conveniences (H2D + kernels + D2H, synchronous) --------------------------
  * The calls the numpy-facing binding makes; these are what `e2e` in bench.py times.              */
 int pcu_b200_knn_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const float* dataset, int64_t m,
@@ -218,6 +234,13 @@ int pcu_b200_chamfer_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n
                               pcu_b200_nn_stats* out_stats, double* out_value);
 int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
                                       int64_t n, int64_t m, float* out_per_pair, double* out_sum);
+int pcu_b200_morton_encode_host_i32(pcu_b200_workspace* ws, const int32_t* pts, int64_t n, uint64_t* out_codes);
+int pcu_b200_morton_encode_host_i64(pcu_b200_workspace* ws, const int64_t* pts, int64_t n, uint64_t* out_codes);
+int pcu_b200_morton_decode_host(pcu_b200_workspace* ws, const uint64_t* codes, int64_t n, int32_t* out_pts);
+int pcu_b200_morton_add_host(pcu_b200_workspace* ws, const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out);
+int pcu_b200_morton_subtract_host(pcu_b200_workspace* ws, const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out);
+int pcu_b200_morton_knn_host(pcu_b200_workspace* ws, const uint64_t* codes, int64_t n, const uint64_t* qcodes, int64_t m, int k,
+                             int sort_dist, int64_t* out_idx);
 int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs, int k,
                                   double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count);
 int pcu_b200_normals_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,

@@ -225,6 +225,101 @@ def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None
     return kept, normal[kept].astype(points.dtype)
 
 
+# ---- Morton codes (src/morton.cpp, src/common/morton_code.cpp) -----------------------------------------------
+_MORTON_PORT = os.path.join(_HERE, "libpcu_oracle_morton.so")
+_MORTON_REF = os.path.join(_HERE, "_ref", "libpcu_ref_morton.so")
+
+
+def have_morton_reference():
+    return os.path.exists(_MORTON_REF)
+
+
+def _morton_lib(impl):
+    if impl is None:
+        impl = "reference" if have_morton_reference() else "port"
+    key = "morton_" + impl
+    if key not in _libs:
+        if impl == "port" and not os.path.exists(_MORTON_PORT):
+            build()
+        _libs[key] = (ctypes.CDLL(_MORTON_PORT if impl == "port" else _MORTON_REF), "pcu_oracle" if impl == "port" else "pcu_ref")
+    return _libs[key]
+
+
+def _codes(a, name):
+    a = np.asarray(a)
+    if a.dtype not in (np.uint32, np.uint64):
+        raise ValueError("%s must have dtype uint32 or uint64" % name)
+    if a.size == 0:
+        raise ValueError("%s must be an array of shape [n] but got an empty array" % name)
+    return np.ascontiguousarray(a.reshape(-1), dtype=np.uint64)
+
+
+def morton_encode(pts, impl=None):
+    """morton.cpp:185-239: (n, 3) int32 / int64 -> (n,) uint64."""
+    pts = np.asarray(pts)
+    if pts.dtype not in (np.int32, np.int64):
+        raise ValueError("pts must have dtype int32 or int64")
+    if pts.ndim != 2 or pts.shape[0] == 0:
+        raise ValueError("pts must be an array of shape [n, 3] but got an empty array")
+    if pts.shape[1] != 3:
+        raise ValueError("pts must be an array of shape [n, 3] but got an invalid number of columns")
+    p32 = np.ascontiguousarray(pts.astype(np.int32))          # int32_t px = pts(i, 0)
+    out = np.empty(p32.shape[0], np.uint64)
+    lib, prefix = _morton_lib(impl)
+    getattr(lib, prefix + "_morton_encode")(_vp(p32.ctypes.data), _c_i64(p32.shape[0]), _vp(out.ctypes.data))
+    return out
+
+
+def morton_decode(codes, impl=None):
+    """morton.cpp:253-310: (n,) -> (n, 3) int32."""
+    c = _codes(codes, "codes")
+    out = np.empty((c.shape[0], 3), np.int32)
+    lib, prefix = _morton_lib(impl)
+    getattr(lib, prefix + "_morton_decode")(_vp(c.ctypes.data), _c_i64(c.shape[0]), _vp(out.ctypes.data))
+    return out
+
+
+def _morton_binary(name, a, b, impl):
+    a, b = _codes(a, "codes_1"), _codes(b, "codes_2")
+    if a.shape != b.shape:
+        raise ValueError("codes_1 and codes_2 must have the same number of entries.")
+    out = np.empty_like(a)
+    lib, prefix = _morton_lib(impl)
+    getattr(lib, prefix + name)(_vp(a.ctypes.data), _vp(b.ctypes.data), _c_i64(a.shape[0]), _vp(out.ctypes.data))
+    return out
+
+
+def morton_add(codes_1, codes_2, impl=None):
+    """morton.cpp:26-103."""
+    return _morton_binary("_morton_add", codes_1, codes_2, impl)
+
+
+def morton_subtract(codes_1, codes_2, impl=None):
+    """morton.cpp:106-183."""
+    return _morton_binary("_morton_subtract", codes_1, codes_2, impl)
+
+
+def morton_knn(codes, qcodes, k, sort_dist=True, impl=None):
+    """morton.cpp:324-414.  The window of positions is the reference's; with sort_dist the rows are ordered by squared
+    distance to the query point, ties by position -- the INTENDED order (the reference's comparator reads three
+    uninitialised variables, :381-398, so its own order is undefined and cannot be pinned)."""
+    if k <= 0:
+        raise ValueError("k must be greater than 0")
+    c, q = _codes(codes, "codes"), _codes(qcodes, "qcodes")
+    k = min(int(k), c.shape[0])
+    out = np.empty((q.shape[0], k), np.int64)
+    lib, prefix = _morton_lib(impl)
+    getattr(lib, prefix + "_morton_knn_window")(_vp(c.ctypes.data), _c_i64(c.shape[0]), _vp(q.ctypes.data), _c_i64(q.shape[0]),
+                                                _c_int(k), _vp(out.ctypes.data))
+    if sort_dist:
+        pts = morton_decode(c, impl=impl).astype(np.float64)
+        qp = morton_decode(q, impl=impl).astype(np.float64)
+        d = ((pts[out] - qp[:, None, :]) ** 2).sum(-1)
+        order = np.argsort(d, axis=1, kind="stable")   # the window ascends in position, so stable = ties by position
+        out = np.take_along_axis(out, order, axis=1)
+    return out
+
+
 def kd_tree(dataset_points, max_points_per_leaf=10):
     """The restatement's built tree (order[] = nanoflann's vAcc, plus the node table), for checking
     GPU-side replicas of the build."""

@@ -37,7 +37,8 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
         "There is no pure-Python or CPU fallback for this package." % (_e,)) from _e
 
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
-           "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "device_count", "current_device", "launch_count"]
+           "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "morton_encode", "morton_decode", "morton_add",
+           "morton_subtract", "morton_knn", "device_count", "current_device", "launch_count"]
 
 _STATS_WORDS = 10  # sizeof(pcu_b200_nn_stats) / 8
 
@@ -437,6 +438,73 @@ def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None
     return _pcu_internal.estimate_point_cloud_normals_knn_internal(points, view_directions, int(num_neighbors),
                                                                    int(max_points_per_leaf), float(drop_angle_threshold),
                                                                    int(num_threads), -1, _dev(device))
+
+
+# ---------------------------------------------------------------------------------------------
+# 64-bit 3-D Morton codes: the reference's five bindings of /root/reference/src/morton.cpp, same names, arguments,
+# dtypes and error conditions (numpy in, numpy out; integer work, bit-identical results)
+def morton_encode(pts, num_threads=-1, *, device=None):
+    """
+    Encode n 3D points using Morton coding, possibly sorting them
+
+    Args:
+        pts : an (n, 3)-shaped int32 / int64 array of 3D points (coordinates in [-2^20, 2^20))
+        num_threads : CPU thread count of the reference; accepted and ignored.
+
+    Returns:
+        codes : an (n,)-shaped uint64 array of Morton codes
+
+    Mirrors /root/reference/src/morton.cpp:185-239 (MortonCode64, src/common/morton_code.cpp:43-63).
+    """
+    return _pcu_internal.morton_encode(_np.asarray(pts), int(num_threads), _dev(device))
+
+
+def morton_decode(codes, num_threads=-1, *, device=None):
+    """
+    Decode n points along a Morton curve into 3D points
+
+    Args:
+        codes : an (n,)-shaped uint32 / uint64 array of Morton codes
+
+    Returns:
+        points : an (n, 3)-shaped int32 array of 3D points
+
+    Mirrors /root/reference/src/morton.cpp:253-310.
+    """
+    return _pcu_internal.morton_decode(_np.asarray(codes), int(num_threads), _dev(device))
+
+
+def morton_add(codes_1, codes_2, num_threads=-1, *, device=None):
+    """Add morton codes together (corresponding to adding the vectors they encode): (n,), (n,) -> (n,) uint64.
+    Mirrors /root/reference/src/morton.cpp:26-103."""
+    return _pcu_internal.morton_add(_np.asarray(codes_1), _np.asarray(codes_2), int(num_threads), _dev(device))
+
+
+def morton_subtract(codes_1, codes_2, num_threads=-1, *, device=None):
+    """Subtract morton codes from each other (codes_1 - codes_2): (n,), (n,) -> (n,) uint64.
+    Mirrors /root/reference/src/morton.cpp:106-183."""
+    return _pcu_internal.morton_subtract(_np.asarray(codes_1), _np.asarray(codes_2), int(num_threads), _dev(device))
+
+
+def morton_knn(codes, qcodes, k, sort_dist=True, *, device=None):
+    """
+    Queries a sorted array of morton encoded points to find the (approximate) k nearest neighbors
+
+    Args:
+        codes : an (n,)-shaped array of morton codes, sorted ascending
+        qcodes : an (m,)-shaped array of query codes (same dtype)
+        k : an integer representing the number of nearest neighbors
+        sort_dist : (optional, defaults to True) whether to return the nearest neighbors in distance sorted order
+
+    Returns:
+        nn_idx : an (m, min(k, n))-shaped int64 array of indices into codes: the k consecutive positions around the
+                 lower bound of each query code -- exactly the reference's window.  With sort_dist each row is ordered by
+                 squared distance to the query point (ties by position); the reference's own order is undefined there
+                 (its comparator reads uninitialised variables, /root/reference/src/morton.cpp:381-398).
+
+    Mirrors /root/reference/src/morton.cpp:324-414.
+    """
+    return _pcu_internal.morton_knn(_np.asarray(codes), _np.asarray(qcodes), int(k), bool(sort_dist), _dev(device))
 
 
 def batched_chamfer_distance(x, y, max_points_per_leaf=10, *, device=None):

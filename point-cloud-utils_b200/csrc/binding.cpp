@@ -13,6 +13,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/numpy.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -438,6 +439,89 @@ void normals_knn_device(bool is_f64, uintptr_t points, int64_t n, uintptr_t view
     check(status);
 }
 
+// ---- Morton codes (src/morton.cpp) ----------------------------------------------------------------
+// dtype rules of the bindings: pts int32 / int64; codes uint32 / uint64 (uint32 codes are widened, as the
+// reference's MortonCode64(uint64_t) constructor does implicitly); results are uint64 / int32 / int64 like the reference's.
+py::array_t<uint64_t, py::array::c_style> as_codes(const py::array& a, const char* name) {
+    if (!a.dtype().is(py::dtype::of<uint64_t>()) && !a.dtype().is(py::dtype::of<uint32_t>()))
+        throw py::value_error(std::string("Invalid scalar type (") + std::string(py::str(a.dtype())) + ") for argument '" + name +
+                              "'. Expected one of ['uint32', 'uint64'].");
+    if (a.ndim() == 0 || a.size() == 0) throw py::value_error(std::string(name) + " must be an array of shape [n] but got an empty array");
+    if (!(a.ndim() == 1 || (a.ndim() == 2 && a.shape(1) == 1)))
+        throw py::value_error(std::string(name) + " must be an array of shape [n] but got an invalid number of columns");
+    return py::array_t<uint64_t, py::array::c_style | py::array::forcecast>::ensure(a);
+}
+
+py::array morton_encode(const py::array& pts, int num_threads, int device) {
+    (void)num_threads;
+    const bool i32 = pts.dtype().is(py::dtype::of<int32_t>()), i64 = pts.dtype().is(py::dtype::of<int64_t>());
+    if (!i32 && !i64)
+        throw py::value_error("Invalid scalar type (" + std::string(py::str(pts.dtype())) + ") for argument 'pts'. Expected one of ['int32', 'int64'].");
+    if (pts.ndim() != 2 || pts.shape(0) <= 0) throw py::value_error("pts must be an array of shape [n, 3] but got an empty array");
+    if (pts.shape(1) != 3) throw py::value_error("pts must be an array of shape [n, 3] but got an invalid number of columns");
+    const int64_t n = pts.shape(0);
+    py::array_t<uint64_t> codes({(py::ssize_t)n});
+    Slot& slot = pool().get(current_device_or_default(device), kHostKey);
+    int status;
+    if (i32) {
+        auto p = py::array_t<int32_t, py::array::c_style | py::array::forcecast>::ensure(pts);
+        CallScope scope(slot);
+        status = pcu_b200_morton_encode_host_i32(slot.ws, p.data(), n, codes.mutable_data());
+    } else {
+        auto p = py::array_t<int64_t, py::array::c_style | py::array::forcecast>::ensure(pts);
+        CallScope scope(slot);
+        status = pcu_b200_morton_encode_host_i64(slot.ws, p.data(), n, codes.mutable_data());
+    }
+    check(status);
+    return codes;
+}
+
+py::array morton_decode(const py::array& codes_in, int num_threads, int device) {
+    (void)num_threads;
+    auto codes = as_codes(codes_in, "codes");
+    const int64_t n = codes.size();
+    py::array_t<int32_t> pts({(py::ssize_t)n, (py::ssize_t)3});
+    Slot& slot = pool().get(current_device_or_default(device), kHostKey);
+    int status;
+    { CallScope scope(slot); status = pcu_b200_morton_decode_host(slot.ws, codes.data(), n, pts.mutable_data()); }
+    check(status);
+    return pts;
+}
+
+py::array morton_addsub(const py::array& a_in, const py::array& b_in, int num_threads, int device, bool subtract) {
+    (void)num_threads;
+    auto a = as_codes(a_in, "codes_1");
+    auto b = as_codes(b_in, "codes_2");
+    if (a.size() != b.size()) throw py::value_error("codes_1 and codes_2 must have the same number of entries.");
+    const int64_t n = a.size();
+    py::array_t<uint64_t> out({(py::ssize_t)n});
+    Slot& slot = pool().get(current_device_or_default(device), kHostKey);
+    int status;
+    {
+        CallScope scope(slot);
+        status = subtract ? pcu_b200_morton_subtract_host(slot.ws, a.data(), b.data(), n, out.mutable_data())
+                          : pcu_b200_morton_add_host(slot.ws, a.data(), b.data(), n, out.mutable_data());
+    }
+    check(status);
+    return out;
+}
+
+py::array morton_knn(const py::array& codes_in, const py::array& qcodes_in, int k, bool sort_dist, int device) {
+    if (k <= 0) throw py::value_error("k must be greater than 0");
+    auto codes = as_codes(codes_in, "codes");
+    auto qcodes = as_codes(qcodes_in, "qcodes");
+    if (!qcodes_in.dtype().is(codes_in.dtype()))
+        throw py::value_error("Invalid scalar type for argument 'qcodes'. Expected it to match argument 'codes'.");
+    const int64_t n = codes.size(), m = qcodes.size();
+    k = (int)std::min<int64_t>(k, n);                       // morton.cpp:351
+    py::array_t<int64_t> idx({(py::ssize_t)m, (py::ssize_t)k});
+    Slot& slot = pool().get(current_device_or_default(device), kHostKey);
+    int status;
+    { CallScope scope(slot); status = pcu_b200_morton_knn_host(slot.ws, codes.data(), n, qcodes.data(), m, k, sort_dist ? 1 : 0, idx.mutable_data()); }
+    check(status);
+    return idx;
+}
+
 // ---- raw device-pointer entry points (CUDA torch tensors) --------------------------------------
 void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int64_t m, int k, bool squared,
                 uintptr_t out_dist, uintptr_t out_idx, uintptr_t out_n_tied, int max_points_per_leaf, int device,
@@ -593,6 +677,19 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("device") = -1,
             "Indices of the kept points and their unit normals (plane fit to the k nearest neighbours of each point).");
     mod.def("_normals_knn_device", &normals_knn_device);
+    mod.def("morton_encode", &morton_encode, py::arg("pts"), py::arg("num_threads") = -1, py::arg("device") = -1,
+            "Encode n 3D integer points into Morton codes: (n, 3) int32 / int64 -> (n,) uint64.");
+    mod.def("morton_decode", &morton_decode, py::arg("codes"), py::arg("num_threads") = -1, py::arg("device") = -1,
+            "Decode n Morton codes into 3D integer points: (n,) -> (n, 3) int32.");
+    mod.def("morton_add", [](const py::array& a, const py::array& b, int t, int d) { return morton_addsub(a, b, t, d, false); },
+            py::arg("codes_1"), py::arg("codes_2"), py::arg("num_threads") = -1, py::arg("device") = -1,
+            "Add morton codes together (corresponding to adding the vectors they encode).");
+    mod.def("morton_subtract", [](const py::array& a, const py::array& b, int t, int d) { return morton_addsub(a, b, t, d, true); },
+            py::arg("codes_1"), py::arg("codes_2"), py::arg("num_threads") = -1, py::arg("device") = -1,
+            "Subtract morton codes from each other (codes_1 - codes_2).");
+    mod.def("morton_knn", &morton_knn, py::arg("codes"), py::arg("qcodes"), py::arg("k"), py::arg("sort_dist") = true,
+            py::arg("device") = -1,
+            "Queries a sorted array of morton encoded points to find the (approximate) k nearest neighbors: (m, min(k, n)) int64.");
     mod.def("_chamfer_stats", &chamfer_stats, py::arg("x"), py::arg("y"), py::arg("max_points_per_leaf") = 10,
             py::arg("device") = -1);
     mod.def("_batched_chamfer", &batched_chamfer_numpy, py::arg("x"), py::arg("y"), py::arg("max_points_per_leaf") = 10,

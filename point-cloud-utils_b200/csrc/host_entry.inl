@@ -173,6 +173,30 @@ int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const
     return PCU_B200_OK;
 }
 
+// Morton entry points on HOST arrays: up to two inputs, one output, copies either side of one device call.
+template <typename Call>
+int morton_host(pcu_b200_workspace* ws, const void* in_a, size_t bytes_a, const void* in_b, size_t bytes_b, void* out,
+                size_t bytes_out, Call&& call) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!in_a || bytes_a == 0 || (bytes_b != 0 && !in_b)) return fail(PCU_B200_INVALID_ARGUMENT, "codes / pts must be non-empty arrays but got an empty array");
+    if (!out) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_ON_DEVICE(ws);
+    cudaStream_t st = ws->own_stream;
+    Carver measure(nullptr);
+    measure.take<unsigned char>(bytes_a); measure.take<unsigned char>(bytes_b ? bytes_b : 1); measure.take<unsigned char>(bytes_out);
+    PCU_TRY(ensure_io(ws, measure.off, st));
+    Carver cv(ws->io);
+    unsigned char* da = cv.take<unsigned char>(bytes_a);
+    unsigned char* db = cv.take<unsigned char>(bytes_b ? bytes_b : 1);
+    unsigned char* dout = cv.take<unsigned char>(bytes_out);
+    PCU_CUDA(cudaMemcpyAsync(da, in_a, bytes_a, cudaMemcpyHostToDevice, st));
+    if (bytes_b) PCU_CUDA(cudaMemcpyAsync(db, in_b, bytes_b, cudaMemcpyHostToDevice, st));
+    PCU_TRY(call(da, db, dout, st));
+    PCU_CUDA(cudaMemcpyAsync(out, dout, bytes_out, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    return PCU_B200_OK;
+}
+
 template <typename T>
 int debug_kd_tree(pcu_b200_workspace* ws, const T* points, long long m, int leaf, int32_t* order, long long node_cap,
                   int32_t* feat, T* div_lo, T* div_hi, int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1,
@@ -247,6 +271,46 @@ int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int
     return debug_kd_tree<double>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
                                  kid0, kid1, out_nodes);
 }
+int pcu_b200_morton_encode_host_i32(pcu_b200_workspace* ws, const int32_t* pts, int64_t n, uint64_t* out_codes) {
+    if (n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "pts must be an array of shape [n, 3] but got an empty array");
+    return morton_host(ws, pts, sizeof(int32_t) * 3 * n, nullptr, 0, out_codes, sizeof(uint64_t) * n,
+                       [&](unsigned char* a, unsigned char*, unsigned char* o, cudaStream_t st) {
+                           return morton_encode_device<int32_t>(ws, (const int32_t*)a, n, (unsigned long long*)o, st); });
+}
+int pcu_b200_morton_encode_host_i64(pcu_b200_workspace* ws, const int64_t* pts, int64_t n, uint64_t* out_codes) {
+    if (n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "pts must be an array of shape [n, 3] but got an empty array");
+    return morton_host(ws, pts, sizeof(int64_t) * 3 * n, nullptr, 0, out_codes, sizeof(uint64_t) * n,
+                       [&](unsigned char* a, unsigned char*, unsigned char* o, cudaStream_t st) {
+                           return morton_encode_device<long long>(ws, (const long long*)a, n, (unsigned long long*)o, st); });
+}
+int pcu_b200_morton_decode_host(pcu_b200_workspace* ws, const uint64_t* codes, int64_t n, int32_t* out_pts) {
+    if (n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "codes must be an array of shape [n] but got an empty array");
+    return morton_host(ws, codes, sizeof(uint64_t) * n, nullptr, 0, out_pts, sizeof(int32_t) * 3 * n,
+                       [&](unsigned char* a, unsigned char*, unsigned char* o, cudaStream_t st) {
+                           return morton_decode_device(ws, (const unsigned long long*)a, n, (int*)o, st); });
+}
+int pcu_b200_morton_add_host(pcu_b200_workspace* ws, const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out) {
+    if (n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "codes_1 must be an array of shape [n,] but got an empty array");
+    return morton_host(ws, a, sizeof(uint64_t) * n, b, sizeof(uint64_t) * n, out, sizeof(uint64_t) * n,
+                       [&](unsigned char* da, unsigned char* db, unsigned char* o, cudaStream_t st) {
+                           return morton_addsub_device(ws, (const unsigned long long*)da, (const unsigned long long*)db, n, 0, (unsigned long long*)o, st); });
+}
+int pcu_b200_morton_subtract_host(pcu_b200_workspace* ws, const uint64_t* a, const uint64_t* b, int64_t n, uint64_t* out) {
+    if (n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "codes_1 must be an array of shape [n,] but got an empty array");
+    return morton_host(ws, a, sizeof(uint64_t) * n, b, sizeof(uint64_t) * n, out, sizeof(uint64_t) * n,
+                       [&](unsigned char* da, unsigned char* db, unsigned char* o, cudaStream_t st) {
+                           return morton_addsub_device(ws, (const unsigned long long*)da, (const unsigned long long*)db, n, 1, (unsigned long long*)o, st); });
+}
+int pcu_b200_morton_knn_host(pcu_b200_workspace* ws, const uint64_t* codes, int64_t n, const uint64_t* qcodes, int64_t m, int k,
+                             int sort_dist, int64_t* out_idx) {
+    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "k must be greater than 0");
+    if (n <= 0 || m <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "codes must be an array of shape [n] but got an empty array");
+    if ((int64_t)k > n) return fail(PCU_B200_INVALID_ARGUMENT, "k (%d) exceeds the number of codes (%lld): clamp it first (morton.cpp:351)", k, (long long)n);
+    return morton_host(ws, codes, sizeof(uint64_t) * n, qcodes, sizeof(uint64_t) * m, out_idx, sizeof(int64_t) * m * k,
+                       [&](unsigned char* da, unsigned char* db, unsigned char* o, cudaStream_t st) {
+                           return morton_knn_device(ws, (const unsigned long long*)da, n, (const unsigned long long*)db, m, k, sort_dist, (long long*)o, st); });
+}
+
 int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs, int k,
                                   double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count) {
     return normals_knn_host<float>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals, (long long*)out_count);
