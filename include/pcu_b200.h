@@ -202,6 +202,26 @@ int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_
 int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                              double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
 
+/* ---- dense pairwise distances and Sinkhorn -------------------------------
+ * Replace the numpy code of point_cloud_utils/_sinkhorn.py: pairwise_distances (:4-34), sinkhorn (:37-126) and the
+ * cost (P * M).sum() of earth_movers_distance (:129-156).  DEVICE pointers, row-major dense arrays:
+ *   pairwise: a (nb, n, d), b (nb, m, d) -> out (nb, n, m), out[k, i, j] = || a[k, i] - b[k, j] ||_p;
+ *             norm_kind 0: p = 2 (np.linalg.norm default), 1: p = 1, 2: inf, 3: -inf, 4: p = 0 (count of non-zeros),
+ *             5: general p (the double argument)
+ *   sinkhorn: weights a (nb, n), b (nb, m), costs M (nb, n, m), eps, max_iters, stop_thresh -> plan out_P (nb, n, m);
+ *             out_cost (nb) fp64 = sum_ij P * M per batch or NULL; out_iters: device int32 or NULL.  The log-domain
+ *             iteration of the reference, its convergence test evaluated on the device (no host synchronisation).
+ * Floating point: element-wise expressions in the arrays' precision and the reference's order, the two reductions in
+ * fp64 -- agreement with numpy to rounding (tests/test_sinkhorn.py states the tolerances). */
+int pcu_b200_pairwise_distances_f32(pcu_b200_workspace* ws, const float* a, const float* b, int64_t nb, int64_t n, int64_t m, int d,
+                                    int norm_kind, double p, float* out, void* stream);
+int pcu_b200_pairwise_distances_f64(pcu_b200_workspace* ws, const double* a, const double* b, int64_t nb, int64_t n, int64_t m, int d,
+                                    int norm_kind, double p, double* out, void* stream);
+int pcu_b200_sinkhorn_f32(pcu_b200_workspace* ws, const float* a, const float* b, const float* M, int64_t nb, int64_t n, int64_t m,
+                          double eps, int max_iters, double stop_thresh, float* out_P, double* out_cost, int32_t* out_iters, void* stream);
+int pcu_b200_sinkhorn_f64(pcu_b200_workspace* ws, const double* a, const double* b, const double* M, int64_t nb, int64_t n, int64_t m,
+                          double eps, int max_iters, double stop_thresh, double* out_P, double* out_cost, int32_t* out_iters, void* stream);
+
 /* ---- 64-bit 3-D Morton codes --------------------------------------------
  * Replace MortonCode64 (src/common/morton_code.cpp:43-163) and the bindings morton_encode / morton_decode /
  * morton_add / morton_subtract / morton_knn (src/morton.cpp:185-239, :253-310, :26-103, :106-183, :324-414).

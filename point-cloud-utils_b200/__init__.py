@@ -38,7 +38,8 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
 
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
            "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "morton_encode", "morton_decode", "morton_add",
-           "morton_subtract", "morton_knn", "device_count", "current_device", "launch_count"]
+           "morton_subtract", "morton_knn", "pairwise_distances", "sinkhorn", "earth_movers_distance", "device_count",
+           "current_device", "launch_count"]
 
 _STATS_WORDS = 10  # sizeof(pcu_b200_nn_stats) / 8
 
@@ -505,6 +506,9 @@ def morton_knn(codes, qcodes, k, sort_dist=True, *, device=None):
     Mirrors /root/reference/src/morton.cpp:324-414.
     """
     return _pcu_internal.morton_knn(_np.asarray(codes), _np.asarray(qcodes), int(k), bool(sort_dist), _dev(device))
+
+
+from ._sinkhorn import pairwise_distances, sinkhorn, earth_movers_distance  # noqa: E402  (N4: dense metrics)
 
 
 def batched_chamfer_distance(x, y, max_points_per_leaf=10, *, device=None):

@@ -522,6 +522,32 @@ py::array morton_knn(const py::array& codes_in, const py::array& qcodes_in, int 
     return idx;
 }
 
+// ---- dense pairwise distances / Sinkhorn on device pointers (the Python layer owns the arrays) ----
+void pairwise_device(bool is_f64, uintptr_t a, uintptr_t b, int64_t nb, int64_t n, int64_t m, int d, int norm_kind, double p,
+                     uintptr_t out, int device, uintptr_t stream) {
+    Slot& slot = pool().get(device, stream);
+    int status;
+    {
+        CallScope scope(slot);
+        status = is_f64 ? pcu_b200_pairwise_distances_f64(slot.ws, (const double*)a, (const double*)b, nb, n, m, d, norm_kind, p, (double*)out, (void*)stream)
+                        : pcu_b200_pairwise_distances_f32(slot.ws, (const float*)a, (const float*)b, nb, n, m, d, norm_kind, p, (float*)out, (void*)stream);
+    }
+    check(status);
+}
+void sinkhorn_device(bool is_f64, uintptr_t a, uintptr_t b, uintptr_t M, int64_t nb, int64_t n, int64_t m, double eps, int max_iters,
+                     double stop_thresh, uintptr_t out_P, uintptr_t out_cost, uintptr_t out_iters, int device, uintptr_t stream) {
+    Slot& slot = pool().get(device, stream);
+    int status;
+    {
+        CallScope scope(slot);
+        status = is_f64 ? pcu_b200_sinkhorn_f64(slot.ws, (const double*)a, (const double*)b, (const double*)M, nb, n, m, eps, max_iters,
+                                                stop_thresh, (double*)out_P, (double*)out_cost, (int32_t*)out_iters, (void*)stream)
+                        : pcu_b200_sinkhorn_f32(slot.ws, (const float*)a, (const float*)b, (const float*)M, nb, n, m, eps, max_iters,
+                                                stop_thresh, (float*)out_P, (double*)out_cost, (int32_t*)out_iters, (void*)stream);
+    }
+    check(status);
+}
+
 // ---- raw device-pointer entry points (CUDA torch tensors) --------------------------------------
 void knn_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t dataset, int64_t m, int k, bool squared,
                 uintptr_t out_dist, uintptr_t out_idx, uintptr_t out_n_tied, int max_points_per_leaf, int device,
@@ -677,6 +703,8 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("device") = -1,
             "Indices of the kept points and their unit normals (plane fit to the k nearest neighbours of each point).");
     mod.def("_normals_knn_device", &normals_knn_device);
+    mod.def("_pairwise_device", &pairwise_device);
+    mod.def("_sinkhorn_device", &sinkhorn_device);
     mod.def("morton_encode", &morton_encode, py::arg("pts"), py::arg("num_threads") = -1, py::arg("device") = -1,
             "Encode n 3D integer points into Morton codes: (n, 3) int32 / int64 -> (n,) uint64.");
     mod.def("morton_decode", &morton_decode, py::arg("codes"), py::arg("num_threads") = -1, py::arg("device") = -1,

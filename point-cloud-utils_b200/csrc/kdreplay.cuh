@@ -33,10 +33,16 @@ namespace pcu {
 
 constexpr int kKdItems = 8;                       // slots per thread and scan tile
 constexpr int kKdTile = kThreads * kKdItems;      // slots per scan tile
+// A node of at most this many points leaves the level-synchronous grid-wide build: its whole subtree is built by
+// ONE CTA (block barriers instead of grid barriers, the levels of all such subtrees advance independently).
+// Small on purpose: a CTA walks its range with blockDim threads, so the subtrees must be numerous enough to keep as
+// many threads busy as the grid-wide passes do (8192 measured slower than no hand-off at all: 128 CTAs for 10^6 points).
+constexpr int kKdLocalCap = 1024;
 
 template <typename T>
 struct KdNode {
-    int feat;            // split dimension; -1 = leaf; -2 = not decided yet; -3 = stub (pruned build: left unsplit)
+    int feat;            // split dimension; -1 = leaf; -2 = not decided yet; -3 = stub (pruned build: left unsplit);
+                         // -4 = root of a subtree handed to one CTA (kKdLocalCap), split in the second phase of the build
     int first, last;     // slot range [first, last) in order[]
     int kid0, kid1;
     int parent;          // parent node (-1 for the root); side: 0 = left child, 1 = right child
@@ -57,6 +63,16 @@ struct KdCounters {
     int done;           // set when a level split nothing
     int levels;         // levels processed (diagnostic)
     int any_eq;         // current level: some live point equals its node's cut (sweep 2 has work to do)
+    int n_local;        // subtree roots handed to single CTAs so far (KdReplayBuffers::local_roots)
+};
+
+// How a pass reads the flag prefix sums: the grid-wide phases store in-tile prefixes plus tile offsets over all
+// slots; a CTA building a subtree stores absolute prefixes over its own slot range [.., range_end) and keeps the
+// grand total ("the prefix at range_end", a slot that belongs to the neighbouring subtree) to itself.
+struct KdScope {
+    bool local;
+    int range_end;
+    unsigned total;
 };
 
 template <typename T>
@@ -70,6 +86,8 @@ struct KdReplayBuffers {
     int* right_pos = nullptr;
     KdNode<T>* nodes = nullptr;       // 2 * capacity
     KdCounters* counters = nullptr;
+    int* local_roots = nullptr;       // capacity: nodes whose subtrees single CTAs build
+    int* level_lists = nullptr;       // 2 * capacity: per subtree, the node ids of the current / the next level (in its slot range)
     unsigned* stub_hits = nullptr;    // searches that ran into a stub of the pruned build (-> full rebuild)
     unsigned* overflows = nullptr;    // searches whose walk was deeper than kKdStack (adversarially deep trees): reported
     long long* one_row = nullptr;     // scratch for the single-query (witness) replay
@@ -86,6 +104,8 @@ struct KdReplayBuffers {
         right_pos = cv.take<int>((size_t)points);
         nodes = cv.take<KdNode<T>>((size_t)2 * points + 2);
         counters = cv.take<KdCounters>(1);
+        local_roots = cv.take<int>((size_t)points);
+        level_lists = cv.take<int>((size_t)2 * points);
         stub_hits = cv.take<unsigned>(1);
         overflows = cv.take<unsigned>(1);
         one_row = cv.take<long long>(1);
@@ -165,7 +185,9 @@ __device__ __forceinline__ void kd_tight_box_slot(const KdReplayBuffers<T>& b, c
 // This is a heuristic, not a proof: a walk that does run into a stub reports it (kd_search_one returns
 // false) and the caller rebuilds the full tree for that call, so results never depend on the pruning.
 constexpr int kKdMaskWords = 4;
-constexpr int kKdMaxPruneQueries = 32 * kKdMaskWords;   // one mask bit per flagged query; more -> full build
+constexpr int kKdMaxPruneQueries = 64;   // one mask bit per flagged query (at most 32 * kKdMaskWords); more -> full build: measured
+                                         // on 10^6 points, the pruned build wins at 6 and 27 flagged rows (2.0 vs 2.6 ms,
+                                         // 2.7 vs 3.0) and loses at 80 (3.5 vs 3.1): their walks reach most of the tree
 constexpr int kKdSmallNode = 256;        // nodes up to this many points always follow their parent
 
 template <typename T>
@@ -255,7 +277,8 @@ __device__ bool kd_node_mask(const KdReplayBuffers<T>& b, const KdPrune<T>& pr, 
 // leaf-or-split decision + split plane of one node; also hands this node's tight extent along the
 // parent's split axis up to the parent (divlow / divhigh, nanoflann.hpp:1047-1048).
 template <typename T>
-__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap, const KdPrune<T>& pr, unsigned n_flagged) {
+__device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int id, int leaf_cap, const KdPrune<T>& pr, unsigned n_flagged,
+                                               bool may_hand_off) {
     using R = Real<T>;
     KdNode<T>& nd = b.nodes[id];
     T tlo[3], thi[3];
@@ -279,6 +302,11 @@ __device__ __forceinline__ void kd_decide_node(const KdReplayBuffers<T>& b, int 
     const int count = nd.last - nd.first;
     if (count <= leaf_cap) { nd.feat = -1; return; }
     if (!wanted) { nd.feat = -3; return; }   // no flagged query comes here: stub
+    if (may_hand_off && count <= kKdLocalCap) {   // small enough: one CTA builds the whole subtree later
+        nd.feat = -4;
+        b.local_roots[atomicAdd(&b.counters->n_local, 1)] = id;
+        return;
+    }
     // middleSplit_ (nanoflann.hpp:1061-1096)
     const T eps = (T)0.00001;
     T widest = R::sub(nd.loose_hi[0], nd.loose_lo[0]);
@@ -322,7 +350,8 @@ __device__ __forceinline__ unsigned kd_flag(const KdReplayBuffers<T>& b, const T
 
 // exclusive prefix of the flags at slot s: in-tile prefix + offset of the tile
 template <typename T>
-__device__ __forceinline__ unsigned kd_prefix(const KdReplayBuffers<T>& b, int s) {
+__device__ __forceinline__ unsigned kd_prefix(const KdReplayBuffers<T>& b, int s, const KdScope& sc) {
+    if (sc.local) return s == sc.range_end ? sc.total : b.prefix[s];
     return b.prefix[s] + b.scan_partial[s / kKdTile];
 }
 
@@ -331,20 +360,20 @@ __device__ __forceinline__ unsigned kd_prefix(const KdReplayBuffers<T>& b, int s
 // unflagged slot of [lo, lo + F) (ascending) exchanges with the j-th flagged slot of [lo + F, last)
 // (descending).
 template <typename T, int kSweep>
-__device__ __forceinline__ void kd_partner_slot(const KdReplayBuffers<T>& b, int s) {
+__device__ __forceinline__ void kd_partner_slot(const KdReplayBuffers<T>& b, int s, const KdScope& sc) {
     const int node = b.node_of[s];
     if (node < 0) return;
     KdNode<T>& nd = b.nodes[node];
     if (nd.feat < 0) return;
     const int lo = kSweep == 1 ? nd.first : nd.first + nd.n_less;
-    const unsigned at_lo = kd_prefix<T>(b, lo), at_last = kd_prefix<T>(b, nd.last);
+    const unsigned at_lo = kd_prefix<T>(b, lo, sc), at_last = kd_prefix<T>(b, nd.last, sc);
     const int F = (int)(at_last - at_lo);
     if (s == nd.first) {
         if (kSweep == 1) { nd.n_less = F; nd.n_less_eq = F; }   // sweep 2, when it runs, overwrites n_less_eq
         else nd.n_less_eq = nd.n_less + F;
     }
     if (s < lo) return;
-    const unsigned here = kd_prefix<T>(b, s), next = kd_prefix<T>(b, s + 1);
+    const unsigned here = kd_prefix<T>(b, s, sc), next = kd_prefix<T>(b, s + 1, sc);
     const bool flagged = next != here;
     const int r = s - lo;
     if (r < F && !flagged) b.left_pos[lo + (r - (int)(here - at_lo))] = s;
@@ -352,7 +381,7 @@ __device__ __forceinline__ void kd_partner_slot(const KdReplayBuffers<T>& b, int
 }
 
 template <typename T, int kSweep>
-__device__ __forceinline__ void kd_exchange_slot(const KdReplayBuffers<T>& b, int s) {
+__device__ __forceinline__ void kd_exchange_slot(const KdReplayBuffers<T>& b, int s, const KdScope& sc) {
     const int node = b.node_of[s];
     if (node < 0) return;
     const KdNode<T>& nd = b.nodes[node];
@@ -361,7 +390,7 @@ __device__ __forceinline__ void kd_exchange_slot(const KdReplayBuffers<T>& b, in
     const int lo = kSweep == 1 ? nd.first : nd.first + nd.n_less;
     if (s < lo) return;
     const int F = kSweep == 1 ? nd.n_less : nd.n_less_eq - nd.n_less;
-    const int misplaced = F - (int)(kd_prefix<T>(b, lo + F) - kd_prefix<T>(b, lo));   // unflagged slots inside [lo, lo + F)
+    const int misplaced = F - (int)(kd_prefix<T>(b, lo + F, sc) - kd_prefix<T>(b, lo, sc));   // unflagged slots inside [lo, lo + F)
     const int j = s - lo;
     if (j >= misplaced) return;
     const int a = b.left_pos[lo + j], c = b.right_pos[lo + j];
@@ -372,7 +401,7 @@ __device__ __forceinline__ void kd_exchange_slot(const KdReplayBuffers<T>& b, in
 
 // children of one split node (nanoflann.hpp:1098-1110, :1033-1045)
 template <typename T>
-__device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, int id) {
+__device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, int id, int* next_list = nullptr, int* next_count = nullptr) {
     using R = Real<T>;
     KdNode<T>& nd = b.nodes[id];
     if (nd.feat < 0) return;
@@ -382,7 +411,11 @@ __device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, in
     else if (nd.n_less_eq < count / 2) left = nd.n_less_eq;
     else left = count / 2;
     const int k0 = atomicAdd(&b.counters->n_nodes, 2);
-    atomicAdd(&b.counters->n_split, 1);
+    if (next_list == nullptr) atomicAdd(&b.counters->n_split, 1);
+    else {   // a CTA building a subtree keeps its own list of the next level's nodes (shared-memory counter)
+        const int at = atomicAdd(next_count, 2);
+        next_list[at] = k0; next_list[at + 1] = k0 + 1;
+    }
     nd.kid0 = k0; nd.kid1 = k0 + 1;
     for (int side = 0; side < 2; ++side) {
         KdNode<T> ch{};
@@ -440,6 +473,95 @@ __device__ __forceinline__ void kd_scan_phase(cooperative_groups::grid_group& gr
     grid.sync();
 }
 
+// One flag-and-scan phase of a CTA building a subtree: absolute exclusive prefixes over the slots [first, last);
+// the grand total stays in shared memory (KdScope::total).  Block-wide.
+template <typename T, int kSweep>
+__device__ __forceinline__ void kd_scan_subtree(const KdReplayBuffers<T>& b, const T* __restrict__ pts, int first, int last,
+                                                unsigned* s_total, int* s_any_eq) {
+    unsigned carry = 0;
+    for (int base = first; base < last; base += kKdTile) {
+        const int at = base + threadIdx.x * kKdItems;
+        unsigned v[kKdItems];
+        unsigned sum = 0, eq = 0;
+#pragma unroll
+        for (int k = 0; k < kKdItems; ++k) {
+            const unsigned r = (at + k) < last ? kd_flag<T, kSweep>(b, pts, at + k, last) : 0u;
+            v[k] = r & 1u; eq |= r >> 1; sum += v[k];
+        }
+        if (kSweep == 1 && eq) *s_any_eq = 1;   // benign race: every writer stores 1
+        unsigned total;
+        unsigned run = carry + kd_block_exclusive_scan(sum, &total);
+#pragma unroll
+        for (int k = 0; k < kKdItems; ++k) {
+            if ((at + k) < last) b.prefix[at + k] = run;
+            run += v[k];
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) *s_total = carry;
+    __syncthreads();
+}
+
+// The whole subtree below `root` (a node the grid-wide phase handed off: feat == -4, at most kKdLocalCap slots),
+// built level by level by ONE CTA with the very passes of the grid-wide build, over the subtree's own slot range,
+// separated by block barriers.  The node ids of a level live in the subtree's part of level_lists.
+template <typename T>
+__device__ void kd_build_subtree(const KdReplayBuffers<T>& b, const T* __restrict__ pts, int root, int leaf_cap,
+                                 const KdPrune<T>& pr, unsigned n_flagged) {
+    __shared__ int s_count[2];       // nodes in the current / the next level
+    __shared__ int s_any_eq;
+    __shared__ unsigned s_total;
+    const int first = b.nodes[root].first, last = b.nodes[root].last;
+    int* cur = b.level_lists + first;
+    int* nxt = b.level_lists + b.capacity + first;
+    const int warp_first = first & ~31;   // whole warps take part in the tight-box reduction
+    __syncthreads();                  // the previous subtree of this CTA is finished with the shared variables
+    if (threadIdx.x == 0) { cur[0] = root; s_count[0] = 1; s_count[1] = 0; b.nodes[root].feat = -2; }
+    for (int s = first + threadIdx.x; s < last; s += blockDim.x) b.node_of[s] = root;   // the grid phase had retired them
+    __syncthreads();
+    for (int level = 0; level < 4096; ++level) {
+        const int ncur = s_count[0];
+        if (ncur == 0) break;
+        if (threadIdx.x == 0) s_any_eq = 0;
+        for (int i = threadIdx.x; i < ncur; i += blockDim.x) kd_decide_node<T>(b, cur[i], leaf_cap, pr, n_flagged, false);
+        __syncthreads();
+        kd_scan_subtree<T, 1>(b, pts, first, last, &s_total, &s_any_eq);
+        KdScope sc{true, last, s_total};
+        for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_partner_slot<T, 1>(b, s, sc);
+        __syncthreads();
+        for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_exchange_slot<T, 1>(b, s, sc);
+        __syncthreads();
+        if (s_any_eq != 0) {
+            kd_scan_subtree<T, 2>(b, pts, first, last, &s_total, &s_any_eq);
+            sc.total = s_total;
+            for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_partner_slot<T, 2>(b, s, sc);
+            __syncthreads();
+            for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_exchange_slot<T, 2>(b, s, sc);
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < ncur; i += blockDim.x) kd_children_node<T>(b, cur[i], nxt, &s_count[1]);
+        __syncthreads();
+        for (int s = warp_first + threadIdx.x; s < ((last + 31) & ~31); s += blockDim.x) {
+            const bool mine = s >= first && s < last;
+            if (mine) {
+                const int node = b.node_of[s];
+                if (node >= 0) {
+                    const KdNode<T>& nd = b.nodes[node];
+                    b.node_of[s] = nd.feat < 0 ? -1 : (s < b.nodes[nd.kid0].last ? nd.kid0 : nd.kid1);
+                }
+            }
+            kd_tight_box_slot<T>(b, pts, mine ? s : last, last);   // slots outside the range take no part
+        }
+        // the tight boxes were updated by atomics (performed at L2); the device-scope fence also drops the stale copies
+        // of those node records from this SM's L1 before the next level's decide reads them with plain loads
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) { s_count[0] = s_count[1]; s_count[1] = 0; }
+        int* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+    }
+}
+
 // The whole build in one cooperative launch.  `gate` (may be null): device counter; when it reads
 // zero nobody needs the tree and every CTA returns immediately.
 template <typename T>
@@ -458,6 +580,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
         if (nt <= (unsigned)kKdMaxPruneQueries) n_flagged = nt;
     }
     cg::grid_group grid = cg::this_grid();
+    const KdScope grid_scope{false, 0, 0u};
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsize = gridDim.x * blockDim.x;
     const int m_warp = (m + 31) & ~31;            // whole warps take part in the tight-box reduction
@@ -477,22 +600,22 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
 
     for (int level = 0; level < 4096; ++level) {
         const int lb = *(volatile int*)&b.counters->level_begin, le = *(volatile int*)&b.counters->level_end;
-        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap, pr, n_flagged);
+        for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap, pr, n_flagged, true);
         grid.sync();
         // sweep 1: strictly-less-than-the-cut to the front
         kd_scan_phase<T, 1>(grid, b, pts, m);
-        for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 1>(b, s);
+        for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 1>(b, s, grid_scope);
         grid.sync();
-        for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 1>(b, s);
+        for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 1>(b, s, grid_scope);
         grid.sync();
         // sweep 2: equal-to-the-cut next.  planeSplit's second loop (nanoflann.hpp:1143-1158) moves nothing
         // when no point of the node equals the cut (lim2 == lim1); any_eq was raised by sweep 1's scan and
         // is stable since the barrier that ended it, so the whole grid takes the same branch.
         if (*(volatile int*)&b.counters->any_eq != 0) {
             kd_scan_phase<T, 2>(grid, b, pts, m);
-            for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 2>(b, s);
+            for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 2>(b, s, grid_scope);
             grid.sync();
-            for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 2>(b, s);
+            for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 2>(b, s, grid_scope);
             grid.sync();
         }
         for (int id = lb + gtid; id < le; id += gsize) kd_children_node<T>(b, id);
@@ -522,6 +645,9 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
         grid.sync();
         if (*(volatile int*)&b.counters->done) break;
     }
+    // second phase: the subtrees handed off above, one CTA each, all of them side by side
+    const int n_local = *(volatile int*)&b.counters->n_local;
+    for (int i = blockIdx.x; i < n_local; i += gridDim.x) kd_build_subtree<T>(b, pts, b.local_roots[i], leaf_cap, pr, n_flagged);
 }
 
 // ---- search ---------------------------------------------------------------------------------------

@@ -26,6 +26,7 @@
 #include "kdreplay.cuh"
 #include "normals.cuh"
 #include "morton.cuh"
+#include "sinkhorn.cuh"
 
 using namespace pcu;
 
@@ -816,6 +817,58 @@ int morton_knn_device(pcu_b200_workspace* ws, const unsigned long long* codes, l
     return PCU_B200_OK;
 }
 
+// ---- dense pairwise distances, Sinkhorn ------------------------------------------------
+template <typename T>
+int pairwise_device(pcu_b200_workspace* ws, const T* a, const T* b, long long nb, long long n, long long m, int d, int norm_kind,
+                    double p, T* out, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!a || !b || !out) return fail(PCU_B200_INVALID_ARGUMENT, "null pointer");
+    if (nb <= 0 || n <= 0 || m <= 0 || d <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid shape: a and b must be [m, n, d] or [n, d] with positive sizes");
+    if (norm_kind < kNorm2 || norm_kind > kNormP) return fail(PCU_B200_INVALID_ARGUMENT, "unknown norm");
+    if (nb > 65535 || n > 65535) return fail(PCU_B200_INVALID_ARGUMENT, "pairwise_distances: at most 65535 batches and rows per launch");
+    PCU_ON_DEVICE(ws);
+    PCU_LAUNCH((pairwise_kernel<T>), dim3(blocks_for(m), (unsigned)n, (unsigned)nb), kThreads, stream, a, b, n, m, d, norm_kind, p, out);
+    return PCU_B200_OK;
+}
+
+// a: (nb, n) weights, b: (nb, m) weights, M: (nb, n, m) costs -> P: (nb, n, m); out_cost (nb) fp64 = sum P * M, or null;
+// out_iters: device int32, iterations run (or null).  No host synchronisation: the iteration's three kernels are
+// enqueued max_iters times and return at once after the convergence test has passed on the device.
+template <typename T>
+int sinkhorn_device(pcu_b200_workspace* ws, const T* a, const T* b, const T* M, long long nb, long long n, long long m, double eps,
+                    int max_iters, double stop_thresh, T* out_P, double* out_cost, int* out_iters, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!a || !b || !M || !out_P) return fail(PCU_B200_INVALID_ARGUMENT, "null pointer");
+    if (nb <= 0 || n <= 0 || m <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Got unexpected shape for M, should be [nb, m, n] with positive sizes");
+    if (nb > 65535 || n > 65535) return fail(PCU_B200_INVALID_ARGUMENT, "sinkhorn: at most 65535 batches and rows per launch");
+    if (max_iters < 0) return fail(PCU_B200_INVALID_ARGUMENT, "max_iters must be >= 0");
+    PCU_ON_DEVICE(ws);
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& u, T*& v, double*& eu, double*& ev, int*& flags) {
+        u = cv.take<T>((size_t)nb * n);
+        v = cv.take<T>((size_t)nb * m);
+        eu = cv.take<double>((size_t)nb);
+        ev = cv.take<double>((size_t)nb);
+        flags = cv.take<int>(2);   // [0] done, [1] iterations
+    };
+    T *u, *v; double *eu, *ev; int* flags;
+    carve(measure, u, v, eu, ev, flags);
+    PCU_TRY(ensure_arena(ws, measure.off, stream));
+    Carver cv(ws->arena);
+    carve(cv, u, v, eu, ev, flags);
+    PCU_CUDA(cudaMemsetAsync(ws->arena, 0, measure.off, stream));   // u = v = 0 (:101-102), accumulators, flags
+    if (out_cost) PCU_CUDA(cudaMemsetAsync(out_cost, 0, sizeof(double) * nb, stream));
+    const T e = (T)eps;
+    for (int it = 0; it < max_iters; ++it) {
+        PCU_LAUNCH((sinkhorn_half_kernel<T, false>), dim3((unsigned)n, (unsigned)nb), kThreads, stream, M, a, v, u, n, m, e, eu, flags);
+        PCU_LAUNCH((sinkhorn_half_kernel<T, true>), dim3((unsigned)((m + 31) / 32), (unsigned)nb), kThreads, stream, M, b, u, v, m, n, e, ev, flags);
+        PCU_LAUNCH(sinkhorn_check_kernel, 1, kThreads, stream, eu, ev, nb, stop_thresh, flags, flags + 1);
+    }
+    PCU_LAUNCH((sinkhorn_plan_kernel<T>), dim3(blocks_for(m), (unsigned)n, (unsigned)nb), kThreads, stream, M, u, v, n, m, e, out_P, out_cost);
+    if (out_iters) PCU_CUDA(cudaMemcpyAsync(out_iters, flags + 1, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    return PCU_B200_OK;
+}
+
 // ---- batched Chamfer ---------------------------------------------------------------------------
 template <typename T>
 int batched_chamfer_device(pcu_b200_workspace* ws, const T* x, const T* y, long long batch, long long n, long long m,
@@ -1075,6 +1128,23 @@ int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, cons
 int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
                          pcu_b200_nn_stats* out_stats, double* out_value, void* stream) {
     return stats_device<double>(ws, x, n, y, m, true, out_stats, out_value, (cudaStream_t)stream);
+}
+
+int pcu_b200_pairwise_distances_f32(pcu_b200_workspace* ws, const float* a, const float* b, int64_t nb, int64_t n, int64_t m, int d,
+                                    int norm_kind, double p, float* out, void* stream) {
+    return pairwise_device<float>(ws, a, b, nb, n, m, d, norm_kind, p, out, (cudaStream_t)stream);
+}
+int pcu_b200_pairwise_distances_f64(pcu_b200_workspace* ws, const double* a, const double* b, int64_t nb, int64_t n, int64_t m, int d,
+                                    int norm_kind, double p, double* out, void* stream) {
+    return pairwise_device<double>(ws, a, b, nb, n, m, d, norm_kind, p, out, (cudaStream_t)stream);
+}
+int pcu_b200_sinkhorn_f32(pcu_b200_workspace* ws, const float* a, const float* b, const float* M, int64_t nb, int64_t n, int64_t m,
+                          double eps, int max_iters, double stop_thresh, float* out_P, double* out_cost, int32_t* out_iters, void* stream) {
+    return sinkhorn_device<float>(ws, a, b, M, nb, n, m, eps, max_iters, stop_thresh, out_P, out_cost, out_iters, (cudaStream_t)stream);
+}
+int pcu_b200_sinkhorn_f64(pcu_b200_workspace* ws, const double* a, const double* b, const double* M, int64_t nb, int64_t n, int64_t m,
+                          double eps, int max_iters, double stop_thresh, double* out_P, double* out_cost, int32_t* out_iters, void* stream) {
+    return sinkhorn_device<double>(ws, a, b, M, nb, n, m, eps, max_iters, stop_thresh, out_P, out_cost, out_iters, (cudaStream_t)stream);
 }
 
 int pcu_b200_morton_encode_i32(pcu_b200_workspace* ws, const int32_t* pts, int64_t n, uint64_t* out_codes, void* stream) {

@@ -21,7 +21,7 @@ def golden_names(prefix_exclude=("metrics_", "c1_metrics")):
 
 
 def knn_golden_names():
-    return [n for n in golden_names() if "metrics" not in n and not n.startswith("morton")]
+    return [n for n in golden_names() if "metrics" not in n and not n.startswith(("morton", "sinkhorn"))]
 
 
 def metric_golden_names():
