@@ -202,6 +202,24 @@ int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_
 int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                              double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
 
+/* ---- voxel-grid down-sampling --------------------------------------------
+ * Replaces downsample_point_cloud_voxel_grid_internal (src/sample_point_cloud.cpp:336-367, :163-244): every point
+ * goes to voxel int(floor((p - min_bound) / voxel_size)) per axis, computed in the cloud's precision exactly like the
+ * reference; every voxel with at least min_points_per_voxel points yields one output row, the mean of its points and
+ * of its rows of `attrib` ((n, attrib_cols) float or double, attrib_cols may be 0).  Exact: voxel assignment, the set
+ * of output voxels, their point counts (out_counts, may be NULL).  Different by construction and documented: the
+ * reference's row order is the iteration order of a std::unordered_map -- here rows follow the first point of each
+ * voxel in the input; the reference sums in the cloud's precision point by point -- here in fp64, so means agree to
+ * the rounding of its float sums.  Capacity of the outputs: n rows; out_rows: device int64.  DEVICE pointers. */
+int pcu_b200_voxel_downsample_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const void* attrib, int attrib_cols,
+                                  int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                  int min_points_per_voxel, float* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows,
+                                  void* stream);
+int pcu_b200_voxel_downsample_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const void* attrib, int attrib_cols,
+                                  int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                  int min_points_per_voxel, double* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows,
+                                  void* stream);
+
 /* ---- dense pairwise distances and Sinkhorn -------------------------------
  * Replace the numpy code of point_cloud_utils/_sinkhorn.py: pairwise_distances (:4-34), sinkhorn (:37-126) and the
  * cost (P * M).sum() of earth_movers_distance (:129-156).  DEVICE pointers, row-major dense arrays:

@@ -225,6 +225,60 @@ def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None
     return kept, normal[kept].astype(points.dtype)
 
 
+# ---- voxel-grid down-sampling (src/sample_point_cloud.cpp:163-244, point_cloud_utils/__init__.py:123-200) ----
+def voxel_indices(points, voxel_size, min_bound):
+    """:201-206 -- int(floor((p - min_bound) / voxel_size)) per axis, in the cloud's precision (the binding casts the
+    double arguments to the cloud's scalar type first, :346-354)."""
+    points = np.asarray(points)
+    t = points.dtype.type
+    size = np.array([t(v) for v in voxel_size], dtype=points.dtype)
+    lo = np.array([t(v) for v in min_bound], dtype=points.dtype)
+    return np.floor((points - lo) / size).astype(np.int32)
+
+
+def downsample_point_cloud_on_voxel_grid(voxel_size, points, *attribs, min_bound=None, max_bound=None, min_points_per_voxel=1,
+                                         return_counts=False):
+    """The wrapper (:123-200) and the accumulation (:163-244) restated with numpy: voxel membership exactly as the
+    reference computes it; sums point after point in the ARRAY's precision like AccumulatedPoint::AddPoint (:119-128) --
+    np.add.at accumulates in input order -- and the division of GetAveragePoint (:130-137).  The reference emits voxels
+    in std::unordered_map iteration order, which is unspecified: rows are returned here in the order of each voxel's
+    first point, and tests compare row SETS.  PARITY: the integer part (membership, counts, number of rows) is pinned by
+    construction of the index arithmetic; no golden vector of the reference exists for the means (its build needs
+    numpyeigen / Eigen, which are not in the tree)."""
+    points = np.asarray(points)
+    vs = np.array([voxel_size] * 3, dtype=np.float64) if np.isscalar(voxel_size) else np.array(voxel_size, dtype=np.float64)
+    if len(vs) != 3:
+        raise ValueError("Invalid voxel size must be a 3-tuple or a single float")
+    lo = np.min(points, axis=0) - vs * 0.5 if min_bound is None else np.array(min_bound)
+    hi = np.max(points, axis=0) + vs * 0.5 if max_bound is None else np.array(max_bound)
+    if np.any(hi - lo <= 0.0):
+        raise ValueError("Invalid min_bound and max_bound. max_bound must be greater than min_bound in all dimensions")
+    t = points.dtype.type
+    for a in range(3):
+        if t(vs[a]) <= 0:
+            raise ValueError("Voxel size is negative")
+        if t(vs[a]) * t(2147483647) < t(hi[a]) - t(lo[a]):
+            raise ValueError("Voxel size is too small")
+    idx = voxel_indices(points, vs, lo)
+    _, first, inverse, counts = np.unique(idx, axis=0, return_index=True, return_inverse=True, return_counts=True)
+    inverse = inverse.reshape(-1)
+    order = np.argsort(first, kind="stable")                 # voxels by their first point
+    rank = np.empty_like(order); rank[order] = np.arange(len(order))
+    group = rank[inverse]
+    counts = counts[order]
+    keep = counts >= min_points_per_voxel
+    outs = []
+    for arr in (points,) + tuple(np.asarray(a) for a in attribs):
+        flat = arr.reshape(arr.shape[0], -1)
+        acc = np.zeros((len(counts), flat.shape[1]), dtype=flat.dtype)
+        np.add.at(acc, group, flat)                           # sequential, in input order, in the array's precision
+        mean = acc / counts[:, None].astype(flat.dtype)
+        outs.append(mean[keep].reshape((int(keep.sum()),) + arr.shape[1:]))
+    if return_counts:
+        outs.append(counts[keep].astype(np.int32))
+    return tuple(outs) if len(outs) > 1 else outs[0]
+
+
 # ---- Morton codes (src/morton.cpp, src/common/morton_code.cpp) -----------------------------------------------
 _MORTON_PORT = os.path.join(_HERE, "libpcu_oracle_morton.so")
 _MORTON_REF = os.path.join(_HERE, "_ref", "libpcu_ref_morton.so")

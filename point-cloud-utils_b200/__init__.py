@@ -38,7 +38,8 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
 
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
            "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "morton_encode", "morton_decode", "morton_add",
-           "morton_subtract", "morton_knn", "pairwise_distances", "sinkhorn", "earth_movers_distance", "device_count",
+           "morton_subtract", "morton_knn", "pairwise_distances", "sinkhorn", "earth_movers_distance",
+           "downsample_point_cloud_on_voxel_grid", "device_count",
            "current_device", "launch_count"]
 
 _STATS_WORDS = 10  # sizeof(pcu_b200_nn_stats) / 8
@@ -509,6 +510,123 @@ def morton_knn(codes, qcodes, k, sort_dist=True, *, device=None):
 
 
 from ._sinkhorn import pairwise_distances, sinkhorn, earth_movers_distance  # noqa: E402  (N4: dense metrics)
+
+
+def _voxel_internal(points, attrib, voxel_size, min_bound, max_bound, min_points_per_voxel, device, return_counts=False):
+    """downsample_point_cloud_voxel_grid_internal (/root/reference/src/sample_point_cloud.cpp:336-367) on the GPU:
+    (mean points, mean attributes[, points per voxel]); numpy in -> numpy out, CUDA tensors in -> CUDA tensors out."""
+    torch = _torch()
+    is_np = isinstance(points, _np.ndarray)
+    if is_np:
+        if points.dtype not in (_np.float32, _np.float64):
+            raise ValueError("Invalid scalar type (%s) for argument 'v'. Expected one of ['float32', 'float64']." % points.dtype)
+        if attrib.dtype not in (_np.float32, _np.float64):
+            raise ValueError("Invalid scalar type (%s) for argument 'attrib'. Expected one of ['float32', 'float64']." % attrib.dtype)
+        dev = torch.device("cuda", _pcu_internal._current_device() if _dev(device) < 0 else _dev(device))
+        pts = torch.from_numpy(_np.ascontiguousarray(points)).to(dev)
+        att = torch.from_numpy(_np.ascontiguousarray(attrib)).to(dev) if attrib.size else None
+    else:
+        if points.dtype not in (torch.float32, torch.float64) or not points.is_cuda:
+            raise ValueError("points must be a float32 / float64 numpy array or CUDA tensor")
+        pts = points.detach().contiguous()
+        att = attrib.detach().contiguous() if attrib is not None and attrib.numel() else None
+        if att is not None and (att.dtype not in (torch.float32, torch.float64) or att.device != pts.device):
+            raise ValueError("attributes must be float32 / float64 tensors on the device of points")
+    if pts.dim() != 2 or pts.shape[1] != 3 or pts.shape[0] == 0:
+        raise ValueError("points must have shape (n, 3) with n > 0, got " + str(tuple(pts.shape)))
+    n = pts.shape[0]
+    cols = 0
+    if att is not None:
+        if att.shape[0] != n:                                                                   # :184-189
+            raise ValueError("Invalid number of attributes (%d). Must match number of input vertices (%d) or be 0." % (att.shape[0], n))
+        att = att.reshape(n, -1)
+        cols = att.shape[1]
+    out_p = torch.empty((n, 3), dtype=pts.dtype, device=pts.device)
+    out_a = torch.empty((n, cols), dtype=att.dtype, device=pts.device) if cols else None
+    counts = torch.empty(n, dtype=torch.int32, device=pts.device) if return_counts else None
+    rows = torch.empty(1, dtype=torch.int64, device=pts.device)
+    _pcu_internal._voxel_downsample_device(pts.dtype == torch.float64, pts.data_ptr(), n, att.data_ptr() if cols else 0, cols,
+                                           bool(cols and att.dtype == torch.float64), [float(v) for v in voxel_size],
+                                           [float(v) for v in min_bound], [float(v) for v in max_bound], int(min_points_per_voxel),
+                                           out_p.data_ptr(), out_a.data_ptr() if cols else 0, counts.data_ptr() if return_counts else 0,
+                                           rows.data_ptr(), pts.device.index or 0, _stream_of(pts))
+    m = int(rows.item())
+    out_p = out_p[:m]
+    out_a = out_a[:m] if cols else (torch.zeros((0, 0), dtype=pts.dtype, device=pts.device))
+    if is_np:
+        res = (out_p.cpu().numpy(), out_a.cpu().numpy().reshape((m,) + attrib.shape[1:]) if cols else _np.zeros([0, 0], dtype=attrib.dtype))
+        return res + ((counts[:m].cpu().numpy(),) if return_counts else ())
+    res = (out_p, out_a.reshape((m,) + tuple(attrib.shape[1:])) if cols else out_a)
+    return res + ((counts[:m],) if return_counts else ())
+
+
+def downsample_point_cloud_on_voxel_grid(voxel_size, points, *args, min_bound=None, max_bound=None, min_points_per_voxel=1,
+                                         device=None):
+    """
+    Downsample a point set to conform with a voxel grid by taking the average of points within each voxel.
+
+    Args:
+        voxel_size : a scalar representing the size of each voxel or a 3 tuple representing the size per axis of each voxel.
+        points: a [#v, 3]-shaped array of 3d points.
+        *args: Any additional arguments of shape [#v, *] are treated as attributes and will averaged into each voxel along
+               with the points
+        min_bound: a 3 tuple representing the minimum coordinate of the voxel grid or None to use the bounding box of the
+                input point cloud.
+        max_bound: a 3 tuple representing the maximum coordinate of the voxel grid or None to use the bounding box of the
+                input point cloud.
+        min_points_per_voxel: If a voxel contains fewer than this many points, then don't include the points in that voxel
+                            in the output.
+
+    Returns:
+        A tuple (v, attrib0, attrib1, ....) of downsampled points, and point attributes.
+        Attributes are returned in the same order they are passed in.
+        If no attributes are passed in, then this function simply returns vertices.
+
+    Mirrors /root/reference/point_cloud_utils/__init__.py:123-200 and /root/reference/src/sample_point_cloud.cpp:163-244.
+    Voxel membership, the set of output voxels and their sizes are the reference's exactly; rows come in the order of each
+    voxel's first input point (the reference's order is that of a std::unordered_map walk, i.e. unspecified); means are
+    accumulated in fp64 (the reference sums in the array's precision).
+    """
+    is_np = isinstance(points, _np.ndarray)
+    if not is_np and not _is_tensor(points):
+        raise ValueError("points must be a numpy array but got type " + str(type(points)))
+    if _np.isscalar(voxel_size):
+        voxel_size = _np.array([voxel_size] * 3)
+    else:
+        voxel_size = _np.array(voxel_size)
+        if len(voxel_size) != 3:
+            raise ValueError("Invalid voxel size must be a 3-tuple or a single float")
+    attribs = []
+    for i, arg in enumerate(args):
+        if type(arg) != type(points):
+            raise ValueError("Additional arguments after points and before keyword arguments must be numpy arrays")
+        if arg.shape[0] != points.shape[0]:
+            raise ValueError("Attribute " + str(i) + " must have same first dimension as number of points (" +
+                             str(tuple(points.shape)) + " but got attrib.shape = " + str(tuple(arg.shape)))
+        attribs.append(arg)
+    if is_np:
+        lo, hi = _np.min(points, axis=0), _np.max(points, axis=0)
+    else:
+        lo, hi = points.amin(dim=0).cpu().numpy(), points.amax(dim=0).cpu().numpy()
+    if min_bound is None:
+        min_bound = lo - voxel_size * 0.5
+    if max_bound is None:
+        max_bound = hi + voxel_size * 0.5
+    min_bound, max_bound = _np.array(min_bound), _np.array(max_bound)
+    if len(min_bound) != 3:
+        raise ValueError("min_bound must be a 3 tuple")
+    if len(max_bound) != 3:
+        raise ValueError("max_bound must be a 3 tuple")
+    if _np.any(max_bound - min_bound <= 0.0):
+        raise ValueError("Invalid min_bound and max_bound. max_bound must be greater than min_bound in all dimensions")
+    empty = _np.zeros([0, 0]) if is_np else None
+    ret_v, ret_a0 = _voxel_internal(points, attribs[0] if attribs else empty, voxel_size, min_bound, max_bound,
+                                    min_points_per_voxel, device)
+    ret = [ret_v, ret_a0] if (attribs and ret_a0 is not None) else [ret_v]
+    for i in range(1, len(attribs)):
+        _, ret_ai = _voxel_internal(points, attribs[i], voxel_size, min_bound, max_bound, min_points_per_voxel, device)
+        ret.append(ret_ai)
+    return tuple(ret) if len(ret) > 1 else ret_v
 
 
 def batched_chamfer_distance(x, y, max_points_per_leaf=10, *, device=None):

@@ -12,8 +12,10 @@
 // nothing is copied and nothing synchronises.
 #include <pybind11/pybind11.h>
 #include <pybind11/numpy.h>
+#include <pybind11/stl.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -522,6 +524,24 @@ py::array morton_knn(const py::array& codes_in, const py::array& qcodes_in, int 
     return idx;
 }
 
+// ---- voxel-grid down-sampling on device pointers (the Python layer owns the arrays) ----
+void voxel_downsample_device(bool is_f64, uintptr_t pts, int64_t n, uintptr_t attr, int attr_cols, bool attr_is_f64,
+                             std::array<double, 3> size, std::array<double, 3> lo, std::array<double, 3> hi, int min_points,
+                             uintptr_t out_pts, uintptr_t out_attr, uintptr_t out_counts, uintptr_t out_rows, int device, uintptr_t stream) {
+    Slot& slot = pool().get(device, stream);
+    int status;
+    {
+        CallScope scope(slot);
+        status = is_f64 ? pcu_b200_voxel_downsample_f64(slot.ws, (const double*)pts, n, (const void*)attr, attr_cols, attr_is_f64 ? 1 : 0,
+                                                        size.data(), lo.data(), hi.data(), min_points, (double*)out_pts, (void*)out_attr,
+                                                        (int32_t*)out_counts, (int64_t*)out_rows, (void*)stream)
+                        : pcu_b200_voxel_downsample_f32(slot.ws, (const float*)pts, n, (const void*)attr, attr_cols, attr_is_f64 ? 1 : 0,
+                                                        size.data(), lo.data(), hi.data(), min_points, (float*)out_pts, (void*)out_attr,
+                                                        (int32_t*)out_counts, (int64_t*)out_rows, (void*)stream);
+    }
+    check(status);
+}
+
 // ---- dense pairwise distances / Sinkhorn on device pointers (the Python layer owns the arrays) ----
 void pairwise_device(bool is_f64, uintptr_t a, uintptr_t b, int64_t nb, int64_t n, int64_t m, int d, int norm_kind, double p,
                      uintptr_t out, int device, uintptr_t stream) {
@@ -703,6 +723,7 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("device") = -1,
             "Indices of the kept points and their unit normals (plane fit to the k nearest neighbours of each point).");
     mod.def("_normals_knn_device", &normals_knn_device);
+    mod.def("_voxel_downsample_device", &voxel_downsample_device);
     mod.def("_pairwise_device", &pairwise_device);
     mod.def("_sinkhorn_device", &sinkhorn_device);
     mod.def("morton_encode", &morton_encode, py::arg("pts"), py::arg("num_threads") = -1, py::arg("device") = -1,

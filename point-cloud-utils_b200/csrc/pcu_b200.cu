@@ -27,6 +27,7 @@
 #include "normals.cuh"
 #include "morton.cuh"
 #include "sinkhorn.cuh"
+#include "voxel.cuh"
 
 using namespace pcu;
 
@@ -817,6 +818,62 @@ int morton_knn_device(pcu_b200_workspace* ws, const unsigned long long* codes, l
     return PCU_B200_OK;
 }
 
+// ---- voxel-grid down-sampling -----------------------------------------------------------
+template <typename T, typename A>
+int voxel_downsample_device(pcu_b200_workspace* ws, const T* pts, long long n, const A* attr, int attr_cols, const double size[3],
+                            const double min_bound[3], const double max_bound[3], int min_points, T* out_pts, A* out_attr,
+                            int* out_counts, long long* out_rows, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!pts || n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "points must be a non-empty (n, 3) array");
+    if (n >= 0x7fffffffLL) return fail(PCU_B200_INVALID_ARGUMENT, "point cloud too large (%lld rows)", n);
+    if (!out_pts || !out_rows || attr_cols < 0 || (attr_cols > 0 && (!attr || !out_attr)))
+        return fail(PCU_B200_INVALID_ARGUMENT, "null pointer");
+    VoxelGrid<T> g;
+    for (int a = 0; a < 3; ++a) {   // src/sample_point_cloud.cpp:175-182, in the cloud's precision like the reference's casts (:346-354)
+        g.size[a] = (T)size[a];
+        g.min_bound[a] = (T)min_bound[a];
+        if (g.size[a] <= (T)0) return fail(PCU_B200_INVALID_ARGUMENT, "Voxel size is negative");
+        if (g.size[a] * (T)2147483647 < (T)max_bound[a] - g.min_bound[a]) return fail(PCU_B200_INVALID_ARGUMENT, "Voxel size is too small");
+    }
+    PCU_ON_DEVICE(ws);
+    const long long nblocks = (n + kThreads - 1) / kThreads;
+    unsigned slots = 64;
+    while ((long long)slots < 2 * n) slots <<= 1;     // load factor <= 1/2
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, int*& table, VoxelAcc*& acc, int*& slot_of, double*& attr_sum, unsigned char*& keep, unsigned*& counts) {
+        table = cv.take<int>(slots);
+        acc = cv.take<VoxelAcc>(slots);
+        slot_of = cv.take<int>((size_t)n);
+        attr_sum = cv.take<double>((size_t)slots * (attr_cols > 0 ? attr_cols : 0) + 1);
+        keep = cv.take<unsigned char>((size_t)n);
+        counts = cv.take<unsigned>((size_t)nblocks);
+    };
+    int *table, *slot_of; VoxelAcc* acc; double* attr_sum; unsigned char* keep; unsigned* counts;
+    carve(measure, table, acc, slot_of, attr_sum, keep, counts);
+    PCU_TRY(ensure_arena(ws, measure.off, stream));
+    Carver cv(ws->arena);
+    carve(cv, table, acc, slot_of, attr_sum, keep, counts);
+    PCU_LAUNCH(voxel_init_kernel, (slots + kThreads - 1) / kThreads, kThreads, stream, table, acc, slots);
+    if (attr_cols > 0) PCU_CUDA(cudaMemsetAsync(attr_sum, 0, sizeof(double) * (size_t)slots * attr_cols, stream));
+    PCU_LAUNCH((voxel_insert_kernel<T, A>), (unsigned)nblocks, kThreads, stream, pts, n, g, table, slots, acc, slot_of, attr, attr_cols, attr_sum);
+    PCU_LAUNCH(voxel_flag_kernel, (unsigned)nblocks, kThreads, stream, slot_of, acc, n, min_points, keep);
+    PCU_LAUNCH(keep_count_kernel, (unsigned)nblocks, kThreads, stream, keep, n, counts);
+    PCU_LAUNCH(keep_offsets_kernel, 1, 1024, stream, counts, nblocks, out_rows);
+    PCU_LAUNCH((voxel_emit_kernel<T, A>), (unsigned)nblocks, kThreads, stream, keep, n, counts, slot_of, acc, attr_sum, attr_cols, out_pts, out_attr, out_counts);
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int voxel_downsample_dispatch(pcu_b200_workspace* ws, const T* pts, long long n, const void* attr, int attr_cols, int attr_is_f64,
+                              const double size[3], const double min_bound[3], const double max_bound[3], int min_points, T* out_pts,
+                              void* out_attr, int* out_counts, long long* out_rows, cudaStream_t stream) {
+    if (attr_is_f64)
+        return voxel_downsample_device<T, double>(ws, pts, n, (const double*)attr, attr_cols, size, min_bound, max_bound, min_points,
+                                                  out_pts, (double*)out_attr, out_counts, out_rows, stream);
+    return voxel_downsample_device<T, float>(ws, pts, n, (const float*)attr, attr_cols, size, min_bound, max_bound, min_points, out_pts,
+                                             (float*)out_attr, out_counts, out_rows, stream);
+}
+
 // ---- dense pairwise distances, Sinkhorn ------------------------------------------------
 template <typename T>
 int pairwise_device(pcu_b200_workspace* ws, const T* a, const T* b, long long nb, long long n, long long m, int d, int norm_kind,
@@ -1128,6 +1185,21 @@ int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, cons
 int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
                          pcu_b200_nn_stats* out_stats, double* out_value, void* stream) {
     return stats_device<double>(ws, x, n, y, m, true, out_stats, out_value, (cudaStream_t)stream);
+}
+
+int pcu_b200_voxel_downsample_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const void* attrib, int attrib_cols,
+                                  int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                  int min_points_per_voxel, float* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows,
+                                  void* stream) {
+    return voxel_downsample_dispatch<float>(ws, points, n, attrib, attrib_cols, attrib_is_f64, voxel_size, min_bound, max_bound,
+                                            min_points_per_voxel, out_points, out_attrib, out_counts, (long long*)out_rows, (cudaStream_t)stream);
+}
+int pcu_b200_voxel_downsample_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const void* attrib, int attrib_cols,
+                                  int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                  int min_points_per_voxel, double* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows,
+                                  void* stream) {
+    return voxel_downsample_dispatch<double>(ws, points, n, attrib, attrib_cols, attrib_is_f64, voxel_size, min_bound, max_bound,
+                                             min_points_per_voxel, out_points, out_attrib, out_counts, (long long*)out_rows, (cudaStream_t)stream);
 }
 
 int pcu_b200_pairwise_distances_f32(pcu_b200_workspace* ws, const float* a, const float* b, int64_t nb, int64_t n, int64_t m, int d,
