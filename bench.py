@@ -234,6 +234,30 @@ def run_reference(args, wl_key):
 
 
 # ------------------------------------------------------------------------------------------------
+def gpu_local_cpus(gpu_index):
+    """CPUs of the NUMA node the GPU hangs off (NVML's ideal CPU affinity), or None when it cannot be told."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        h = None
+        try:   # CUDA and NVML may enumerate differently (CUDA_VISIBLE_DEVICES): go through the UUID when torch has it
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        return cpus or None
+    except Exception:
+        return None
+
+
 class Bench:
     """One rank of the GPU arm."""
 
@@ -252,11 +276,22 @@ class Bench:
             raise SystemExit("bench.py needs a B200: the product has no CPU path")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        # Host buffers are first touched (and pinned) by this process: keep it on the CPUs next to its GPU, or the
+        # kernel may start it on the other socket and every H2D crosses the socket interconnect (measured on these
+        # boxes: 24 MB in 0.43 ms local, up to 1.0 ms remote, varying from process to process).  The CPU baseline
+        # leg gets all CPUs back (restore_affinity).
+        self.all_cpus = os.sched_getaffinity(0)
+        self.numa_cpus = gpu_local_cpus(self.local)
+        if self.numa_cpus:
+            os.sched_setaffinity(0, self.numa_cpus)
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
         self.stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.exchange = self.bmod.ScalarSumExchange(self.dev)
+
+    def restore_affinity(self):
+        os.sched_setaffinity(0, self.all_cpus)
 
     def barrier(self):
         if self.world > 1:
@@ -365,9 +400,22 @@ class Bench:
         xp = self.torch.from_numpy(xh).pin_memory()
         yp = self.torch.from_numpy(yh).pin_memory()
         pinned_s = timed(xp.numpy(), yp.numpy(), steps)
+        # where the time of such a call goes: the library's own CUDA events on the host path's streams (a few extra
+        # calls, outside the timed loop); "h2d" = from the call's start to the first kernel, "d2h" = results + sync
+        internal = pcu._pcu_internal
+        stages = {}
+        try:
+            internal._set_profiling(self.local, None, True)
+            for _ in range(5):
+                host_step(xp.numpy(), yp.numpy())
+                for key, val in internal._last_profile(self.local, None).items():
+                    stages[key] = stages.get(key, 0.0) + val / 5
+            internal._set_profiling(self.local, None, False)
+        except Exception:
+            stages = {}
         del xp, yp
         pageable_s = timed(np.array(xh, copy=True), np.array(yh, copy=True), max(3, steps // 4))
-        return pinned_s, pageable_s
+        return pinned_s, pageable_s, {kk: round(v, 5) for kk, v in stages.items()}
 
 
 def main():
@@ -419,14 +467,43 @@ def main():
 
     # ---- end-to-end arm: numpy-facing API, host buffers, copies inside the timed region ----------------
     e2e_steps = args.steps if wl_key in ("c3", "c2") else min(args.steps, 10)
-    pinned_s, pageable_s = B.host_arm(wl_key, xh, yh, e2e_steps, res["units"])
+    pinned_s, pageable_s, host_stages = B.host_arm(wl_key, xh, yh, e2e_steps, res["units"])
     h2d = int(xh.nbytes + yh.nbytes)
     d2h = 2 * 80 + 4 if wl_key == "c3" else (4 * local_batch + 8 if wl_key == "c5" else int(n * k * 12 + 8))
     e2e = {"value": res["units"] / pinned_s, "unit": unit_name(wl_key), "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": pinned_s * 1e3, "steps": e2e_steps,
            "api": E2E_API[wl_key] + " (pinned host buffers; every rank on its own GPU)",
+           "stage_ms": host_stages,
            "pageable": {"value": res["units"] / pageable_s, "ms_per_step": pageable_s * 1e3,
                         "note": "same call on ordinary (pageable) numpy arrays"}}
+    # ---- the same step against a PREPARED target (the fixed cloud of a loss loop binned once) -----------
+    prepared = None
+    if wl_key == "c3":
+        reps = min(args.steps, 30)
+        target = pcu.prepare_cloud(yd)
+        for _ in range(3):
+            pcu.chamfer_distance(xd, target)
+        B.barrier()
+        a0 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        a1 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        for s in range(reps):
+            B.flush.fill_(s & 0xff)
+            a0[s].record(); pcu.chamfer_distance(xd, target); a1[s].record()
+        B.barrier()
+        dev_ms = B.reduce_max(sum(a.elapsed_time(b) for a, b in zip(a0, a1))) / reps
+        xp = torch.from_numpy(xh).pin_memory()
+        for _ in range(3):
+            float(pcu.chamfer_distance(xp.numpy(), target))
+        B.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            float(pcu.chamfer_distance(xp.numpy(), target))
+        host_s = B.reduce_max(time.perf_counter() - t0) / reps
+        prepared = {"note": "chamfer_distance(x, pcu.prepare_cloud(y)): y binned once outside the timed region, x as in the headline",
+                    "value": res["units"] / (dev_ms * 1e-3), "ms_per_step": dev_ms,
+                    "e2e": {"value": res["units"] / host_s, "ms_per_step": host_s * 1e3, "h2d_bytes_per_step": int(xh.nbytes)}}
+        target.close()
+        del xp
     del xd, yd
 
     # ---- C5 strong scaling beside the headline (BASELINE configs[4]) -----------------------------------
@@ -447,6 +524,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------
     cpu = None
+    B.restore_affinity()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
@@ -494,6 +572,8 @@ def main():
                                 "stream (overlaps the next step's binning)") if world > 1 else "1 GPU",
                 "l2": "inputs (24 MB) < L2: a 256 MiB buffer is overwritten before every timed step, outside the interval",
                 "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
+                "host_placement": ("process bound to the %d CPUs next to its GPU (NVML affinity) while it allocates and copies "
+                                   "host buffers; all CPUs again for the CPU baseline" % len(B.numa_cpus)) if B.numa_cpus else "no CPU binding",
                 "ratio_note": "N GPUs process N pairs per step; the reference arm is one CPU process: a throughput ratio",
             },
             "clocks": res["clocks"],
@@ -504,6 +584,8 @@ def main():
         }
         if c5 is not None:
             line["c5_strong"] = c5
+        if prepared is not None:
+            line["prepared_target"] = prepared
         print(json.dumps(line), flush=True)
     if world > 1:
         B.dist.barrier()

@@ -181,6 +181,44 @@ int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, cons
 int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
                          pcu_b200_nn_stats* out_stats, double* out_value, void* stream);
 
+/* ---- prepared clouds: bin a fixed cloud ONCE, use it as one side of many calls ---------------
+ * The reference rebuilds its kd-tree on every call -- three times per direction (src/point_cloud_distance.cpp:41-42,
+ * nanoflann.hpp:1357, 2288) -- even when one cloud never changes (a loss against a fixed target evaluated every
+ * iteration).  pcu_b200_cloud_prepare_* copies the points into a private device block and bins them there; the
+ * *_prepared_* calls take the handle as the SECOND cloud (y / target / dataset), bin only the first cloud and run
+ * the same fused sweeps: results are those of the unprepared calls bit for bit.  Host variants copy only the first
+ * cloud over PCIe.  A handle may serve calls on several workspaces / streams of its device at once (it is
+ * read-only after preparation, apart from an occupancy pyramid every user would write identically).
+ * pcu_b200_cloud_destroy synchronises the device. */
+typedef struct pcu_b200_cloud pcu_b200_cloud;
+int pcu_b200_cloud_prepare_f32(pcu_b200_workspace* ws, const float* points, int64_t n, pcu_b200_cloud** out_cloud, void* stream);
+int pcu_b200_cloud_prepare_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud, void* stream);
+int pcu_b200_cloud_prepare_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, pcu_b200_cloud** out_cloud);
+int pcu_b200_cloud_prepare_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud);
+int pcu_b200_cloud_destroy(pcu_b200_cloud* cloud);
+int64_t pcu_b200_cloud_size(const pcu_b200_cloud* cloud);
+/* DEVICE pointer to the handle's private (n, 3) copy of the points (what pcu_b200_resolve_witness_* wants as the
+ * prepared side's array). */
+const void* pcu_b200_cloud_points(const pcu_b200_cloud* cloud);
+/* out_stats: TWO records ([0] = x -> y, [1] = y -> x) as for pcu_b200_chamfer_*; out_value may be NULL */
+int pcu_b200_chamfer_prepared_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const pcu_b200_cloud* y,
+                                  pcu_b200_nn_stats* out_stats, float* out_value, void* stream);
+int pcu_b200_chamfer_prepared_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const pcu_b200_cloud* y,
+                                  pcu_b200_nn_stats* out_stats, double* out_value, void* stream);
+/* out_stats: ONE record (query -> dataset) as for pcu_b200_nn_stats_* */
+int pcu_b200_nn_stats_prepared_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const pcu_b200_cloud* dataset,
+                                   pcu_b200_nn_stats* out_stats, void* stream);
+int pcu_b200_nn_stats_prepared_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const pcu_b200_cloud* dataset,
+                                   pcu_b200_nn_stats* out_stats, void* stream);
+int pcu_b200_chamfer_prepared_host_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const pcu_b200_cloud* y,
+                                       pcu_b200_nn_stats* out_stats, float* out_value);
+int pcu_b200_chamfer_prepared_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const pcu_b200_cloud* y,
+                                       pcu_b200_nn_stats* out_stats, double* out_value);
+int pcu_b200_nn_stats_prepared_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const pcu_b200_cloud* dataset,
+                                        pcu_b200_nn_stats* out_stats);
+int pcu_b200_nn_stats_prepared_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const pcu_b200_cloud* dataset,
+                                        pcu_b200_nn_stats* out_stats);
+
 /* ---- batched Chamfer over independent pairs, DEVICE pointers -------------------------------
  * x : (B, n, 3), y : (B, m, 3) dense; out_per_pair : (B) scalars of the input precision;
  * out_sum (may be NULL): device double = sum of the B per-pair values (the quantity a multi-GPU

@@ -39,7 +39,7 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
            "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "morton_encode", "morton_decode", "morton_add",
            "morton_subtract", "morton_knn", "pairwise_distances", "sinkhorn", "earth_movers_distance",
-           "downsample_point_cloud_on_voxel_grid", "device_count",
+           "downsample_point_cloud_on_voxel_grid", "prepare_cloud", "PreparedCloud", "device_count",
            "current_device", "launch_count"]
 
 _STATS_WORDS = 10  # sizeof(pcu_b200_nn_stats) / 8
@@ -173,6 +173,93 @@ def _metric_value(max_sq, squared, dtype):
 
 
 # ---------------------------------------------------------------------------------------------
+class PreparedCloud:
+    """A point cloud binned once on the GPU (``prepare_cloud``), to be passed as the SECOND argument -- y / target --
+    of ``chamfer_distance``, ``hausdorff_distance`` and ``one_sided_hausdorff_distance`` as often as wanted: every such
+    call bins only its first argument (and, for numpy inputs, copies only that one over PCIe).  The reference rebuilds
+    its kd-tree three times per direction on every call (/root/reference/src/point_cloud_distance.cpp:41-42).
+    Results are those of the plain calls.  Holds a private copy of the points; ``close()`` (or garbage collection)
+    frees the device memory."""
+
+    def __init__(self, handle, n, is_f64, device_index, on_device):
+        self._handle, self.shape, self._f64, self.device_index, self._on_device = handle, (int(n), 3), bool(is_f64), int(device_index), on_device
+
+    @property
+    def dtype(self):
+        return _np.dtype(_np.float64 if self._f64 else _np.float32)
+
+    def close(self):
+        if self._handle:
+            _pcu_internal._cloud_destroy(self._handle)
+            self._handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown
+            pass
+
+    def __len__(self):
+        return self.shape[0]
+
+
+def prepare_cloud(points, *, device=None):
+    """Bin ``points`` ((n, 3) float32 / float64 numpy array or CUDA tensor) once; returns a ``PreparedCloud``."""
+    if _is_tensor(points):
+        torch = _torch()
+        if points.dtype not in (torch.float32, torch.float64) or points.dim() != 2 or points.shape[1] != 3 or points.shape[0] == 0:
+            raise ValueError("points must be a float32 / float64 tensor of shape (n, 3) with n > 0")
+        if not points.is_cuda:
+            return prepare_cloud(points.detach().numpy(), device=device)
+        _same_device(points, device)
+        p = points.detach().contiguous()
+        dev = p.device.index or 0
+        h = _pcu_internal._cloud_prepare_device(p.dtype == torch.float64, p.data_ptr(), p.shape[0], dev, _stream_of(p))
+        return PreparedCloud(h, p.shape[0], p.dtype == torch.float64, dev, True)
+    pts = _np.asarray(points)
+    d = _dev(device)
+    h = _pcu_internal._cloud_prepare(pts, d)
+    return PreparedCloud(h, pts.shape[0], pts.dtype == _np.float64, _pcu_internal._current_device() if d < 0 else d, False)
+
+
+def _prepared_resolved(buf, which, xs, cloud, leaf):
+    """Record `which` of a prepared-cloud call on device tensors, its Hausdorff witness replayed when tie order decided it."""
+    st = _stats_from_tensor(buf, which)
+    if st["witness_tied"]:
+        yp, m = _pcu_internal._cloud_points(cloud._handle), cloud.shape[0]
+        q, n, d, k = (xs.data_ptr(), xs.shape[0], yp, m) if which == 0 else (yp, m, xs.data_ptr(), xs.shape[0])
+        _pcu_internal._resolve_witness_device(cloud._f64, q, n, d, k, buf.data_ptr() + 8 * _STATS_WORDS * which, int(leaf),
+                                              cloud.device_index, _stream_of(xs))
+        st = _stats_from_tensor(buf, which)
+    return st
+
+
+def _prepared_stats(x, cloud, both, leaf, device):
+    """(where, dtype, value, payload) like _both_stats, for a PreparedCloud second argument."""
+    if not cloud._handle:
+        raise ValueError("the PreparedCloud has been closed")
+    if _is_tensor(x) and x.is_cuda:
+        torch = _torch()
+        if x.dtype != (torch.float64 if cloud._f64 else torch.float32) or x.dim() != 2 or x.shape[1] != 3 or x.shape[0] == 0:
+            raise ValueError("the first argument must be an (n, 3) tensor of the prepared cloud's dtype (%s)" % cloud.dtype)
+        if (x.device.index or 0) != cloud.device_index:
+            raise ValueError("the points live on %s, the prepared cloud on cuda:%d" % (x.device, cloud.device_index))
+        xs = x.detach().contiguous()
+        buf = torch.empty(2 * _STATS_WORDS, dtype=torch.int64, device=xs.device)
+        val = torch.empty((), dtype=xs.dtype, device=xs.device)
+        _pcu_internal._stats_prepared_device(cloud._f64, both, xs.data_ptr(), xs.shape[0], cloud._handle, buf.data_ptr(),
+                                             val.data_ptr() if both else 0, int(leaf), cloud.device_index, _stream_of(xs))
+        return "cuda", xs.dtype, val, (buf, xs)
+    if _is_tensor(x):
+        x = x.detach().numpy()
+    d = _dev(device)
+    if d >= 0 and d != cloud.device_index:
+        raise ValueError("device=%r contradicts the prepared cloud, which lives on cuda:%d" % (device, cloud.device_index))
+    res = _pcu_internal._stats_prepared(_np.asarray(x), cloud._handle, cloud._f64, both, int(leaf), cloud.device_index)
+    return "host", cloud.dtype.type, res[0], res[1:]
+
+
+# ---------------------------------------------------------------------------------------------
 def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False, max_points_per_leaf=10,
                         num_threads=-1, *, device=None):
     """
@@ -243,6 +330,15 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
     Mirrors /root/reference/src/point_cloud_distance.cpp:186-234.  One fused sweep: no per-point distance array
     is written; the maximum, its first row and that row's neighbour are reduced inside the search kernel.
     """
+    if isinstance(target, PreparedCloud):
+        where, dtype, _, payload = _prepared_stats(source, target, False, max_points_per_leaf, device)
+        if where == "cuda":
+            st = _prepared_resolved(payload[0], 0, payload[1], target, max_points_per_leaf)
+            np_t = _np.float32 if dtype == _torch().float32 else _np.float64
+        else:
+            st, np_t = payload[0], dtype
+        value = _metric_value(st["max_sq_dist"], squared_distances, np_t)
+        return (value, st["argmax_query"], st["argmax_data"]) if return_index else value
     if _is_tensor(source) or _is_tensor(target):
         if not _is_tensor(source):
             raise ValueError("source and target must both be torch tensors or both be numpy arrays")
@@ -265,6 +361,11 @@ def one_sided_hausdorff_distance(source, target, return_index=True, squared_dist
 
 def _both_stats(x, y, max_points_per_leaf, device=None):
     """(dtype, chamfer value, stats x->y, stats y->x) from ONE fused bidirectional launch sequence."""
+    if isinstance(y, PreparedCloud):
+        where, dtype, val, payload = _prepared_stats(x, y, True, max_points_per_leaf, device)
+        if where == "cuda":
+            return ("cuda-prepared", dtype, val, payload + (y,))
+        return ("host", dtype, val, payload)
     if _is_tensor(x) or _is_tensor(y):
         if not _is_tensor(x):
             raise ValueError("x and y must both be torch tensors or both be numpy arrays")
@@ -300,7 +401,12 @@ def hausdorff_distance(x, y, return_index=False, squared_distances=False, max_po
     both directions come from one fused launch sequence over the two binned clouds.
     """
     where, dtype, _, st = _both_stats(x, y, max_points_per_leaf, device)
-    if where == "cuda":
+    if where == "cuda-prepared":
+        buf, xs, cloud = st
+        sxy = _prepared_resolved(buf, 0, xs, cloud, max_points_per_leaf)
+        syx = _prepared_resolved(buf, 1, xs, cloud, max_points_per_leaf)
+        np_t = _np.float32 if dtype == _torch().float32 else _np.float64
+    elif where == "cuda":
         buf, xs, ys = st
         sxy = _resolved_stats(buf, 0, xs, ys, max_points_per_leaf)
         syx = _resolved_stats(buf, 1, ys, xs, max_points_per_leaf)
@@ -342,6 +448,8 @@ def chamfer_distance(x, y, return_index=False, p_norm=2, max_points_per_leaf=10,
     if p_norm == 2 and not return_index:
         where, _, val, _ = _both_stats(x, y, max_points_per_leaf, device)
         return val
+    if isinstance(y, PreparedCloud):
+        raise ValueError("a PreparedCloud serves the fused metrics (p_norm = 2, return_index = False); pass the array for the others")
     dists_x_to_y, corrs_x_to_y = k_nearest_neighbors(x, y, k=1, squared_distances=False,
                                                      max_points_per_leaf=max_points_per_leaf, device=device)
     dists_y_to_x, corrs_y_to_x = k_nearest_neighbors(y, x, k=1, squared_distances=False,

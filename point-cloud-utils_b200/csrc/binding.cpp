@@ -524,6 +524,101 @@ py::array morton_knn(const py::array& codes_in, const py::array& qcodes_in, int 
     return idx;
 }
 
+// ---- prepared clouds (handles travel as integers; point-cloud-utils_b200/__init__.py wraps them in PreparedCloud) ----
+uintptr_t cloud_prepare_numpy(const py::array& pts_in, int device) {
+    const bool f32 = pts_in.dtype().is(py::dtype::of<float>()), f64 = pts_in.dtype().is(py::dtype::of<double>());
+    if (!f32 && !f64)
+        throw py::value_error("Invalid scalar type (" + std::string(py::str(pts_in.dtype())) + ") for argument 'points'. Expected one of ['float32', 'float64'].");
+    if (pts_in.ndim() != 2 || pts_in.shape(1) != 3 || pts_in.shape(0) == 0)
+        throw py::value_error("Only 3D inputs are supported: points must have shape (n, 3) with n > 0.");
+    const int dev = current_device_or_default(device);
+    Slot& slot = pool().get(dev, kHostKey);
+    pcu_b200_cloud* cloud = nullptr;
+    int status;
+    if (f32) {
+        auto p = dense<float>(pts_in);
+        CallScope scope(slot);
+        status = pcu_b200_cloud_prepare_host_f32(slot.ws, p.data(), p.shape(0), &cloud);
+    } else {
+        auto p = dense<double>(pts_in);
+        CallScope scope(slot);
+        status = pcu_b200_cloud_prepare_host_f64(slot.ws, p.data(), p.shape(0), &cloud);
+    }
+    check(status);
+    return (uintptr_t)cloud;
+}
+uintptr_t cloud_prepare_device(bool is_f64, uintptr_t pts, int64_t n, int device, uintptr_t stream) {
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_cloud* cloud = nullptr;
+    int status;
+    {
+        CallScope scope(slot);
+        status = is_f64 ? pcu_b200_cloud_prepare_f64(slot.ws, (const double*)pts, n, &cloud, (void*)stream)
+                        : pcu_b200_cloud_prepare_f32(slot.ws, (const float*)pts, n, &cloud, (void*)stream);
+    }
+    check(status);
+    return (uintptr_t)cloud;
+}
+void cloud_destroy(uintptr_t cloud) {
+    py::gil_scoped_release nogil;
+    pcu_b200_cloud_destroy((pcu_b200_cloud*)cloud);
+}
+// fused sweep(s) of numpy points against a prepared cloud: (value or None, stats[, stats])
+py::tuple stats_prepared_numpy(const py::array& x_in, uintptr_t cloud, bool cloud_is_f64, bool both, int max_points_per_leaf, int device) {
+    const bool f32 = x_in.dtype().is(py::dtype::of<float>()), f64 = x_in.dtype().is(py::dtype::of<double>());
+    if ((!f32 && !f64) || f64 != cloud_is_f64)
+        throw py::value_error("Invalid scalar type (" + std::string(py::str(x_in.dtype())) + "): expected the prepared cloud's " +
+                              (cloud_is_f64 ? "float64" : "float32") + ".");
+    if (x_in.ndim() != 2 || x_in.shape(1) != 3)
+        throw py::value_error("Only 3D inputs are supported: points must have shape (n, 3).");
+    if (x_in.shape(0) == 0) throw py::value_error("Invalid input set with zero elements: points must have shape (n, 3) with n > 0.");
+    const int dev = current_device_or_default(device);
+    Slot& slot = pool().get(dev, kHostKey);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
+    pcu_b200_nn_stats st[2] = {};
+    int status;
+    py::object value = py::none();
+    auto* y = (const pcu_b200_cloud*)cloud;
+    if (f32) {
+        auto x = dense<float>(x_in);
+        float v = 0.f;
+        { CallScope scope(slot); pcu_b200_workspace_set_options(slot.ws, &opts);
+          status = both ? pcu_b200_chamfer_prepared_host_f32(slot.ws, x.data(), x.shape(0), y, st, &v)
+                        : pcu_b200_nn_stats_prepared_host_f32(slot.ws, x.data(), x.shape(0), y, st); }
+        check(status);
+        if (both) value = py::module_::import("numpy").attr("float32")(v);
+    } else {
+        auto x = dense<double>(x_in);
+        double v = 0.0;
+        { CallScope scope(slot); pcu_b200_workspace_set_options(slot.ws, &opts);
+          status = both ? pcu_b200_chamfer_prepared_host_f64(slot.ws, x.data(), x.shape(0), y, st, &v)
+                        : pcu_b200_nn_stats_prepared_host_f64(slot.ws, x.data(), x.shape(0), y, st); }
+        check(status);
+        if (both) value = py::module_::import("numpy").attr("float64")(v);
+    }
+    if (both) return py::make_tuple(value, stats_to_dict(st[0]), stats_to_dict(st[1]));
+    return py::make_tuple(value, stats_to_dict(st[0]));
+}
+void stats_prepared_device(bool is_f64, bool both, uintptr_t a, int64_t n, uintptr_t cloud, uintptr_t out_stats, uintptr_t out_value,
+                           int max_points_per_leaf, int device, uintptr_t stream) {
+    Slot& slot = pool().get(device, stream);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
+    int status;
+    {
+        CallScope scope(slot);
+        pcu_b200_workspace_set_options(slot.ws, &opts);
+        auto* st = (pcu_b200_nn_stats*)out_stats;
+        auto* y = (const pcu_b200_cloud*)cloud;
+        if (both)
+            status = is_f64 ? pcu_b200_chamfer_prepared_f64(slot.ws, (const double*)a, n, y, st, (double*)out_value, (void*)stream)
+                            : pcu_b200_chamfer_prepared_f32(slot.ws, (const float*)a, n, y, st, (float*)out_value, (void*)stream);
+        else
+            status = is_f64 ? pcu_b200_nn_stats_prepared_f64(slot.ws, (const double*)a, n, y, st, (void*)stream)
+                            : pcu_b200_nn_stats_prepared_f32(slot.ws, (const float*)a, n, y, st, (void*)stream);
+    }
+    check(status);
+}
+
 // ---- voxel-grid down-sampling on device pointers (the Python layer owns the arrays) ----
 void voxel_downsample_device(bool is_f64, uintptr_t pts, int64_t n, uintptr_t attr, int attr_cols, bool attr_is_f64,
                              std::array<double, 3> size, std::array<double, 3> lo, std::array<double, 3> hi, int min_points,
@@ -723,6 +818,12 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("device") = -1,
             "Indices of the kept points and their unit normals (plane fit to the k nearest neighbours of each point).");
     mod.def("_normals_knn_device", &normals_knn_device);
+    mod.def("_cloud_prepare", &cloud_prepare_numpy, py::arg("points"), py::arg("device") = -1);
+    mod.def("_cloud_prepare_device", &cloud_prepare_device);
+    mod.def("_cloud_destroy", &cloud_destroy);
+    mod.def("_cloud_points", [](uintptr_t cloud) { return (uintptr_t)pcu_b200_cloud_points((const pcu_b200_cloud*)cloud); });
+    mod.def("_stats_prepared", &stats_prepared_numpy);
+    mod.def("_stats_prepared_device", &stats_prepared_device);
     mod.def("_voxel_downsample_device", &voxel_downsample_device);
     mod.def("_pairwise_device", &pairwise_device);
     mod.def("_sinkhorn_device", &sinkhorn_device);

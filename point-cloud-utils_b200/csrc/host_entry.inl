@@ -54,8 +54,9 @@ struct StatsResult {
 
 template <typename T>
 int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
-               pcu_b200_nn_stats* out_stats, T* out_value) {
+               pcu_b200_nn_stats* out_stats, T* out_value, const pcu_b200_cloud* prepared = nullptr) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (prepared != nullptr) { b = a; m = 1; }   // placeholders for the checks and the staging layout: nothing of b is copied
     PCU_TRY(check_cloud_args<T>(a, n, b, m));
     if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     PCU_ON_DEVICE(ws);
@@ -78,9 +79,9 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     mark(ws, 9, st);
     PCU_CUDA(cudaMemcpyAsync(da, a, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, ws->copy_stream));
     PCU_CUDA(cudaEventRecord(ws->arrived[0], ws->copy_stream));
-    PCU_CUDA(cudaMemcpyAsync(db, b, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, ws->copy_stream));
+    if (prepared == nullptr) PCU_CUDA(cudaMemcpyAsync(db, b, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, ws->copy_stream));
     PCU_CUDA(cudaEventRecord(ws->arrived[1], ws->copy_stream));
-    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, dr->stats, both ? &dr->value : nullptr, st, ws->arrived));
+    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, dr->stats, both ? &dr->value : nullptr, st, ws->arrived, prepared));
     StatsResult<T>* hr = reinterpret_cast<StatsResult<T>*>(ws->host_slot);
     auto fetch = [&]() -> int {
         PCU_CUDA(cudaMemcpyAsync(hr, dr, sizeof(StatsResult<T>), cudaMemcpyDeviceToHost, st));
@@ -93,9 +94,11 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     if (ws->opts.disable_tie_replay != 1) {
         for (int s = 0; s < (both ? 2 : 1); ++s) {
             if (!hr->stats[s].witness_tied) continue;
-            const T* qs = s == 0 ? da : db;
-            const T* dsrc = s == 0 ? db : da;
-            PCU_TRY(resolve_witness_device<T>(ws, qs, s == 0 ? n : m, dsrc, s == 0 ? m : n, dr->stats + s, st));
+            const T* second = prepared ? (const T*)prepared->raw : db;
+            const long long msecond = prepared ? prepared->n : m;
+            const T* qs = s == 0 ? da : second;
+            const T* dsrc = s == 0 ? second : da;
+            PCU_TRY(resolve_witness_device<T>(ws, qs, s == 0 ? n : msecond, dsrc, s == 0 ? msecond : n, dr->stats + s, st));
             PCU_TRY(fetch());
         }
     }
@@ -170,6 +173,20 @@ int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const
         PCU_CUDA(cudaStreamSynchronize(st));
     }
     *out_count = kept;
+    return PCU_B200_OK;
+}
+
+// Prepares a cloud from HOST points: staged through the workspace, binned into the handle's own block.
+template <typename T>
+int cloud_prepare_host(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out) {
+    if (!ws || !out) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
+    PCU_TRY(check_cloud_args<T>(points, n, points, 1));
+    PCU_ON_DEVICE(ws);
+    cudaStream_t st = ws->own_stream;
+    PCU_TRY(ensure_io(ws, align_up(sizeof(T) * 3 * (size_t)n), st));
+    PCU_CUDA(cudaMemcpyAsync(ws->io, points, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    PCU_TRY(cloud_prepare_device<T>(ws, reinterpret_cast<const T*>(ws->io), n, out, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
     return PCU_B200_OK;
 }
 
@@ -271,6 +288,33 @@ int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int
     return debug_kd_tree<double>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
                                  kid0, kid1, out_nodes);
 }
+int pcu_b200_cloud_prepare_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, pcu_b200_cloud** out_cloud) {
+    return cloud_prepare_host<float>(ws, points, n, out_cloud);
+}
+int pcu_b200_cloud_prepare_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud) {
+    return cloud_prepare_host<double>(ws, points, n, out_cloud);
+}
+int pcu_b200_chamfer_prepared_host_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const pcu_b200_cloud* y,
+                                       pcu_b200_nn_stats* out_stats, float* out_value) {
+    if (!y) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_host<float>(ws, x, n, nullptr, 0, true, out_stats, out_value, y);
+}
+int pcu_b200_chamfer_prepared_host_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const pcu_b200_cloud* y,
+                                       pcu_b200_nn_stats* out_stats, double* out_value) {
+    if (!y) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_host<double>(ws, x, n, nullptr, 0, true, out_stats, out_value, y);
+}
+int pcu_b200_nn_stats_prepared_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const pcu_b200_cloud* dataset,
+                                        pcu_b200_nn_stats* out_stats) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_host<float>(ws, query, n, nullptr, 0, false, out_stats, nullptr, dataset);
+}
+int pcu_b200_nn_stats_prepared_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const pcu_b200_cloud* dataset,
+                                        pcu_b200_nn_stats* out_stats) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_host<double>(ws, query, n, nullptr, 0, false, out_stats, nullptr, dataset);
+}
+
 int pcu_b200_morton_encode_host_i32(pcu_b200_workspace* ws, const int32_t* pts, int64_t n, uint64_t* out_codes) {
     if (n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "pts must be an array of shape [n, 3] but got an empty array");
     return morton_host(ws, pts, sizeof(int32_t) * 3 * n, nullptr, 0, out_codes, sizeof(uint64_t) * n,

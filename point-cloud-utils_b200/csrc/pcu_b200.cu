@@ -219,6 +219,19 @@ struct pcu_b200_workspace {
     bool host_marks = false;      // marks 9 and 10 belong to the last call
 };
 
+// A cloud binned once (pcu_b200_cloud_prepare_*): its cell-sorted points, cell table, grid header, wall tables and
+// pyramid buffers live in one private device block, described by the same Cloud<T> record the kernels take.
+struct pcu_b200_cloud {
+    int device = 0;
+    int is_f64 = 0;
+    long long n = 0;
+    unsigned char* block = nullptr;
+    size_t bytes = 0;
+    Cloud<float> desc32{};
+    Cloud<double> desc64{};
+    const void* raw = nullptr;   // the handle's own copy of the caller's (n, 3) array (inside block)
+};
+
 #define PCU_STAGE_NAMES "descriptors", "bbox+grid", "histogram", "scan", "scatter", "search", "search_far", "finalize", "h2d", "d2h"
 
 namespace {
@@ -328,6 +341,7 @@ struct PlanSpec {
     float cell_mult[2] = {1.f, 1.f};   // grid refinement from the previous call's fill statistics
     unsigned* hint_dev = nullptr;      // 2 x 4 words of host-mapped memory, or null
     int binning = 0;                // pcu_b200_options::binning
+    bool prepared_second = false;   // the second cloud is a pcu_b200_cloud: its descriptor replaces the carved one, it is not binned
     T* out_dist = nullptr;          // want_out (batch == 1)
     long long* out_idx = nullptr;
     pcu_b200_nn_stats* stats = nullptr;   // caller's device buffer, or null -> carved from the arena
@@ -416,7 +430,7 @@ struct Plan {
         // grid-wide passes do in ~50 us, and a batch of 1024 such pairs is 5 % slower, so larger clouds keep
         // the grid-wide passes whatever the batch size).
         const bool fits = max_cap + 1 <= kSmallMaxCells && max_n <= kSmallMaxPoints;
-        one_cta_binning = fits && (sp.binning == 2 || (sp.binning == 0 && max_n <= 8192));
+        one_cta_binning = !sp.prepared_second && fits && (sp.binning == 2 || (sp.binning == 0 && max_n <= 8192));
         for (int d = 0; d < sp.nsweeps; ++d)
             args.sweep[d].counters = take_strided<unsigned>(cv, 8, B, args.ss[d].counters);
         zero_begin = base ? base + zero_from : nullptr;
@@ -544,14 +558,15 @@ int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, PlanSpec<T>& spec, cudaS
 // cloud has arrived on the device.  The first cloud is then binned -- all five passes -- while the second is
 // still crossing PCIe, and only the second cloud's passes follow its copy.
 template <typename T>
-int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream, const cudaEvent_t* ready = nullptr) {
+int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream, const cudaEvent_t* ready = nullptr,
+                    bool first_only = false) {
     const int nclouds = plan.nclouds;
-    if (ready != nullptr && plan.by_value && !plan.one_cta_binning) {
+    if ((ready != nullptr || first_only) && plan.by_value && !plan.one_cta_binning) {
         PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
         const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
         const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
-        for (int s = 0; s < 2; ++s) {
-            PCU_CUDA(cudaStreamWaitEvent(stream, ready[s], 0));
+        for (int s = 0; s < (first_only ? 1 : 2); ++s) {   // first_only: the second cloud is a prepared one
+            if (ready != nullptr) PCU_CUDA(cudaStreamWaitEvent(stream, ready[s], 0));
             CloudsVal<T> one;
             one.v[0] = plan.cv.v[s];
             one.v[1] = plan.cv.v[s];
@@ -568,7 +583,7 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
     }
     if (ready != nullptr) {
         PCU_CUDA(cudaStreamWaitEvent(stream, ready[0], 0));
-        PCU_CUDA(cudaStreamWaitEvent(stream, ready[1], 0));
+        if (!first_only) PCU_CUDA(cudaStreamWaitEvent(stream, ready[1], 0));
     }
     if (plan.one_cta_binning) {
         PCU_CUDA(cudaMemsetAsync(plan.zero_begin + plan.zero_cells_bytes, 0, plan.zero_bytes - plan.zero_cells_bytes, stream));
@@ -686,10 +701,21 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
 
 // ---- fused k = 1 statistics -------------------------------------------------------------------
 // nsweeps == 1: query -> dataset.  nsweeps == 2: x -> y and y -> x over the same two binned clouds.
+template <typename T> const Cloud<T>& cloud_desc(const pcu_b200_cloud* c);
+template <> const Cloud<float>& cloud_desc<float>(const pcu_b200_cloud* c) { return c->desc32; }
+template <> const Cloud<double>& cloud_desc<double>(const pcu_b200_cloud* c) { return c->desc64; }
+
 template <typename T>
 int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
-                 pcu_b200_nn_stats* out_stats, T* out_value, cudaStream_t stream, const cudaEvent_t* ready = nullptr) {
+                 pcu_b200_nn_stats* out_stats, T* out_value, cudaStream_t stream, const cudaEvent_t* ready = nullptr,
+                 const pcu_b200_cloud* prepared = nullptr) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (prepared != nullptr) {
+        if (prepared->is_f64 != (sizeof(T) == 8 ? 1 : 0)) return fail(PCU_B200_INVALID_ARGUMENT, "the prepared cloud has another precision than the points");
+        if (prepared->device != ws->device) return fail(PCU_B200_INVALID_ARGUMENT, "the prepared cloud lives on device %d, the workspace on %d", prepared->device, ws->device);
+        b = (const T*)prepared->raw;
+        m = prepared->n;
+    }
     PCU_TRY(check_cloud_args<T>(a, n, b, m));
     if (!out_stats) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     PCU_ON_DEVICE(ws);
@@ -701,12 +727,14 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     spec.binning = ws->opts.binning;
     spec.stats = out_stats;
     spec.value_out = both ? out_value : nullptr;
+    spec.prepared_second = prepared != nullptr;
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec, stream));
+    if (prepared != nullptr) plan.cv.v[1] = cloud_desc<T>(prepared);   // a single pair: descriptors travel by value
     mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
     mark(ws, 1, stream);
-    PCU_TRY(enqueue_binning(ws, plan, stream, ready));
+    PCU_TRY(enqueue_binning(ws, plan, stream, ready, prepared != nullptr));
     const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
     PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, ns), kThreads, false, true);
     mark(ws, 6, stream);
@@ -815,6 +843,49 @@ int morton_knn_device(pcu_b200_workspace* ws, const unsigned long long* codes, l
     if (!out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     PCU_ON_DEVICE(ws);
     PCU_LAUNCH(morton_knn_kernel, blocks_for(m), kThreads, stream, codes, n, qcodes, m, k, sort_dist, out_idx);
+    return PCU_B200_OK;
+}
+
+// ---- prepared clouds ---------------------------------------------------------------------------------------
+// Bins `points` once into a private block: the layout of an ordinary plan whose second cloud is a one-point
+// dummy, with only the first cloud binned; the handle keeps that cloud's descriptor.
+template <typename T>
+int cloud_prepare_device(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out, cudaStream_t stream) {
+    if (!ws || !out) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    PCU_TRY(check_cloud_args<T>(points, n, points, 1));
+    PCU_ON_DEVICE(ws);
+    PlanSpec<T> spec;
+    spec.a = points; spec.n = n; spec.b = points; spec.m = 1;
+    spec.nsweeps = 1; spec.k = 1;
+    spec.occupancy = occupancy_for(ws, 1);
+    spec.binning = 1;                 // the grid-wide passes: the handle's buffers are global memory either way
+    spec.prepared_second = true;      // (also keeps the dummy out of the one-CTA build)
+    Plan<T> plan;
+    plan.layout(nullptr, spec);
+    const size_t raw_bytes = align_up(sizeof(T) * 3 * (size_t)n);
+    pcu_b200_cloud* c = new (std::nothrow) pcu_b200_cloud();
+    if (!c) return fail(PCU_B200_OUT_OF_MEMORY, "out of host memory");
+    c->device = ws->device; c->is_f64 = sizeof(T) == 8 ? 1 : 0; c->n = n; c->bytes = plan.total + raw_bytes;
+    cudaError_t e = cudaMalloc((void**)&c->block, c->bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return fail(PCU_B200_OUT_OF_MEMORY, "cudaMalloc of %zu bytes for a prepared cloud failed: %s", plan.total + raw_bytes, cudaGetErrorString(e));
+    }
+    T* raw_copy = reinterpret_cast<T*>(c->block + plan.total);
+    auto bail = [&](int status) { cudaFree(c->block); delete c; return status; };
+    if (cudaMemcpyAsync(raw_copy, points, sizeof(T) * 3 * n, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+        return bail(fail(PCU_B200_CUDA_ERROR, "copy of the points failed: %s", cudaGetErrorString(cudaGetLastError())));
+    spec.a = raw_copy; spec.b = raw_copy;
+    plan.layout(c->block, spec);
+    const int st = enqueue_binning(ws, plan, stream, nullptr, true);
+    if (st != PCU_B200_OK) return bail(st);
+    Cloud<T> d = plan.cv.v[0];
+    d.hint_out = nullptr;             // a prepared cloud takes no part in the grid-sizing feedback
+    if (sizeof(T) == 8) std::memcpy(&c->desc64, &d, sizeof d); else std::memcpy(&c->desc32, &d, sizeof d);
+    c->raw = raw_copy;
+    *out = c;
     return PCU_B200_OK;
 }
 
@@ -1185,6 +1256,43 @@ int pcu_b200_chamfer_f32(pcu_b200_workspace* ws, const float* x, int64_t n, cons
 int pcu_b200_chamfer_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const double* y, int64_t m,
                          pcu_b200_nn_stats* out_stats, double* out_value, void* stream) {
     return stats_device<double>(ws, x, n, y, m, true, out_stats, out_value, (cudaStream_t)stream);
+}
+
+int pcu_b200_cloud_prepare_f32(pcu_b200_workspace* ws, const float* points, int64_t n, pcu_b200_cloud** out_cloud, void* stream) {
+    return cloud_prepare_device<float>(ws, points, n, out_cloud, (cudaStream_t)stream);
+}
+int pcu_b200_cloud_prepare_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud, void* stream) {
+    return cloud_prepare_device<double>(ws, points, n, out_cloud, (cudaStream_t)stream);
+}
+int pcu_b200_cloud_destroy(pcu_b200_cloud* cloud) {
+    if (!cloud) return PCU_B200_OK;
+    DeviceGuard guard(cloud->device);
+    cudaDeviceSynchronize();          // calls that use the cloud may still be queued
+    if (cloud->block) cudaFree(cloud->block);
+    delete cloud;
+    return PCU_B200_OK;
+}
+int64_t pcu_b200_cloud_size(const pcu_b200_cloud* cloud) { return cloud ? cloud->n : 0; }
+const void* pcu_b200_cloud_points(const pcu_b200_cloud* cloud) { return cloud ? cloud->raw : nullptr; }
+int pcu_b200_chamfer_prepared_f32(pcu_b200_workspace* ws, const float* x, int64_t n, const pcu_b200_cloud* y,
+                                  pcu_b200_nn_stats* out_stats, float* out_value, void* stream) {
+    if (!y) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_device<float>(ws, x, n, nullptr, 0, true, out_stats, out_value, (cudaStream_t)stream, nullptr, y);
+}
+int pcu_b200_chamfer_prepared_f64(pcu_b200_workspace* ws, const double* x, int64_t n, const pcu_b200_cloud* y,
+                                  pcu_b200_nn_stats* out_stats, double* out_value, void* stream) {
+    if (!y) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_device<double>(ws, x, n, nullptr, 0, true, out_stats, out_value, (cudaStream_t)stream, nullptr, y);
+}
+int pcu_b200_nn_stats_prepared_f32(pcu_b200_workspace* ws, const float* query, int64_t n, const pcu_b200_cloud* dataset,
+                                   pcu_b200_nn_stats* out_stats, void* stream) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_device<float>(ws, query, n, nullptr, 0, false, out_stats, nullptr, (cudaStream_t)stream, nullptr, dataset);
+}
+int pcu_b200_nn_stats_prepared_f64(pcu_b200_workspace* ws, const double* query, int64_t n, const pcu_b200_cloud* dataset,
+                                   pcu_b200_nn_stats* out_stats, void* stream) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return stats_device<double>(ws, query, n, nullptr, 0, false, out_stats, nullptr, (cudaStream_t)stream, nullptr, dataset);
 }
 
 int pcu_b200_voxel_downsample_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const void* attrib, int attrib_cols,

@@ -226,3 +226,40 @@ def test_device_call_then_numpy_call_without_synchronising(pcu, oracle):
         c = pcu.chamfer_distance(a, b)
         assert h == ref_small and abs(float(c) - ref_cham) <= REL * ref_cham
         assert np.array_equal(i.cpu().numpy(), ref_big[1]) and np.array_equal(d.cpu().numpy(), ref_big[0])
+
+
+# ---- prepared clouds: a fixed cloud binned once -------------------------------------------------------------
+def test_prepared_cloud_gives_the_plain_results(pcu, oracle):
+    import torch
+    rng = np.random.default_rng(41)
+    for dtype in (np.float32, np.float64):
+        y = rng.random((150000, 3)).astype(dtype)
+        target = pcu.prepare_cloud(y)
+        assert len(target) == 150000 and target.dtype == dtype
+        yt = torch.from_numpy(y).cuda()
+        target_dev = pcu.prepare_cloud(yt)
+        for n in (90000, 1, 150000):
+            x = (rng.random((n, 3)) * np.array([1.0, 0.8, 1.2])).astype(dtype)
+            ref_c = float(oracle.chamfer_distance(x, y))
+            ref_h = oracle.hausdorff_distance(x, y, return_index=True)
+            ref_o = oracle.one_sided_hausdorff_distance(x, y)
+            for t, xin in ((target, x), (target_dev, torch.from_numpy(x).cuda())):
+                c = pcu.chamfer_distance(xin, t)
+                assert abs(float(c) - ref_c) <= REL * ref_c and abs(float(c) - float(pcu.chamfer_distance(x, y))) <= 1e-7 * ref_c
+                assert pcu.hausdorff_distance(xin, t, return_index=True) == ref_h
+                assert pcu.one_sided_hausdorff_distance(xin, t) == ref_o
+                assert pcu.one_sided_hausdorff_distance(xin, t, False, True) == oracle.one_sided_hausdorff_distance(x, y, False, True)
+        # duplicates in the target: the Hausdorff witness is decided by tie order -> the replay runs against the handle's copy
+        yd = np.concatenate([y[:5000], y[:5000]])
+        td = pcu.prepare_cloud(yd)
+        xq = (y[:300] + dtype(0.25)).astype(dtype)
+        assert pcu.one_sided_hausdorff_distance(xq, td) == oracle.one_sided_hausdorff_distance(xq, yd)
+        assert pcu.hausdorff_distance(torch.from_numpy(xq).cuda(), pcu.prepare_cloud(torch.from_numpy(yd).cuda()), return_index=True) == \
+            oracle.hausdorff_distance(xq, yd, return_index=True)
+        with pytest.raises(ValueError):
+            pcu.chamfer_distance(x.astype(np.float64 if dtype == np.float32 else np.float32), target)
+        with pytest.raises(ValueError):
+            pcu.chamfer_distance(x, target, return_index=True)
+        target.close()
+        with pytest.raises(ValueError, match="closed"):
+            pcu.chamfer_distance(x, target)
