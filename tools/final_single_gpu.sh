@@ -19,15 +19,10 @@ except Exception as e:
 PY
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_c3.csv python bench.py --steps 2 --warmup 3 --no-c5 --no-cpu-baseline > gpurun_out/${tag}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'nn1_kernel' -s 4 -c 1 -o gpurun_out/${tag}_nn1 python tools/run_chamfer.py > gpurun_out/${tag}_ncu_nn1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'nn1_kernel' -s 2 -c 1 -o gpurun_out/${tag}_nn1 python tools/run_chamfer.py > gpurun_out/${tag}_ncu_nn1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'nn1_kernel' -s 1 -c 1 -o gpurun_out/${tag}_nn1_c2 python tools/run_knn.py 1 > gpurun_out/${tag}_ncu_nn1_c2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'knn_thread_kernel' -s 1 -c 1 -o gpurun_out/${tag}_knn16_c4 python tools/run_knn.py 16 10000000 1000000 > gpurun_out/${tag}_ncu_knn16.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'nn1_kernel' -s 1 -c 1 -o gpurun_out/${tag}_nn1_c5 python tools/run_chamfer.py 65536 65536 1024 > gpurun_out/${tag}_ncu_nn1_c5.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'kd_build_kernel' -s 0 -c 1 -o gpurun_out/${tag}_kdbuild python tools/run_knn.py 16 > gpurun_out/${tag}_ncu_kdbuild.log 2>&1
 ls -la gpurun_out/${tag}_* | awk '{print $5, $9}'
-# diagnostic: does the host-path time depend on the process environment (torchrun sets OMP_NUM_THREADS=1)?
-python tools/host_path_time.py > gpurun_out/${tag}_host_default.log 2>&1
-OMP_NUM_THREADS=1 python tools/host_path_time.py > gpurun_out/${tag}_host_omp1.log 2>&1
-(command -v numactl > /dev/null && numactl --cpunodebind=0 --membind=0 python tools/host_path_time.py > gpurun_out/${tag}_host_numa0.log 2>&1) || true
-head -3 gpurun_out/${tag}_host_default.log gpurun_out/${tag}_host_omp1.log gpurun_out/${tag}_host_numa0.log 2>/dev/null
-cat /sys/bus/pci/devices/*/numa_node 2>/dev/null | sort | uniq -c | head -5; nvidia-smi topo -m 2>/dev/null | head -12
+python tools/host_path_time.py > gpurun_out/${tag}_host_path.log 2>&1; head -12 gpurun_out/${tag}_host_path.log
