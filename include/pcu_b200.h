@@ -240,6 +240,28 @@ int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_
 int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                              double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
 
+/* ---- point-cloud normals from all points in a ball -----------------------
+ * Replaces estimate_point_cloud_normals_ball_internal (src/point_cloud_normals.cpp:303-370, estimator :48-113).
+ * The neighbourhood of a point is what the reference's call nanoflann radiusSearch(query, ball_radius) returns:
+ * every point (itself included) whose SQUARED distance, rounded like the reference's metric, is below
+ * (scalar)radius -- nanoflann's radius is in squared units and the reference passes ball_radius as it is -- while
+ * the weight function sees the true distance: 1 ("constant") or (1 - d/r)^4 (4 d/r + 1) ("rbf").  Points with
+ * fewer than min_pts_per_ball neighbours are dropped; with max_pts_per_ball > 0 a uniformly random subset of that
+ * size is fitted (the reference shuffles with rand(); here selection sampling from a hash of seed, row, position:
+ * same distribution, reproducible for a given seed, not the same subset).  Outputs as for the k-NN variant. */
+typedef struct pcu_b200_ball_options {
+    double radius;                 /* > 0 */
+    double drop_angle_threshold;   /* radians; only used with view directions */
+    int32_t min_pts_per_ball;      /* >= 3 */
+    int32_t max_pts_per_ball;      /* <= 0: no limit, else >= 3 */
+    int32_t weight_function;       /* 0 "constant", 1 "rbf" */
+    uint32_t seed;                 /* subset selection when max_pts_per_ball > 0 */
+} pcu_b200_ball_options;
+int pcu_b200_normals_ball_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs,
+                              const pcu_b200_ball_options* options, int64_t* out_idx, float* out_normals, int64_t* out_count, void* stream);
+int pcu_b200_normals_ball_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,
+                              const pcu_b200_ball_options* options, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
+
 /* ---- voxel-grid down-sampling --------------------------------------------
  * Replaces downsample_point_cloud_voxel_grid_internal (src/sample_point_cloud.cpp:336-367, :163-244): every point
  * goes to voxel int(floor((p - min_bound) / voxel_size)) per axis, computed in the cloud's precision exactly like the
@@ -321,6 +343,10 @@ int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, i
                                   double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count);
 int pcu_b200_normals_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                                   double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count);
+int pcu_b200_normals_ball_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs,
+                                   const pcu_b200_ball_options* options, int64_t* out_idx, float* out_normals, int64_t* out_count);
+int pcu_b200_normals_ball_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,
+                                   const pcu_b200_ball_options* options, int64_t* out_idx, double* out_normals, int64_t* out_count);
 
 /* ---- diagnostics ----------------------------------------------------------------------------
  * Builds the kd-tree replica used by the tie replay for HOST points and copies it out, so tests can

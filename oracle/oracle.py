@@ -225,6 +225,71 @@ def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None
     return kept, normal[kept].astype(points.dtype)
 
 
+def ball_neighbourhoods(points, ball_radius, chunk=512):
+    """What the reference's tree.index->radiusSearch(query, ball_radius, ...) returns (src/point_cloud_normals.cpp:73-74),
+    by brute force: nanoflann's RadiusResultSet keeps a point when `dist < radius` where dist is the L2_Simple value,
+    i.e. the SQUARED distance ((dx*dx + dy*dy) + dz*dz, every operation rounded in the cloud's precision,
+    nanoflann.hpp:496-507), and radius is ball_radius narrowed to that precision.  Returns a list of index arrays
+    (ascending) and the matching squared distances."""
+    points = np.ascontiguousarray(points)
+    t = points.dtype.type
+    r2 = t(ball_radius)
+    n = points.shape[0]
+    nbrs, d2s = [], []
+    for a in range(0, n, chunk):
+        q = points[a:a + chunk]
+        d = q[:, None, :] - points[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        inside = d2 < r2
+        for i in range(q.shape[0]):
+            j = np.nonzero(inside[i])[0]
+            nbrs.append(j)
+            d2s.append(d2[i, j])
+    return nbrs, d2s
+
+
+def estimate_point_cloud_normals_ball(points, ball_radius, view_directions=None, drop_angle_threshold=np.deg2rad(90.0),
+                                      min_pts_per_ball=3, max_pts_per_ball=-1, weight_function="constant"):
+    """src/point_cloud_normals.cpp:48-113 + :303-370 restated (max_pts_per_ball <= 0 only: with a cap the reference fits a
+    rand()-dependent subset, which no oracle can reproduce).  Neighbourhoods by brute force with the reference's rounded
+    metric; weights and offsets as the reference forms them (difference in the cloud's precision, times the double
+    weight); numpy's LAPACK SVD stands in for Eigen's JacobiSVD.  PARITY UNPINNED for the normal vector itself (as for
+    the k-NN variant); the neighbour sets, hence the kept indices without view directions, are exact by construction."""
+    points = np.asarray(points)
+    if not ball_radius > 0.0:
+        raise ValueError("Invalid radius (%f) must be greater than 0." % ball_radius)
+    if min_pts_per_ball < 3:
+        raise ValueError("Invalid min_pts_per_ball (%d) must be greater than 3." % min_pts_per_ball)
+    if max_pts_per_ball > 0:
+        raise ValueError("the oracle does not model the reference's random subset (max_pts_per_ball > 0)")
+    if weight_function not in ("constant", "rbf"):
+        raise ValueError("Invalid weight_function, must be one of 'constant' or 'rbf'.")
+    n = points.shape[0]
+    has_dirs = view_directions is not None and np.asarray(view_directions).shape[0] != 0
+    nbrs, d2s = ball_neighbourhoods(points, ball_radius)
+    kept, normals = [], []
+    for i in range(n):
+        j = nbrs[i]
+        if len(j) < min_pts_per_ball:
+            continue
+        w = np.ones(len(j))
+        if weight_function == "rbf":
+            r = np.sqrt(d2s[i].astype(np.float64)) / float(ball_radius)
+            w = (1.0 - r) ** 4 * (4 * r + 1.0)
+        offsets = (points[j] - points[i]).astype(np.float64) * w[:, None]
+        _, _, vt = np.linalg.svd(offsets, full_matrices=False)
+        normal = vt[2].copy()
+        if has_dirs:
+            dirv = np.asarray(view_directions[i], dtype=np.float64)
+            normal *= np.sign(normal @ dirv)
+            with np.errstate(invalid="ignore"):
+                if np.arccos(normal @ dirv) > drop_angle_threshold:
+                    continue
+        kept.append(i)
+        normals.append(normal)
+    return np.array(kept, dtype=np.int64), np.array(normals, dtype=np.float64).reshape(-1, 3).astype(points.dtype)
+
+
 # ---- voxel-grid down-sampling (src/sample_point_cloud.cpp:163-244, point_cloud_utils/__init__.py:123-200) ----
 def voxel_indices(points, voxel_size, min_bound):
     """:201-206 -- int(floor((p - min_bound) / voxel_size)) per axis, in the cloud's precision (the binding casts the

@@ -37,7 +37,7 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken insta
         "There is no pure-Python or CPU fallback for this package." % (_e,)) from _e
 
 __all__ = ["k_nearest_neighbors", "one_sided_hausdorff_distance", "hausdorff_distance", "chamfer_distance",
-           "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "morton_encode", "morton_decode", "morton_add",
+           "batched_chamfer_distance", "estimate_point_cloud_normals_knn", "estimate_point_cloud_normals_ball", "morton_encode", "morton_decode", "morton_add",
            "morton_subtract", "morton_knn", "pairwise_distances", "sinkhorn", "earth_movers_distance",
            "downsample_point_cloud_on_voxel_grid", "prepare_cloud", "PreparedCloud", "device_count",
            "current_device", "launch_count"]
@@ -548,6 +548,89 @@ def estimate_point_cloud_normals_knn(points, num_neighbors, view_directions=None
     return _pcu_internal.estimate_point_cloud_normals_knn_internal(points, view_directions, int(num_neighbors),
                                                                    int(max_points_per_leaf), float(drop_angle_threshold),
                                                                    int(num_threads), -1, _dev(device))
+
+
+def estimate_point_cloud_normals_ball(points, ball_radius, view_directions=None, drop_angle_threshold=_np.deg2rad(90.0),
+                                      min_pts_per_ball=3, max_pts_per_ball=-1, weight_function="constant",
+                                      max_points_per_leaf=10, num_threads=-1, *, device=None):
+    """
+    Estimate normals for a point cloud by locally fitting a plane to all points within a radius of each point
+    (possibly weighted by a radial basis function).
+
+    Args:
+        points: (n, 3)-shaped NumPy array (or CUDA tensor) of point positions (each row is a point)
+        ball_radius: The radius of each neighborhood used to estimate normals.  As in the reference, this value is
+                     handed to the radius search as it is, and that search compares SQUARED distances with it: the
+                     neighbourhood of a point is every point whose squared distance is below ball_radius, while the
+                     'rbf' weight is evaluated with the true distance d and r = ball_radius.
+        view_directions: (n, 3)-shaped array or None, the unit direction to the sensor for each point; used to align
+                         the normals and to drop points.
+        drop_angle_threshold: If view_directions is passed in, drop points whose angle between the normal and view
+                              direction exceeds drop_angle_threshold (in radians).
+        min_pts_per_ball: Discard points whose neighborhood contains fewer than min_pts_per_ball points.
+        max_pts_per_ball: If set to a positive number, then only use a random subset of max_pts_per_ball points of each
+                          neighborhood whose number of points exceeds this value (the subset is drawn from NumPy's
+                          global random state: seed it for reproducible results).
+        weight_function: 'constant' (weight 1 for every point) or 'rbf' ((1 - d/r)^4 * (4 * d/r + 1)).
+        max_points_per_leaf, num_threads: kd-tree leaf size / CPU threads of the reference; accepted and ignored.
+        device : see `k_nearest_neighbors` (keyword only).
+
+    Returns:
+        idx : an (m,)-shaped int64 array of indices into points (the points that were kept, ascending)
+        n : an (m, 3)-shaped array of unit normals for those points
+
+    Mirrors /root/reference/point_cloud_utils/_pointcloud_normals.py:57-123 and
+    /root/reference/src/point_cloud_normals.cpp:48-113, :303-370.  Neighbour sets (hence which points are kept by
+    min_pts_per_ball) are the reference's; normals agree up to rounding and, without view directions, up to sign.
+    """
+    seed = int(_np.random.randint(2 ** 31 - 1))
+    if _is_tensor(points):
+        torch = _torch()
+        if points.dtype not in (torch.float32, torch.float64):
+            raise ValueError("Invalid scalar type (%s) for argument 'points'. Expected one of ['float32', 'float64']." % points.dtype)
+        if points.dim() != 2 or points.shape[-1] != 3:
+            raise ValueError("Invalid shape for points, must be (n, 3) but got " + str(tuple(points.shape)))
+        if points.shape[0] == 0:
+            raise ValueError("Invalid point set with zero elements: points must have shape (n, 3)")
+        dirs = None
+        if view_directions is not None:
+            if not _is_tensor(view_directions) or view_directions.dtype != points.dtype or \
+                    view_directions.device != points.device or tuple(view_directions.shape) != tuple(points.shape):
+                raise ValueError("Invalid view directions does not match the number of points. If view directions are passed "
+                                 "in, they must be a tensor with the dtype, device and shape of points.")
+            dirs = view_directions.detach().contiguous()
+        pts = points.detach().contiguous()
+        if not pts.is_cuda:
+            i, nrm = estimate_point_cloud_normals_ball(pts.numpy(), ball_radius, None if dirs is None else dirs.numpy(),
+                                                       drop_angle_threshold, min_pts_per_ball, max_pts_per_ball, weight_function,
+                                                       max_points_per_leaf, num_threads, device=device)
+            return torch.from_numpy(i), torch.from_numpy(nrm)
+        _same_device(pts, device)
+        n = pts.shape[0]
+        idx = torch.empty(n, dtype=torch.int64, device=pts.device)
+        nrm = torch.empty((n, 3), dtype=pts.dtype, device=pts.device)
+        count = torch.empty(1, dtype=torch.int64, device=pts.device)
+        _pcu_internal._normals_ball_device(pts.dtype == torch.float64, pts.data_ptr(), n, 0 if dirs is None else dirs.data_ptr(),
+                                           float(ball_radius), int(min_pts_per_ball), int(max_pts_per_ball),
+                                           float(drop_angle_threshold), str(weight_function), seed, idx.data_ptr(), nrm.data_ptr(),
+                                           count.data_ptr(), pts.device.index or 0, _stream_of(pts))
+        m = int(count.item())
+        return idx[:m], nrm[:m]
+    if type(points) != _np.ndarray:
+        raise ValueError("Invalid type for points, must be a NumPy array, but got " + str(type(points)) + ".")
+    if view_directions is None:
+        view_directions = _np.zeros([0, 3], dtype=points.dtype)
+    if type(view_directions) != _np.ndarray:
+        raise ValueError("Invalid type for view_directions, must be None or a NumPy array, but got " +
+                         str(type(view_directions)) + ".")
+    if len(points.shape) != 2 or points.shape[-1] != 3:
+        raise ValueError("Invalid shape for points, must be (n, 3) but got " + str(points.shape))
+    if len(view_directions.shape) != 2:
+        raise ValueError("Invalid shape for view_directions, must be (n, 3) but got " + str(view_directions.shape))
+    return _pcu_internal.estimate_point_cloud_normals_ball_internal(points, view_directions, float(ball_radius),
+                                                                    int(min_pts_per_ball), int(max_pts_per_ball),
+                                                                    float(drop_angle_threshold), int(max_points_per_leaf),
+                                                                    int(num_threads), str(weight_function), seed, _dev(device))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -365,6 +365,26 @@ py::tuple chamfer_stats(const py::array& x_in, const py::array& y_in, int max_po
     return py::make_tuple(value, stats_to_dict(st[0]), stats_to_dict(st[1]));
 }
 
+// validate_input of the reference (src/point_cloud_normals.cpp:25-42) plus the npe dtype rule
+Dt validate_normals_input(const py::array& points, const py::array& view_dirs) {
+    const Dt dt = common_dtype(points, view_dirs, "points", "view_dirs");
+    auto shape_of = [](const py::array& a) {
+        std::ostringstream ss;
+        ss << "(";
+        for (py::ssize_t i = 0; i < a.ndim(); ++i) ss << (i ? ", " : "") << a.shape(i);
+        ss << ")";
+        return ss.str();
+    };
+    if (points.ndim() != 2 || points.shape(0) == 0 || points.shape(1) != 3)      // validate_input, :25-33
+        throw py::value_error("Invalid point set with zero elements: points must have shape (n, 3), but got points.shape = " +
+                              shape_of(points) + ".");
+    if (view_dirs.ndim() != 2 || (view_dirs.shape(0) != 0 && (view_dirs.shape(0) != points.shape(0) || view_dirs.shape(1) != 3)))
+        throw py::value_error("Invalid view directions does not match the number of points. If view directions are passed in, "
+                              "they must have the same shape as points. Got points.shape = " + shape_of(points) +
+                              ", and view_dirs.shape = " + shape_of(view_dirs) + ".");   // :34-42
+    return dt;
+}
+
 // estimate_point_cloud_normals_knn_internal (src/point_cloud_normals.cpp:375-411): (indices of the kept points,
 // their unit normals).  view_dirs is a (0, 3) array when no view directions are given, as in the reference's wrapper.
 template <typename T>
@@ -402,21 +422,7 @@ py::tuple estimate_point_cloud_normals_knn_internal(const py::array& points, con
     (void)num_threads; (void)random_seed;   // CPU threading / rand() seeding of the reference: no effect on the k-NN variant
     if (num_neighbors <= 0)
         throw py::value_error("Invalid number of neighbors (" + std::to_string(num_neighbors) + ") must be greater than 0.");
-    const Dt dt = common_dtype(points, view_dirs, "points", "view_dirs");
-    auto shape_of = [](const py::array& a) {
-        std::ostringstream ss;
-        ss << "(";
-        for (py::ssize_t i = 0; i < a.ndim(); ++i) ss << (i ? ", " : "") << a.shape(i);
-        ss << ")";
-        return ss.str();
-    };
-    if (points.ndim() != 2 || points.shape(0) == 0 || points.shape(1) != 3)      // validate_input, :25-33
-        throw py::value_error("Invalid point set with zero elements: points must have shape (n, 3), but got points.shape = " +
-                              shape_of(points) + ".");
-    if (view_dirs.ndim() != 2 || (view_dirs.shape(0) != 0 && (view_dirs.shape(0) != points.shape(0) || view_dirs.shape(1) != 3)))
-        throw py::value_error("Invalid view directions does not match the number of points. If view directions are passed in, "
-                              "they must have the same shape as points. Got points.shape = " + shape_of(points) +
-                              ", and view_dirs.shape = " + shape_of(view_dirs) + ".");   // :34-42
+    const Dt dt = validate_normals_input(points, view_dirs);
     const int dev = current_device_or_default(device);
     return dt == Dt::f32 ? normals_knn_numpy<float>(points, view_dirs, num_neighbors, max_points_per_leaf, drop_angle_threshold, dev)
                          : normals_knn_numpy<double>(points, view_dirs, num_neighbors, max_points_per_leaf, drop_angle_threshold, dev);
@@ -437,6 +443,77 @@ void normals_knn_device(bool is_f64, uintptr_t points, int64_t n, uintptr_t view
                                                    (int64_t*)out_idx, (double*)out_normals, (int64_t*)out_count, (void*)stream)
                         : pcu_b200_normals_knn_f32(ws, (const float*)points, n, (const float*)view_dirs, k, drop_angle,
                                                    (int64_t*)out_idx, (float*)out_normals, (int64_t*)out_count, (void*)stream);
+    }
+    check(status);
+}
+
+// estimate_point_cloud_normals_ball_internal (src/point_cloud_normals.cpp:303-370), argument order of the reference
+pcu_b200_ball_options ball_options(double radius, int min_pts, int max_pts, double drop_angle, const std::string& weight_function, int seed) {
+    if (radius <= 0.0) throw py::value_error("Invalid radius (" + std::to_string(radius) + ") must be greater than 0.");
+    if (min_pts < 3) throw py::value_error("Invalid min_pts_per_ball (" + std::to_string(min_pts) + ") must be greater than 3.");
+    if (max_pts > 0 && max_pts < 3)
+        throw py::value_error("Invalid max_pts_per_ball (" + std::to_string(max_pts) +
+                              ") must either be negative (no max) or a number greater than 3.");
+    pcu_b200_ball_options o;
+    o.radius = radius; o.drop_angle_threshold = drop_angle; o.min_pts_per_ball = min_pts; o.max_pts_per_ball = max_pts;
+    if (weight_function == "constant") o.weight_function = 0;
+    else if (weight_function == "rbf") o.weight_function = 1;
+    else throw py::value_error("Invalid weight_function, must be one of 'constant' or 'rbf'.");
+    o.seed = (uint32_t)seed;
+    return o;
+}
+
+template <typename T>
+py::tuple normals_ball_numpy(const py::array& p_in, const py::array& v_in, const pcu_b200_ball_options& o, int device) {
+    auto pts = dense<T>(p_in);
+    auto dirs = dense<T>(v_in);
+    const int64_t n = pts.shape(0);
+    const bool has_dirs = dirs.shape(0) != 0;
+    py::array_t<int64_t> idx({(py::ssize_t)n});
+    py::array_t<T> normals({(py::ssize_t)n, (py::ssize_t)3});
+    int64_t kept = 0;
+    Slot& slot = pool().get(device, kHostKey);
+    pcu_b200_workspace* ws = slot.ws;
+    int status;
+    {
+        CallScope scope(slot);
+        if (sizeof(T) == 4)
+            status = pcu_b200_normals_ball_host_f32(ws, (const float*)pts.data(), n, has_dirs ? (const float*)dirs.data() : nullptr, &o,
+                                                    idx.mutable_data(), (float*)normals.mutable_data(), &kept);
+        else
+            status = pcu_b200_normals_ball_host_f64(ws, (const double*)pts.data(), n, has_dirs ? (const double*)dirs.data() : nullptr, &o,
+                                                    idx.mutable_data(), (double*)normals.mutable_data(), &kept);
+    }
+    check(status);
+    idx.resize({(py::ssize_t)kept});
+    normals.resize({(py::ssize_t)kept, (py::ssize_t)3});
+    return py::make_tuple(idx, normals);
+}
+
+py::tuple estimate_point_cloud_normals_ball_internal(const py::array& points, const py::array& view_dirs, double radius,
+                                                     int min_pts_per_ball, int max_pts_per_ball, double drop_angle_threshold,
+                                                     int max_points_per_leaf, int num_threads, const std::string& weight_function,
+                                                     int random_seed, int device) {
+    (void)max_points_per_leaf; (void)num_threads;   // kd-tree leaf size / CPU threads of the reference: no effect on the result
+    const pcu_b200_ball_options o = ball_options(radius, min_pts_per_ball, max_pts_per_ball, drop_angle_threshold, weight_function, random_seed);
+    const Dt dt = validate_normals_input(points, view_dirs);
+    const int dev = current_device_or_default(device);
+    return dt == Dt::f32 ? normals_ball_numpy<float>(points, view_dirs, o, dev) : normals_ball_numpy<double>(points, view_dirs, o, dev);
+}
+
+void normals_ball_device(bool is_f64, uintptr_t points, int64_t n, uintptr_t view_dirs, double radius, int min_pts, int max_pts,
+                         double drop_angle, const std::string& weight_function, int seed, uintptr_t out_idx, uintptr_t out_normals,
+                         uintptr_t out_count, int device, uintptr_t stream) {
+    const pcu_b200_ball_options o = ball_options(radius, min_pts, max_pts, drop_angle, weight_function, seed);
+    Slot& slot = pool().get(device, stream);
+    pcu_b200_workspace* ws = slot.ws;
+    int status;
+    {
+        CallScope scope(slot);
+        status = is_f64 ? pcu_b200_normals_ball_f64(ws, (const double*)points, n, (const double*)view_dirs, &o, (int64_t*)out_idx,
+                                                    (double*)out_normals, (int64_t*)out_count, (void*)stream)
+                        : pcu_b200_normals_ball_f32(ws, (const float*)points, n, (const float*)view_dirs, &o, (int64_t*)out_idx,
+                                                    (float*)out_normals, (int64_t*)out_count, (void*)stream);
     }
     check(status);
 }
@@ -818,6 +895,12 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("device") = -1,
             "Indices of the kept points and their unit normals (plane fit to the k nearest neighbours of each point).");
     mod.def("_normals_knn_device", &normals_knn_device);
+    mod.def("estimate_point_cloud_normals_ball_internal", &estimate_point_cloud_normals_ball_internal, py::arg("points"),
+            py::arg("view_dirs"), py::arg("radius"), py::arg("min_pts_per_ball"), py::arg("max_pts_per_ball") = -1,
+            py::arg("drop_angle_threshold") = 1.5707963267948966, py::arg("max_points_per_leaf") = 10, py::arg("num_threads") = 0,
+            py::arg("weight_function") = "constant", py::arg("random_seed") = -1, py::arg("device") = -1,
+            "Indices of the kept points and their unit normals (plane fit to the points in a ball around each point).");
+    mod.def("_normals_ball_device", &normals_ball_device);
     mod.def("_cloud_prepare", &cloud_prepare_numpy, py::arg("points"), py::arg("device") = -1);
     mod.def("_cloud_prepare_device", &cloud_prepare_device);
     mod.def("_cloud_destroy", &cloud_destroy);

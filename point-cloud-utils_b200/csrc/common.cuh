@@ -171,7 +171,7 @@ struct Cloud {
     int cell_cap;           // upper bound on ncells (host-known)
     int stride;             // wall table stride (host-known)
     int bbox_blocks;        // partial bounding boxes of this cloud (host-known, <= kMaxBBoxBlocks)
-    int pad;
+    float min_cell;         // lower limit of the cell size (0: none) -- radius searches ask for cells no finer than their reach
 };
 
 // How kernels receive the cloud descriptors: a device array (batches) or, for a single pair, by value

@@ -165,7 +165,8 @@ __device__ void grid_setup_body(const Cloud<T>& c, const T* box, GridHeader<T>& 
             s_ext[a] = e;
             emax = fmax(emax, e);
         }
-        s_lo = emax / (double)maxdim;       // finest admissible cell (no axis exceeds maxdim cells)
+        // finest admissible cell: no axis exceeds maxdim cells, and not below the caller's limit
+        s_lo = fmin(emax, fmax(emax / (double)maxdim, (double)c.min_cell));
         s_hi = emax;                        // a single cell
     }
     __syncthreads();

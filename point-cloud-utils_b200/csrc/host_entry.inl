@@ -137,11 +137,12 @@ int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long lo
     return PCU_B200_OK;
 }
 
-template <typename T>
-int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, int k,
-                     double drop_angle_threshold, long long* out_idx, T* out_normals, long long* out_count) {
+// Host wrapper shared by the two normal estimators: stage points (and view directions), run `device_call` on the
+// workspace's stream, fetch the count, then exactly the kept rows.
+template <typename T, typename DeviceCall>
+int normals_host(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, long long* out_idx, T* out_normals,
+                 long long* out_count, DeviceCall&& device_call) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
-    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid number of neighbors (%d) must be greater than 0.", k);
     if (!points || n <= 0)
         return fail(PCU_B200_INVALID_ARGUMENT, "Invalid point set with zero elements: points must have shape (n, 3) (got %lld rows)", n);
     if (!out_idx || !out_normals || !out_count) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
@@ -162,7 +163,7 @@ int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const
     carve(cv, dp, dv, di, dn, dc);
     PCU_CUDA(cudaMemcpyAsync(dp, points, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
     if (view_dirs) PCU_CUDA(cudaMemcpyAsync(dv, view_dirs, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
-    PCU_TRY(normals_knn_device<T>(ws, dp, n, view_dirs ? dv : (const T*)nullptr, k, drop_angle_threshold, di, dn, dc, st));
+    PCU_TRY(device_call(dp, view_dirs ? dv : (const T*)nullptr, di, dn, dc, st));
     long long* hc = reinterpret_cast<long long*>(ws->host_slot);
     PCU_CUDA(cudaMemcpyAsync(hc, dc, sizeof(long long), cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
@@ -174,6 +175,25 @@ int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const
     }
     *out_count = kept;
     return PCU_B200_OK;
+}
+
+template <typename T>
+int normals_knn_host(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, int k,
+                     double drop_angle_threshold, long long* out_idx, T* out_normals, long long* out_count) {
+    if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid number of neighbors (%d) must be greater than 0.", k);
+    return normals_host<T>(ws, points, n, view_dirs, out_idx, out_normals, out_count,
+                           [&](const T* dp, const T* dv, long long* di, T* dn, long long* dc, cudaStream_t st) {
+                               return normals_knn_device<T>(ws, dp, n, dv, k, drop_angle_threshold, di, dn, dc, st);
+                           });
+}
+
+template <typename T>
+int normals_ball_host(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, const pcu_b200_ball_options* o,
+                      long long* out_idx, T* out_normals, long long* out_count) {
+    return normals_host<T>(ws, points, n, view_dirs, out_idx, out_normals, out_count,
+                           [&](const T* dp, const T* dv, long long* di, T* dn, long long* dc, cudaStream_t st) {
+                               return normals_ball_device<T>(ws, dp, n, dv, o, di, dn, dc, st);
+                           });
 }
 
 // Prepares a cloud from HOST points: staged through the workspace, binned into the handle's own block.
@@ -362,6 +382,14 @@ int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, i
 int pcu_b200_normals_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                                   double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count) {
     return normals_knn_host<double>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals, (long long*)out_count);
+}
+int pcu_b200_normals_ball_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs,
+                                   const pcu_b200_ball_options* options, int64_t* out_idx, float* out_normals, int64_t* out_count) {
+    return normals_ball_host<float>(ws, points, n, view_dirs, options, (long long*)out_idx, out_normals, (long long*)out_count);
+}
+int pcu_b200_normals_ball_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,
+                                   const pcu_b200_ball_options* options, int64_t* out_idx, double* out_normals, int64_t* out_count) {
+    return normals_ball_host<double>(ws, points, n, view_dirs, options, (long long*)out_idx, out_normals, (long long*)out_count);
 }
 int pcu_b200_batched_chamfer_host_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch,
                                       int64_t n, int64_t m, float* out_per_pair, double* out_sum) {

@@ -64,6 +64,16 @@ __device__ __forceinline__ void smallest_eigenvector(double xx, double xy, doubl
     n[0] = nx; n[1] = ny; n[2] = nz;
 }
 
+// Orientation towards / filtering by the view direction (:160-171 and :103-112, the same code in both estimators).
+__device__ __forceinline__ bool orient_by_view(double (&nrm)[3], double vx, double vy, double vz, double drop_angle_threshold) {
+    const double d = nrm[0] * vx + nrm[1] * vy + nrm[2] * vz;
+    const double sgn = (double)((0.0 < d) - (d < 0.0));       // sign(): 0 when the dot product is 0 (:21-23)
+    nrm[0] *= sgn; nrm[1] *= sgn; nrm[2] *= sgn;
+    const double angle = acos(nrm[0] * vx + nrm[1] * vy + nrm[2] * vz);
+    if (angle > drop_angle_threshold) { nrm[0] = nrm[1] = nrm[2] = 0.0; return false; }
+    return true;
+}
+
 // One thread per point.  idx: (n, k) neighbour rows from the k-NN call (-1 padded when the cloud has fewer than k
 // points: such points are dropped, src/point_cloud_normals.cpp:139-142).  view_dirs: (n, 3) or null.
 // normals: (n, 3) dense, written for every point; keep: (n) 1 = the reference would return this point.
@@ -90,15 +100,134 @@ __global__ void __launch_bounds__(kThreads) normals_knn_kernel(const T* __restri
         smallest_eigenvector(xx, xy, xz, yy, yz, zz, nrm);
         if (view_dirs != nullptr) {
             const double vx = (double)view_dirs[3 * i], vy = (double)view_dirs[3 * i + 1], vz = (double)view_dirs[3 * i + 2];
-            const double d = nrm[0] * vx + nrm[1] * vy + nrm[2] * vz;
-            const double sgn = (double)((0.0 < d) - (d < 0.0));       // sign(): 0 when the dot product is 0 (:21-23)
-            nrm[0] *= sgn; nrm[1] *= sgn; nrm[2] *= sgn;
-            const double angle = acos(nrm[0] * vx + nrm[1] * vy + nrm[2] * vz);
-            if (angle > drop_angle_threshold) { ok = false; nrm[0] = nrm[1] = nrm[2] = 0.0; }   // :166-170
+            ok = orient_by_view(nrm, vx, vy, vz, drop_angle_threshold);   // :160-171
         }
     }
     normals[3 * i] = (T)nrm[0]; normals[3 * i + 1] = (T)nrm[1]; normals[3 * i + 2] = (T)nrm[2];
     keep[i] = ok ? 1 : 0;
+}
+
+// ---- normals from all points in a ball (estimate_local_normal_rbf, src/point_cloud_normals.cpp:48-113; binding
+// :303-370) ------------------------------------------------------------------------------------------------------
+// The reference hands `ball_radius` to nanoflann's radiusSearch, whose radius is in the metric's units -- SQUARED
+// distance for L2_Simple (nanoflann.hpp RadiusResultSet::addPoint: `if (dist < radius)`) -- so the neighbourhood is
+//     { j : d2(p_i, p_j) < (T)ball_radius }        (the point itself included),
+// while the weight function receives the true distance: w = wendland(sqrt(d2), ball_radius).  Both are reproduced as
+// they are.  The neighbourhood test uses the reference-rounded d2 of common.cuh, so neighbour SETS are exact.
+//
+// max_pts_per_ball > 0: the reference shuffles the neighbours with std::shuffle(default_random_engine(rand())) and
+// keeps the first max_pts_per_ball -- a uniformly random subset that depends on the C library's rand() state and on
+// the thread that happens to process the point.  Here: a uniformly random subset of the same size by selection
+// sampling (Knuth 3.4.2 S) over the neighbours in cell order, driven by a counter-based hash of (seed, row, position):
+// deterministic for a given seed, the same distribution, not the same subset.
+struct BallParams {
+    double radius;
+    double drop_angle_threshold;
+    int min_pts, max_pts;
+    int weight_kind;        // 0 constant, 1 Wendland ("rbf")
+    unsigned seed;
+};
+
+__device__ __forceinline__ unsigned mix32(unsigned h) {
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h;
+}
+
+template <typename T> __device__ __forceinline__ T sub_down(T a, T b);
+template <> __device__ __forceinline__ float sub_down<float>(float a, float b) { return __fsub_rd(a, b); }
+template <> __device__ __forceinline__ double sub_down<double>(double a, double b) { return __dsub_rd(a, b); }
+template <typename T> __device__ __forceinline__ T add_up(T a, T b);
+template <> __device__ __forceinline__ float add_up<float>(float a, float b) { return __fadd_ru(a, b); }
+template <> __device__ __forceinline__ double add_up<double>(double a, double b) { return __dadd_ru(a, b); }
+
+// Calls visit(point, d2) for every point of the binned cloud with d2(q, point) < r2, in cell order.
+// Coverage: d2 >= fl(fl(q-p)^2) per axis and every rounding is monotone, so |q_a - p_a| <= sqrt(r2) (1 + 2 ulp) for
+// every qualifying point; the box below is that interval, widened and rounded outwards, mapped through the monotone
+// cell_of.  Rows (fixed y, z) whose wall gap already reaches r2 are skipped with the bound of search.cuh.
+template <typename T, typename Visit>
+__device__ __forceinline__ void walk_ball(const Cloud<T>& cl, const GridHeader<T>& g, const Pt<T>& q, T r2, Visit&& visit) {
+    using R = Real<T>;
+    const T eps = sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16;
+    const T reach = R::root(r2) * ((T)1 + (T)8 * eps) + (sizeof(T) == 4 ? (T)1.1754944e-38 : (T)2.2250738585072014e-308);
+    int lo[3], hi[3], c[3];
+    const T qv[3] = {q.x, q.y, q.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = cell_of<T>(sub_down<T>(qv[a], reach), g.origin[a], g.inv_h, g.dim[a]);
+        hi[a] = cell_of<T>(add_up<T>(qv[a], reach), g.origin[a], g.inv_h, g.dim[a]);
+        c[a] = cell_of<T>(qv[a], g.origin[a], g.inv_h, g.dim[a]);
+    }
+    const int st = g.stride;
+    const T* lo_y = cl.wall_lo + st;      const T* hi_y = cl.wall_hi + st;
+    const T* lo_z = cl.wall_lo + 2 * st;  const T* hi_z = cl.wall_hi + 2 * st;
+    for (int z = lo[2]; z <= hi[2]; ++z) {
+        const T bz = z < c[2] ? sq_gap<T>(q.z, lo_z[z + 1]) : (z > c[2] ? sq_gap<T>(q.z, hi_z[z]) : (T)0);
+        if (!(bz < r2)) continue;
+        for (int y = lo[1]; y <= hi[1]; ++y) {
+            const T by = y < c[1] ? sq_gap<T>(q.y, lo_y[y + 1]) : (y > c[1] ? sq_gap<T>(q.y, hi_y[y]) : (T)0);
+            if (!(R::add(by, bz) < r2)) continue;
+            const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+            const unsigned a = cl.cell_start[row + lo[0]], b = cl.cell_start[row + hi[0] + 1];
+            for (unsigned j = a; j < b; ++j) {
+                const Pt<T> p = load_pt<T>(cl.sorted + j);
+                const T d2 = dist2<T>(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (d2 < r2) visit(p, d2);
+            }
+        }
+    }
+}
+
+// One thread per point, in CELL order (neighbouring lanes walk overlapping boxes).  normals / keep are indexed by the
+// caller's row.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) normals_ball_kernel(Cloud<T> cl, const T* __restrict__ view_dirs, BallParams bp,
+                                                                T* __restrict__ normals, unsigned char* __restrict__ keep) {
+    grid_dependency_wait();
+    using R = Real<T>;
+    __shared__ GridHeader<T> g;
+    if (threadIdx.x == 0) g = *cl.grid;
+    __syncthreads();
+    const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= cl.n) return;
+    const Pt<T> q = load_pt<T>(cl.sorted + pos);
+    const long long row = (long long)q.i;
+    const T r2 = (T)bp.radius;                       // radiusSearch takes a DistanceType: the double is narrowed (:74)
+    double xx = 0.0, xy = 0.0, xz = 0.0, yy = 0.0, yz = 0.0, zz = 0.0;
+    auto fold = [&](const Pt<T>& p, T d2) {
+        double w = 1.0;
+        if (bp.weight_kind == 1) {                   // wendland_rbf (:334-339), in double like the reference
+            const double r = sqrt((double)d2) / bp.radius;
+            const double v1 = 1.0 - r, v2 = 4 * r + 1.0;
+            w = v1 * v1 * v1 * v1 * v2;
+        }
+        // (points(nbr, j) - query[j]) * weight: the difference in the cloud's precision, the product in double (:89)
+        const double dx = (double)R::sub(p.x, q.x) * w, dy = (double)R::sub(p.y, q.y) * w, dz = (double)R::sub(p.z, q.z) * w;
+        xx += dx * dx; xy += dx * dy; xz += dx * dz; yy += dy * dy; yz += dy * dz; zz += dz * dz;
+    };
+    long long found = 0;
+    walk_ball<T>(cl, g, q, r2, [&](const Pt<T>& p, T d2) { ++found; fold(p, d2); });
+    bool ok = found >= (long long)bp.min_pts;        // :75-77 (before the cap)
+    if (ok && bp.max_pts > 0 && found > (long long)bp.max_pts) {
+        xx = xy = xz = yy = yz = zz = 0.0;
+        unsigned long long remaining = (unsigned long long)found, needed = (unsigned long long)bp.max_pts;
+        unsigned t = 0;
+        const unsigned salt = mix32(bp.seed ^ mix32((unsigned)row * 0x9e3779b9u + 0x85ebca6bu));
+        walk_ball<T>(cl, g, q, r2, [&](const Pt<T>& p, T d2) {
+            const unsigned long long u = ((unsigned long long)mix32(salt + t * 0x9e3779b9u) * remaining) >> 32;   // uniform in [0, remaining)
+            ++t;
+            if (u < needed) { fold(p, d2); --needed; }
+            --remaining;
+        });
+    }
+    double nrm[3] = {0.0, 0.0, 0.0};
+    if (ok) {
+        smallest_eigenvector(xx, xy, xz, yy, yz, zz, nrm);
+        if (view_dirs != nullptr)
+            ok = orient_by_view(nrm, (double)view_dirs[3 * row], (double)view_dirs[3 * row + 1], (double)view_dirs[3 * row + 2],
+                                bp.drop_angle_threshold);
+    }
+    normals[3 * row] = (T)nrm[0]; normals[3 * row + 1] = (T)nrm[1]; normals[3 * row + 2] = (T)nrm[2];
+    keep[row] = ok ? 1 : 0;
 }
 
 // Order-preserving compaction of the kept points (the reference's single-thread loop appends in index order,

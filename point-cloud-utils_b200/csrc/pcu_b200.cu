@@ -802,6 +802,69 @@ int normals_knn_device(pcu_b200_workspace* ws, const T* points, long long n, con
     return PCU_B200_OK;
 }
 
+// ---- normals from all points in a ball (the radius variant) ---------------------------
+// The cloud is binned once (cells no finer than half the reach of the search, at most 8 per point), one thread per
+// point walks the cells its ball touches; the compaction is the k-NN variant's.
+template <typename T>
+int normals_ball_device(pcu_b200_workspace* ws, const T* points, long long n, const T* view_dirs, const pcu_b200_ball_options* o,
+                        long long* out_idx, T* out_normals, long long* out_count, cudaStream_t stream) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!o) return fail(PCU_B200_INVALID_ARGUMENT, "null options");
+    // the checks of the binding, src/point_cloud_normals.cpp:316-327
+    if (!(o->radius > 0.0)) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid radius (%f) must be greater than 0.", o->radius);
+    if (o->min_pts_per_ball < 3) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid min_pts_per_ball (%d) must be greater than 3.", o->min_pts_per_ball);
+    if (o->max_pts_per_ball > 0 && o->max_pts_per_ball < 3)
+        return fail(PCU_B200_INVALID_ARGUMENT, "Invalid max_pts_per_ball (%d) must either be negative (no max) or a number greater than 3.", o->max_pts_per_ball);
+    if (o->weight_function != 0 && o->weight_function != 1)
+        return fail(PCU_B200_INVALID_ARGUMENT, "Invalid weight_function, must be one of 'constant' or 'rbf'.");
+    if (!points || n <= 0)
+        return fail(PCU_B200_INVALID_ARGUMENT, "Invalid point set with zero elements: points must have shape (n, 3) (got %lld rows)", n);
+    PCU_TRY(check_cloud_args<T>(points, n, points, 1));
+    if (!out_idx || !out_normals || !out_count) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    PCU_ON_DEVICE(ws);
+    PlanSpec<T> spec;
+    spec.a = points; spec.n = n; spec.b = points; spec.m = 1;
+    spec.nsweeps = 1; spec.k = 1;
+    spec.occupancy = 0.125f;          // the cell budget; the cell size itself is held up by min_cell below
+    spec.binning = 1;
+    spec.prepared_second = true;      // the one-point second cloud is a dummy: only the first is binned
+    Plan<T> plan;
+    plan.layout(nullptr, spec);
+    PCU_TRY(adopt_stream(ws, stream));
+    PCU_TRY(ensure_arena(ws, plan.total, stream));
+    plan.layout(ws->arena, spec);
+    const double reach = std::sqrt((double)(T)o->radius);     // the search radius is a squared distance (normals.cuh)
+    plan.cv.v[0].min_cell = (float)std::min(1e30, 0.5 * reach);
+    plan.cv.v[0].hint_out = nullptr;
+    const long long nblocks = (n + kThreads - 1) / kThreads;
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& dense, unsigned char*& keep, unsigned*& counts) {
+        dense = cv.take<T>((size_t)3 * n);
+        keep = cv.take<unsigned char>((size_t)n);
+        counts = cv.take<unsigned>((size_t)nblocks);
+    };
+    T* dense; unsigned char* keep; unsigned* counts;
+    carve(measure, dense, keep, counts);
+    PCU_TRY(grow_block(ws->aux, ws->aux_bytes, measure.off, stream, "normal scratch"));
+    Carver cv(ws->aux);
+    carve(cv, dense, keep, counts);
+    mark(ws, 0, stream);
+    mark(ws, 1, stream);
+    PCU_TRY(enqueue_binning(ws, plan, stream, nullptr, true));
+    BallParams bp;
+    bp.radius = o->radius; bp.drop_angle_threshold = o->drop_angle_threshold;
+    bp.min_pts = o->min_pts_per_ball; bp.max_pts = o->max_pts_per_ball;
+    bp.weight_kind = o->weight_function; bp.seed = o->seed;
+    PCU_LAUNCH((normals_ball_kernel<T>), (unsigned)nblocks, kThreads, stream, plan.cv.v[0], view_dirs, bp, dense, keep);
+    mark(ws, 6, stream);
+    PCU_LAUNCH(keep_count_kernel, (unsigned)nblocks, kThreads, stream, keep, n, counts);
+    PCU_LAUNCH(keep_offsets_kernel, 1, 1024, stream, counts, nblocks, out_count);
+    PCU_LAUNCH((keep_scatter_kernel<T>), (unsigned)nblocks, kThreads, stream, keep, n, counts, dense, out_idx, out_normals);
+    mark(ws, 7, stream);
+    mark(ws, 8, stream);
+    return PCU_B200_OK;
+}
+
 // ---- Morton codes -------------------------------------------------------------------
 inline unsigned blocks_for(long long n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
@@ -1357,6 +1420,15 @@ int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64
                              double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream) {
     return normals_knn_device<double>(ws, points, n, view_dirs, k, drop_angle_threshold, (long long*)out_idx, out_normals,
                                       (long long*)out_count, (cudaStream_t)stream);
+}
+
+int pcu_b200_normals_ball_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs,
+                              const pcu_b200_ball_options* options, int64_t* out_idx, float* out_normals, int64_t* out_count, void* stream) {
+    return normals_ball_device<float>(ws, points, n, view_dirs, options, (long long*)out_idx, out_normals, (long long*)out_count, (cudaStream_t)stream);
+}
+int pcu_b200_normals_ball_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,
+                              const pcu_b200_ball_options* options, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream) {
+    return normals_ball_device<double>(ws, points, n, view_dirs, options, (long long*)out_idx, out_normals, (long long*)out_count, (cudaStream_t)stream);
 }
 
 int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
