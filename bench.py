@@ -282,8 +282,10 @@ class Bench:
         # leg gets all CPUs back (restore_affinity).
         self.all_cpus = os.sched_getaffinity(0)
         self.numa_cpus = gpu_local_cpus(self.local)
-        if self.numa_cpus:
+        if self.numa_cpus and not os.environ.get("PCU_BENCH_NO_BIND"):
             os.sched_setaffinity(0, self.numa_cpus)
+        else:
+            self.numa_cpus = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)

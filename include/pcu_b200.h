@@ -240,6 +240,24 @@ int pcu_b200_normals_knn_f32(pcu_b200_workspace* ws, const float* points, int64_
 int pcu_b200_normals_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                              double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream);
 
+/* ---- duplicate removal ---------------------------------------------------
+ * Replaces deduplicate_point_cloud / deduplicate_mesh_vertices (src/remove_duplicates.cpp:108-176, helpers :11-79;
+ * libigl's round + unique_rows underneath).  epsilon > 0: rows are compared after round(p / epsilon) (division in the
+ * cloud's precision, halves away from zero); otherwise as they are.  Unique rows come in ascending lexicographic
+ * order of the compared values.
+ *   out_points (capacity n x 3): points[out_svi];  out_svi (capacity n): for every unique row the FIRST input row of its
+ *   cluster (libigl returns an unspecified member: its row sort is not stable);  out_svj (n): unique row of every input
+ *   row;  faces (may be NULL): (n_faces, face_cols) int32 or int64 vertex indices -> out_faces (capacity n_faces x
+ *   face_cols) holds the re-indexed faces whose corners stay distinct, in their original order.
+ *   out_counts: 3 device int64 = { unique points, surviving faces, faces with a corner outside [0, n) (dropped) }.
+ * DEVICE pointers. */
+int pcu_b200_deduplicate_f32(pcu_b200_workspace* ws, const float* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                             int face_cols, int faces_are_i64, float* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                             int64_t* out_counts, void* stream);
+int pcu_b200_deduplicate_f64(pcu_b200_workspace* ws, const double* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                             int face_cols, int faces_are_i64, double* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                             int64_t* out_counts, void* stream);
+
 /* ---- point-cloud normals from all points in a ball -----------------------
  * Replaces estimate_point_cloud_normals_ball_internal (src/point_cloud_normals.cpp:303-370, estimator :48-113).
  * The neighbourhood of a point is what the reference's call nanoflann radiusSearch(query, ball_radius) returns:

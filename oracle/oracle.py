@@ -344,6 +344,48 @@ def downsample_point_cloud_on_voxel_grid(voxel_size, points, *attribs, min_bound
     return tuple(outs) if len(outs) > 1 else outs[0]
 
 
+# ---- duplicate removal (src/remove_duplicates.cpp:11-79, :108-176; libigl's round + unique_rows) ----
+def deduplicate_point_cloud(points, epsilon, return_index=True):
+    """remove_duplicate_vertices (:11-34) restated with numpy.  The reference calls libigl, which is fetched at build
+    time and is NOT in the reference tree (PARITY UNPINNED: no golden vector exists and the reference cannot be built
+    here; anchored on the published algorithm of igl::round / igl::unique_rows / igl::sortrows and on the properties
+    the reference's own test asserts, tests/test_examples.py:509-520):
+      epsilon > 0: rV = round(V / epsilon) -- division in V's precision, std::round (halves away from zero) -- and the
+      unique rows of rV; else the unique rows of V.  unique_rows = ascending lexicographic row sort, one row per run;
+      SVI = an input row of every run (libigl: whichever its non-stable std::sort puts first; here, like np.unique,
+      the smallest), SVJ = run of every input row; SV = V[SVI]."""
+    points = np.asarray(points)
+    t = points.dtype.type
+    if epsilon > 0:
+        q = points / t(epsilon)
+        # std::round: nearest integer, halves away from zero.  (floor(q + 0.5) would be wrong where q + 0.5 rounds up,
+        # e.g. q = 0.49999997f; q - trunc(q) is exact.)
+        frac = q - np.trunc(q)
+        keyed = np.trunc(q) + np.where(np.abs(frac) >= t(0.5), np.sign(q), 0).astype(points.dtype)
+    else:
+        keyed = points
+    keyed = keyed + t(0)                                                          # -0 -> +0 (they compare equal)
+    _, svi, svj = np.unique(keyed, axis=0, return_index=True, return_inverse=True)
+    svi = svi.astype(np.int32)
+    svj = np.asarray(svj).reshape(-1).astype(np.int32)
+    sv = points[svi]
+    return (sv, svi, svj) if return_index else sv
+
+
+def deduplicate_mesh_vertices(v, f, epsilon, return_index=True):
+    """:36-77 restated: vertices as above; every face is re-indexed through SVJ and dropped when two corners coincide."""
+    v = np.asarray(v)
+    f = np.asarray(f)
+    sv, svi, svj = deduplicate_point_cloud(v, epsilon, True)
+    mapped = svj[f].astype(f.dtype)
+    degenerate = np.zeros(len(f), dtype=bool)
+    for c in range(f.shape[1]):
+        for c2 in range(c + 1, f.shape[1]):
+            degenerate |= mapped[:, c] == mapped[:, c2]
+    sf = mapped[~degenerate]
+    return (sv, sf, svi, svj) if return_index else (sv, sf)
+
+
 # ---- Morton codes (src/morton.cpp, src/common/morton_code.cpp) -----------------------------------------------
 _MORTON_PORT = os.path.join(_HERE, "libpcu_oracle_morton.so")
 _MORTON_REF = os.path.join(_HERE, "_ref", "libpcu_ref_morton.so")

@@ -714,6 +714,23 @@ void voxel_downsample_device(bool is_f64, uintptr_t pts, int64_t n, uintptr_t at
     check(status);
 }
 
+void deduplicate_device(bool is_f64, uintptr_t pts, int64_t n, double epsilon, uintptr_t faces, int64_t nf, int cols, bool faces_i64,
+                        uintptr_t out_pts, uintptr_t out_svi, uintptr_t out_svj, uintptr_t out_faces, uintptr_t out_counts, int device,
+                        uintptr_t stream) {
+    Slot& slot = pool().get(device, stream);
+    int status;
+    {
+        CallScope scope(slot);
+        status = is_f64 ? pcu_b200_deduplicate_f64(slot.ws, (const double*)pts, n, epsilon, (const void*)faces, nf, cols, faces_i64 ? 1 : 0,
+                                                   (double*)out_pts, (int32_t*)out_svi, (int32_t*)out_svj, (void*)out_faces,
+                                                   (int64_t*)out_counts, (void*)stream)
+                        : pcu_b200_deduplicate_f32(slot.ws, (const float*)pts, n, epsilon, (const void*)faces, nf, cols, faces_i64 ? 1 : 0,
+                                                   (float*)out_pts, (int32_t*)out_svi, (int32_t*)out_svj, (void*)out_faces,
+                                                   (int64_t*)out_counts, (void*)stream);
+    }
+    check(status);
+}
+
 // ---- dense pairwise distances / Sinkhorn on device pointers (the Python layer owns the arrays) ----
 void pairwise_device(bool is_f64, uintptr_t a, uintptr_t b, int64_t nb, int64_t n, int64_t m, int d, int norm_kind, double p,
                      uintptr_t out, int device, uintptr_t stream) {
@@ -908,6 +925,7 @@ PYBIND11_MODULE(_pcu_internal, mod) {
     mod.def("_stats_prepared", &stats_prepared_numpy);
     mod.def("_stats_prepared_device", &stats_prepared_device);
     mod.def("_voxel_downsample_device", &voxel_downsample_device);
+    mod.def("_deduplicate_device", &deduplicate_device);
     mod.def("_pairwise_device", &pairwise_device);
     mod.def("_sinkhorn_device", &sinkhorn_device);
     mod.def("morton_encode", &morton_encode, py::arg("pts"), py::arg("num_threads") = -1, py::arg("device") = -1,

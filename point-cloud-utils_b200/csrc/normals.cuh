@@ -177,6 +177,47 @@ __device__ __forceinline__ void walk_ball(const Cloud<T>& cl, const GridHeader<T
     }
 }
 
+// The binning kernels place the points of a cell in arrival order (an atomic counter), which changes from run to run.
+// The ball walk adds its neighbours up in cell order, so for reproducible sums -- and a reproducible random subset --
+// the points of every cell are put in ascending row order first.  One thread per cell; cells hold a few points
+// (insertion sort), the odd crowded cell is heap-sorted in place.
+template <typename T>
+__device__ __forceinline__ void sift_down(Pt<T>* p, unsigned root, unsigned m) {
+    for (;;) {
+        unsigned child = 2 * root + 1;
+        if (child >= m) return;
+        if (child + 1 < m && p[child].i < p[child + 1].i) ++child;
+        if (!(p[root].i < p[child].i)) return;
+        const Pt<T> t = p[root]; p[root] = p[child]; p[child] = t;
+        root = child;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cell_order_kernel(Cloud<T> cl) {
+    grid_dependency_wait();
+    const int ncells = cl.grid->ncells;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+        const unsigned a = cl.cell_start[c], b = cl.cell_start[c + 1];
+        const unsigned m = b - a;
+        if (m < 2) continue;
+        Pt<T>* p = cl.sorted + a;
+        if (m <= 24) {
+            for (unsigned j = 1; j < m; ++j) {
+                const Pt<T> key = p[j];
+                unsigned t = j;
+                while (t > 0 && p[t - 1].i > key.i) { p[t] = p[t - 1]; --t; }
+                p[t] = key;
+            }
+        } else {
+            for (unsigned r = m / 2; r-- > 0;) sift_down<T>(p, r, m);
+            for (unsigned end = m - 1; end > 0; --end) {
+                const Pt<T> t = p[0]; p[0] = p[end]; p[end] = t;
+                sift_down<T>(p, 0, end);
+            }
+        }
+    }
+}
+
 // One thread per point, in CELL order (neighbouring lanes walk overlapping boxes).  normals / keep are indexed by the
 // caller's row.
 template <typename T>

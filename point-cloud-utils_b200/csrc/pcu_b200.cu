@@ -28,6 +28,7 @@
 #include "morton.cuh"
 #include "sinkhorn.cuh"
 #include "voxel.cuh"
+#include "dedup.cuh"
 
 using namespace pcu;
 
@@ -855,6 +856,7 @@ int normals_ball_device(pcu_b200_workspace* ws, const T* points, long long n, co
     bp.radius = o->radius; bp.drop_angle_threshold = o->drop_angle_threshold;
     bp.min_pts = o->min_pts_per_ball; bp.max_pts = o->max_pts_per_ball;
     bp.weight_kind = o->weight_function; bp.seed = o->seed;
+    PCU_LAUNCH((cell_order_kernel<T>), (unsigned)std::min<long long>(((long long)plan.cv.v[0].cell_cap + kThreads - 1) / kThreads, 148 * 64), kThreads, stream, plan.cv.v[0]);
     PCU_LAUNCH((normals_ball_kernel<T>), (unsigned)nblocks, kThreads, stream, plan.cv.v[0], view_dirs, bp, dense, keep);
     mark(ws, 6, stream);
     PCU_LAUNCH(keep_count_kernel, (unsigned)nblocks, kThreads, stream, keep, n, counts);
@@ -863,6 +865,94 @@ int normals_ball_device(pcu_b200_workspace* ws, const T* points, long long n, co
     mark(ws, 7, stream);
     mark(ws, 8, stream);
     return PCU_B200_OK;
+}
+
+// ---- duplicate removal (src/remove_duplicates.cpp) ----------------------------------------
+// Stable LSD radix sort of `n` records between two buffers; returns the buffer holding the sorted records.
+template <typename Rec>
+int radix_sort_records(Rec* a, Rec* b, long long n, int words, unsigned* hist, unsigned long long* totals, unsigned* base, int* constant,
+                       cudaStream_t stream, Rec** sorted) {
+    const unsigned ntiles = (unsigned)((n + kSortTile - 1) / kSortTile);
+    const int bits = (int)sizeof(a->key[0]) * 8;
+    Rec *in = a, *out = b;
+    for (int w = words - 1; w >= 0; --w)          // least significant word first
+        for (int shift = 0; shift < bits; shift += 8) {
+            PCU_LAUNCH((sort_hist_kernel<Rec>), ntiles, kSortThreads, stream, (const Rec*)in, n, w, shift, hist, ntiles);
+            PCU_LAUNCH(sort_scan_rows, kSortBins, kSortThreads, stream, hist, ntiles, totals);
+            PCU_LAUNCH(sort_scan_bins, 1, kSortBins, stream, (const unsigned long long*)totals, n, base, constant);
+            PCU_LAUNCH((sort_scatter_kernel<Rec>), ntiles, kSortThreads, stream, (const Rec*)in, out, n, w, shift, (const unsigned*)hist, ntiles,
+                       (const unsigned*)base, (const int*)constant);
+            std::swap(in, out);
+        }
+    *sorted = in;
+    return PCU_B200_OK;
+}
+
+// faces == nullptr: points only.  out_pts (n, 3), out_svi (n) and out_faces (nf, cols) are sized for the worst case;
+// out_counts[0] = unique points, [1] = surviving faces, [2] = faces with a corner out of range (an error for the caller).
+template <typename T, typename I>
+int dedup_device(pcu_b200_workspace* ws, const T* pts, long long n, double epsilon, const I* faces, long long nf, int cols,
+                 T* out_pts, int* out_svi, int* out_svj, I* out_faces, long long* out_counts, cudaStream_t stream) {
+    using Rec = typename DedupRec<T>::type;
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!pts || n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "points must be a non-empty (n, 3) array");
+    if (n >= 0x7fffffffLL) return fail(PCU_B200_INVALID_ARGUMENT, "point cloud too large (%lld rows)", n);
+    if (!out_pts || !out_svi || !out_svj || !out_counts) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    if (faces != nullptr && (nf < 0 || cols <= 0 || cols > 16 || (nf > 0 && !out_faces)))
+        return fail(PCU_B200_INVALID_ARGUMENT, "faces must be an (m, c) array with 1 <= c <= 16");
+    if (nf >= 0x7fffffffLL) return fail(PCU_B200_INVALID_ARGUMENT, "too many faces (%lld)", nf);
+    PCU_ON_DEVICE(ws);
+    const long long nblocks = (n + kThreads - 1) / kThreads;
+    const long long fblocks = faces ? (nf + kThreads - 1) / kThreads : 0;
+    const unsigned ntiles = (unsigned)((n + kSortTile - 1) / kSortTile);
+    Carver measure(nullptr);
+    struct Scratch { Rec *a, *b; unsigned* hist; unsigned long long* totals; unsigned* base; int* constant; unsigned char* head;
+                     unsigned* counts; unsigned char* fkeep; unsigned* fcounts; unsigned* bad; } sc;
+    auto carve = [&](Carver& cv) {
+        sc.a = cv.take<Rec>((size_t)n);
+        sc.b = cv.take<Rec>((size_t)n);
+        sc.hist = cv.take<unsigned>((size_t)kSortBins * ntiles);
+        sc.totals = cv.take<unsigned long long>(kSortBins);
+        sc.base = cv.take<unsigned>(kSortBins);
+        sc.constant = cv.take<int>(1);
+        sc.head = cv.take<unsigned char>((size_t)n);
+        sc.counts = cv.take<unsigned>((size_t)nblocks);
+        sc.fkeep = cv.take<unsigned char>((size_t)std::max<long long>(1, nf));
+        sc.fcounts = cv.take<unsigned>((size_t)std::max<long long>(1, fblocks));
+        sc.bad = cv.take<unsigned>(1);
+    };
+    carve(measure);
+    PCU_TRY(ensure_arena(ws, measure.off, stream));
+    Carver cv(ws->arena);
+    carve(cv);
+    PCU_CUDA(cudaMemsetAsync(out_counts, 0, 3 * sizeof(long long), stream));
+    PCU_LAUNCH((dedup_keys_kernel<T>), (unsigned)nblocks, kThreads, stream, pts, n, (T)epsilon, sc.a);
+    Rec* sorted = nullptr;
+    PCU_TRY(radix_sort_records<Rec>(sc.a, sc.b, n, 3, sc.hist, sc.totals, sc.base, sc.constant, stream, &sorted));
+    PCU_LAUNCH((dedup_heads_kernel<Rec>), (unsigned)nblocks, kThreads, stream, (const Rec*)sorted, n, sc.head);
+    PCU_LAUNCH(keep_count_kernel, (unsigned)nblocks, kThreads, stream, (const unsigned char*)sc.head, n, sc.counts);
+    PCU_LAUNCH(keep_offsets_kernel, 1, 1024, stream, sc.counts, nblocks, out_counts);
+    PCU_LAUNCH((dedup_emit_kernel<T, Rec>), (unsigned)nblocks, kThreads, stream, (const Rec*)sorted, n, (const unsigned char*)sc.head,
+               (const unsigned*)sc.counts, pts, out_pts, out_svi, out_svj);
+    if (faces != nullptr && nf > 0) {
+        PCU_CUDA(cudaMemsetAsync(sc.bad, 0, sizeof(unsigned), stream));
+        PCU_LAUNCH((dedup_faces_flag_kernel<I>), (unsigned)fblocks, kThreads, stream, faces, nf, cols, n, (const int*)out_svj, sc.fkeep, sc.bad);
+        PCU_LAUNCH(keep_count_kernel, (unsigned)fblocks, kThreads, stream, (const unsigned char*)sc.fkeep, nf, sc.fcounts);
+        PCU_LAUNCH(keep_offsets_kernel, 1, 1024, stream, sc.fcounts, fblocks, out_counts + 1);
+        PCU_LAUNCH((dedup_faces_emit_kernel<I>), (unsigned)fblocks, kThreads, stream, faces, nf, cols, (const int*)out_svj,
+                   (const unsigned char*)sc.fkeep, (const unsigned*)sc.fcounts, out_faces);
+        PCU_LAUNCH(widen_counter_kernel, 1, 1, stream, sc.bad, out_counts + 2);
+    }
+    return PCU_B200_OK;
+}
+
+template <typename T>
+int dedup_dispatch(pcu_b200_workspace* ws, const T* pts, long long n, double epsilon, const void* faces, long long nf, int cols,
+                   int faces_are_i64, T* out_pts, int* out_svi, int* out_svj, void* out_faces, long long* out_counts, cudaStream_t stream) {
+    if (faces_are_i64)
+        return dedup_device<T, long long>(ws, pts, n, epsilon, (const long long*)faces, nf, cols, out_pts, out_svi, out_svj,
+                                          (long long*)out_faces, out_counts, stream);
+    return dedup_device<T, int>(ws, pts, n, epsilon, (const int*)faces, nf, cols, out_pts, out_svi, out_svj, (int*)out_faces, out_counts, stream);
 }
 
 // ---- Morton codes -------------------------------------------------------------------
@@ -1429,6 +1519,19 @@ int pcu_b200_normals_ball_f32(pcu_b200_workspace* ws, const float* points, int64
 int pcu_b200_normals_ball_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,
                               const pcu_b200_ball_options* options, int64_t* out_idx, double* out_normals, int64_t* out_count, void* stream) {
     return normals_ball_device<double>(ws, points, n, view_dirs, options, (long long*)out_idx, out_normals, (long long*)out_count, (cudaStream_t)stream);
+}
+
+int pcu_b200_deduplicate_f32(pcu_b200_workspace* ws, const float* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                             int face_cols, int faces_are_i64, float* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                             int64_t* out_counts, void* stream) {
+    return dedup_dispatch<float>(ws, points, n, epsilon, faces, n_faces, face_cols, faces_are_i64, out_points, out_svi, out_svj, out_faces,
+                                 (long long*)out_counts, (cudaStream_t)stream);
+}
+int pcu_b200_deduplicate_f64(pcu_b200_workspace* ws, const double* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                             int face_cols, int faces_are_i64, double* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                             int64_t* out_counts, void* stream) {
+    return dedup_dispatch<double>(ws, points, n, epsilon, faces, n_faces, face_cols, faces_are_i64, out_points, out_svi, out_svj, out_faces,
+                                  (long long*)out_counts, (cudaStream_t)stream);
 }
 
 int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
