@@ -234,30 +234,6 @@ def run_reference(args, wl_key):
 
 
 # ------------------------------------------------------------------------------------------------
-def gpu_local_cpus(gpu_index):
-    """CPUs of the NUMA node the GPU hangs off (NVML's ideal CPU affinity), or None when it cannot be told."""
-    try:
-        import pynvml
-        import torch
-        pynvml.nvmlInit()
-        h = None
-        try:   # CUDA and NVML may enumerate differently (CUDA_VISIBLE_DEVICES): go through the UUID when torch has it
-            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
-            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
-        except Exception:
-            h = None
-        if h is None:
-            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        words = (os.cpu_count() + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
-        allowed = os.sched_getaffinity(0)
-        cpus = [c for c in cpus if c in allowed]
-        return cpus or None
-    except Exception:
-        return None
-
-
 class Bench:
     """One rank of the GPU arm."""
 
@@ -276,24 +252,11 @@ class Bench:
             raise SystemExit("bench.py needs a B200: the product has no CPU path")
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
-        # Host buffers are first touched (and pinned) by this process: keep it on the CPUs next to its GPU, or the
-        # kernel may start it on the other socket and every H2D crosses the socket interconnect (measured on these
-        # boxes: 24 MB in 0.43 ms local, up to 1.0 ms remote, varying from process to process).  The CPU baseline
-        # leg gets all CPUs back (restore_affinity).
-        self.all_cpus = os.sched_getaffinity(0)
-        self.numa_cpus = gpu_local_cpus(self.local)
-        if self.numa_cpus and not os.environ.get("PCU_BENCH_NO_BIND"):
-            os.sched_setaffinity(0, self.numa_cpus)
-        else:
-            self.numa_cpus = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
         self.stream = torch.cuda.current_stream(self.dev).cuda_stream
         self.exchange = self.bmod.ScalarSumExchange(self.dev)
-
-    def restore_affinity(self):
-        os.sched_setaffinity(0, self.all_cpus)
 
     def barrier(self):
         if self.world > 1:
@@ -526,7 +489,6 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------
     cpu = None
-    B.restore_affinity()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
@@ -574,8 +536,8 @@ def main():
                                 "stream (overlaps the next step's binning)") if world > 1 else "1 GPU",
                 "l2": "inputs (24 MB) < L2: a 256 MiB buffer is overwritten before every timed step, outside the interval",
                 "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
-                "host_placement": ("process bound to the %d CPUs next to its GPU (NVML affinity) while it allocates and copies "
-                                   "host buffers; all CPUs again for the CPU baseline" % len(B.numa_cpus)) if B.numa_cpus else "no CPU binding",
+                "e2e_note": ("e2e is PCIe-bound: e2e.stage_ms['bbox+grid'] is the wait for the 24 MB of input; that copy ran at "
+                             "15 - 55 GB/s depending on the box and the moment (shared hosts), CPU placement made no difference"),
                 "ratio_note": "N GPUs process N pairs per step; the reference arm is one CPU process: a throughput ratio",
             },
             "clocks": res["clocks"],
