@@ -366,6 +366,11 @@ int pcu_b200_normals_ball_host_f32(pcu_b200_workspace* ws, const float* points, 
 int pcu_b200_normals_ball_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,
                                    const pcu_b200_ball_options* options, int64_t* out_idx, double* out_normals, int64_t* out_count);
 
+/* Timeline of the last kd-tree build on the workspace's device (globaltimer, ns; synchronises the device):
+ * [0] start, [1] set-up done, [2 + l] grid-wide level l done (l < 28), [30] grid-wide phase done, [31] last CTA done,
+ * [32] grid-wide levels, [33] subtrees built by single CTAs. */
+int pcu_b200_debug_kd_times(pcu_b200_workspace* ws, uint64_t* out40);
+
 /* ---- diagnostics ----------------------------------------------------------------------------
  * Builds the kd-tree replica used by the tie replay for HOST points and copies it out, so tests can
  * compare it node for node with the reference's tree.  order: (m) slot -> point index (nanoflann's

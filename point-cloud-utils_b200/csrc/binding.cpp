@@ -949,6 +949,12 @@ PYBIND11_MODULE(_pcu_internal, mod) {
     mod.def("_knn_device", &knn_device);
     mod.def("_stats_device", &stats_device);
     mod.def("_resolve_witness_device", &resolve_witness_device);
+    mod.def("_debug_kd_times", [](int device, py::object stream) {
+        Slot& slot = pool().get(current_device_or_default(device), stream.is_none() ? kHostKey : stream.cast<uintptr_t>());
+        std::array<uint64_t, 40> t{};
+        { CallScope scope(slot); check(pcu_b200_debug_kd_times(slot.ws, t.data())); }
+        return t;
+    }, py::arg("device") = -1, py::arg("stream") = py::none());
     mod.def("_debug_kd_tree", &debug_kd_tree, py::arg("points"), py::arg("max_points_per_leaf") = 10,
             py::arg("device") = -1);
     mod.def("_stats_nbytes", []() { return (int)sizeof(pcu_b200_nn_stats); });

@@ -562,10 +562,20 @@ __device__ void kd_build_subtree(const KdReplayBuffers<T>& b, const T* __restric
     }
 }
 
+// Diagnostics: globaltimer stamps of the last build (ns): [0] start, [1] after the set-up, [2 + l] after grid-wide
+// level l (l < 28), [30] end of the grid-wide phase, [31] the last CTA's end of the second phase, [32] grid-wide levels,
+// [33] handed-off subtrees.  Read with pcu_b200_debug_kd_times.
+__device__ unsigned long long g_kd_times[40];
+__device__ __forceinline__ unsigned long long kd_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // The whole build in one cooperative launch.  `gate` (may be null): device counter; when it reads
 // zero nobody needs the tree and every CTA returns immediately.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b, const T* __restrict__ pts, int m,
+__global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 ? 6 : 4)) kd_build_kernel(KdReplayBuffers<T> b, const T* __restrict__ pts, int m,
                                                             int leaf_cap, const unsigned* __restrict__ gate, KdPrune<T> pr) {
     namespace cg = cooperative_groups;
     using R = Real<T>;
@@ -587,6 +597,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
 
     for (int s = gtid; s < m; s += gsize) { b.order[s] = s; b.node_of[s] = 0; }
     if (gtid == 0) {
+        g_kd_times[0] = kd_now(); g_kd_times[31] = 0ull;
         KdNode<T> nd{};
         nd.feat = -2; nd.first = 0; nd.last = m; nd.kid0 = nd.kid1 = -1; nd.parent = -1; nd.side = 0;
         for (int d = 0; d < 3; ++d) { nd.tight_lo[d] = ordered<T>(R::inf()); nd.tight_hi[d] = ordered<T>(-R::inf()); }
@@ -597,6 +608,7 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
     grid.sync();
     for (int s = gtid; s < m_warp; s += gsize) kd_tight_box_slot<T>(b, pts, s, m);
     grid.sync();
+    if (gtid == 0) g_kd_times[1] = kd_now();
 
     for (int level = 0; level < 4096; ++level) {
         const int lb = *(volatile int*)&b.counters->level_begin, le = *(volatile int*)&b.counters->level_end;
@@ -643,11 +655,14 @@ __global__ void __launch_bounds__(kThreads) kd_build_kernel(KdReplayBuffers<T> b
             *b.counters = c;
         }
         grid.sync();
+        if (gtid == 0 && level < 28) g_kd_times[2 + level] = kd_now();
         if (*(volatile int*)&b.counters->done) break;
     }
     // second phase: the subtrees handed off above, one CTA each, all of them side by side
     const int n_local = *(volatile int*)&b.counters->n_local;
+    if (gtid == 0) { g_kd_times[30] = kd_now(); g_kd_times[32] = (unsigned long long)b.counters->levels; g_kd_times[33] = (unsigned long long)n_local; }
     for (int i = blockIdx.x; i < n_local; i += gridDim.x) kd_build_subtree<T>(b, pts, b.local_roots[i], leaf_cap, pr, n_flagged);
+    if (threadIdx.x == 0) atomicMax(&g_kd_times[31], kd_now());
 }
 
 // ---- search ---------------------------------------------------------------------------------------
@@ -793,10 +808,9 @@ int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int le
     int blocks_per_sm = cached_blocks[slot].load(std::memory_order_acquire), sms = cached_sms[slot].load(std::memory_order_acquire);
     if (blocks_per_sm == 0 || slot != dev) {
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-        int f32 = 0, f64 = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f32, kd_build_kernel<float>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f64, kd_build_kernel<double>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
-        blocks_per_sm = std::max(1, std::min(8, std::min(f32, f64)));   // enough threads to cover the latency of the element passes
+        int fit = 0;   // (the statics above are per instantiation: fp32 and fp64 builds have their own limits)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, kd_build_kernel<T>, kThreads, 0) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+        blocks_per_sm = std::max(1, std::min(8, fit));   // enough threads to cover the latency of the element passes
         cached_sms[slot].store(sms, std::memory_order_release);
         cached_blocks[slot].store(blocks_per_sm, std::memory_order_release);
     }

@@ -323,7 +323,16 @@ float occupancy_for(const pcu_b200_workspace* ws, int k) {
     // k = 1: 1.5 points per cell (measured on C3, profiles/r2d_occ.log: the sweep visits fewer candidates -- 139 -> 124 us --
     // while the scan over more cells and the far pass grow by less; 1.25 and 1.75 are within 1 % of it, 1.0 loses 8 %)
     if (k <= 1) return 1.5f;
-    return std::max(2.0f, 0.5f * (float)k);
+    // k > 1 (thread-per-query lists): measured on 2 x 10^6 queries against 10^6 uniform points (profiles/r2r_knn_occ.log) --
+    // fewer points per cell mean fewer candidates in the 27 cells but more queries left to the slow warp pass; the best
+    // trade-off was 3 at k = 4 (0.239 vs 0.277 ms per 10^6 queries at 2), 4 at k = 8, 7 at k = 16, 12 at k = 32
+    // (2.78 vs 3.02 ms at 16).  Piecewise linear through those points.
+    static const float ks[] = {2.f, 4.f, 8.f, 16.f, 32.f}, occ[] = {2.f, 3.f, 4.f, 7.f, 12.f};
+    const float kf = (float)k;
+    if (kf <= ks[0]) return occ[0];
+    for (int i = 1; i < 5; ++i)
+        if (kf <= ks[i]) return occ[i - 1] + (occ[i] - occ[i - 1]) * (kf - ks[i - 1]) / (ks[i] - ks[i - 1]);
+    return 0.375f * kf;     // k > 32: the generic pyramid path, same slope as the last segment
 }
 
 // What one call works on: `batch` independent pairs (first cloud: n points, second: m points).
@@ -1532,6 +1541,14 @@ int pcu_b200_deduplicate_f64(pcu_b200_workspace* ws, const double* points, int64
                              int64_t* out_counts, void* stream) {
     return dedup_dispatch<double>(ws, points, n, epsilon, faces, n_faces, face_cols, faces_are_i64, out_points, out_svi, out_svj, out_faces,
                                   (long long*)out_counts, (cudaStream_t)stream);
+}
+
+int pcu_b200_debug_kd_times(pcu_b200_workspace* ws, uint64_t* out40) {
+    if (!ws || !out40) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
+    PCU_ON_DEVICE(ws);
+    PCU_CUDA(cudaDeviceSynchronize());
+    PCU_CUDA(cudaMemcpyFromSymbol(out40, g_kd_times, sizeof(unsigned long long) * 40));
+    return PCU_B200_OK;
 }
 
 int pcu_b200_batched_chamfer_f32(pcu_b200_workspace* ws, const float* x, const float* y, int64_t batch, int64_t n,
