@@ -73,7 +73,9 @@ struct KdScope {
     bool local;
     int range_end;
     unsigned total;
+    const unsigned* tile_off;   // grid-wide phases: the tile offsets in THIS CTA's shared memory (null: in scan_partial)
 };
+constexpr int kKdSharedTiles = 4096;   // tile offsets a CTA keeps to itself (clouds up to kKdTile * 4096 = 8.4 M points)
 
 template <typename T>
 struct KdReplayBuffers {
@@ -352,7 +354,7 @@ __device__ __forceinline__ unsigned kd_flag(const KdReplayBuffers<T>& b, const T
 template <typename T>
 __device__ __forceinline__ unsigned kd_prefix(const KdReplayBuffers<T>& b, int s, const KdScope& sc) {
     if (sc.local) return s == sc.range_end ? sc.total : b.prefix[s];
-    return b.prefix[s] + b.scan_partial[s / kKdTile];
+    return b.prefix[s] + (sc.tile_off != nullptr ? sc.tile_off[s / kKdTile] : b.scan_partial[s / kKdTile]);
 }
 
 // Who trades places with whom (nanoflann.hpp:1125-1160): inside a node, with F = number of flagged
@@ -363,15 +365,11 @@ template <typename T, int kSweep>
 __device__ __forceinline__ void kd_partner_slot(const KdReplayBuffers<T>& b, int s, const KdScope& sc) {
     const int node = b.node_of[s];
     if (node < 0) return;
-    KdNode<T>& nd = b.nodes[node];
+    const KdNode<T>& nd = b.nodes[node];
     if (nd.feat < 0) return;
     const int lo = kSweep == 1 ? nd.first : nd.first + nd.n_less;
     const unsigned at_lo = kd_prefix<T>(b, lo, sc), at_last = kd_prefix<T>(b, nd.last, sc);
-    const int F = (int)(at_last - at_lo);
-    if (s == nd.first) {
-        if (kSweep == 1) { nd.n_less = F; nd.n_less_eq = F; }   // sweep 2, when it runs, overwrites n_less_eq
-        else nd.n_less_eq = nd.n_less + F;
-    }
+    const int F = (int)(at_last - at_lo);   // (kd_children_node, in the same phase, stores it as n_less / n_less_eq)
     if (s < lo) return;
     const unsigned here = kd_prefix<T>(b, s, sc), next = kd_prefix<T>(b, s + 1, sc);
     const bool flagged = next != here;
@@ -400,11 +398,22 @@ __device__ __forceinline__ void kd_exchange_slot(const KdReplayBuffers<T>& b, in
 }
 
 // children of one split node (nanoflann.hpp:1098-1110, :1033-1045)
-template <typename T>
-__device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, int id, int* next_list = nullptr, int* next_count = nullptr) {
+// Runs in the partner phase of sweep kSweep (the prefix sums of that sweep are final, nobody reads n_less_eq and
+// only sweep 2 reads n_less, which sweep 1 left): stores the sweep's counts -- what planeSplit returns as lim1 / lim2 --
+// and, when this is the node's last sweep (`create`), allocates the two children.
+template <typename T, int kSweep>
+__device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, int id, const KdScope& sc, bool create,
+                                                 int* next_list = nullptr, int* next_count = nullptr) {
     using R = Real<T>;
     KdNode<T>& nd = b.nodes[id];
     if (nd.feat < 0) return;
+    {
+        const int lo = kSweep == 1 ? nd.first : nd.first + nd.n_less;
+        const int F = (int)(kd_prefix<T>(b, nd.last, sc) - kd_prefix<T>(b, lo, sc));
+        if (kSweep == 1) { nd.n_less = F; nd.n_less_eq = F; }   // sweep 2, when it runs, overwrites n_less_eq
+        else nd.n_less_eq = nd.n_less + F;
+    }
+    if (!create) return;
     const int count = nd.last - nd.first;
     int left;
     if (nd.n_less > count / 2) left = nd.n_less;
@@ -436,7 +445,7 @@ __device__ __forceinline__ void kd_children_node(const KdReplayBuffers<T>& b, in
 // (after a grid barrier) the first CTA turns the totals into tile offsets.
 template <typename T, int kSweep>
 __device__ __forceinline__ void kd_scan_phase(cooperative_groups::grid_group& grid, const KdReplayBuffers<T>& b,
-                                              const T* __restrict__ pts, int m) {
+                                              const T* __restrict__ pts, int m, unsigned* tile_off) {
     const int count = m + 1;
     const int ntiles = (count + kKdTile - 1) / kKdTile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -459,6 +468,28 @@ __device__ __forceinline__ void kd_scan_phase(cooperative_groups::grid_group& gr
         if (threadIdx.x == 0) b.scan_partial[tile] = total;
     }
     grid.sync();
+    if (tile_off != nullptr) {
+        // every CTA turns the tile totals into offsets for itself (shared memory): no serial CTA, no second barrier
+        constexpr int kPer = kKdSharedTiles / kThreads;
+        unsigned v[kPer];
+        unsigned sum = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = threadIdx.x * kPer + k;
+            v[k] = i < ntiles ? b.scan_partial[i] : 0u;
+            sum += v[k];
+        }
+        unsigned total;
+        unsigned run = kd_block_exclusive_scan(sum, &total);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int i = threadIdx.x * kPer + k;
+            if (i < ntiles) tile_off[i] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        return;
+    }
     if (blockIdx.x == 0) {
         unsigned carry = 0;
         for (int base = 0; base < ntiles; base += kThreads) {
@@ -526,21 +557,22 @@ __device__ void kd_build_subtree(const KdReplayBuffers<T>& b, const T* __restric
         for (int i = threadIdx.x; i < ncur; i += blockDim.x) kd_decide_node<T>(b, cur[i], leaf_cap, pr, n_flagged, false);
         __syncthreads();
         kd_scan_subtree<T, 1>(b, pts, first, last, &s_total, &s_any_eq);
-        KdScope sc{true, last, s_total};
+        KdScope sc{true, last, s_total, nullptr};
+        const bool second = s_any_eq != 0;   // stable: last written before the barrier that ended the scan
         for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_partner_slot<T, 1>(b, s, sc);
+        for (int i = threadIdx.x; i < ncur; i += blockDim.x) kd_children_node<T, 1>(b, cur[i], sc, !second, nxt, &s_count[1]);
         __syncthreads();
         for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_exchange_slot<T, 1>(b, s, sc);
         __syncthreads();
-        if (s_any_eq != 0) {
+        if (second) {
             kd_scan_subtree<T, 2>(b, pts, first, last, &s_total, &s_any_eq);
             sc.total = s_total;
             for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_partner_slot<T, 2>(b, s, sc);
+            for (int i = threadIdx.x; i < ncur; i += blockDim.x) kd_children_node<T, 2>(b, cur[i], sc, true, nxt, &s_count[1]);
             __syncthreads();
             for (int s = first + threadIdx.x; s < last; s += blockDim.x) kd_exchange_slot<T, 2>(b, s, sc);
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < ncur; i += blockDim.x) kd_children_node<T>(b, cur[i], nxt, &s_count[1]);
-        __syncthreads();
         for (int s = warp_first + threadIdx.x; s < ((last + 31) & ~31); s += blockDim.x) {
             const bool mine = s >= first && s < last;
             if (mine) {
@@ -590,7 +622,9 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 ? 6 : 4)) kd_build_k
         if (nt <= (unsigned)kKdMaxPruneQueries) n_flagged = nt;
     }
     cg::grid_group grid = cg::this_grid();
-    const KdScope grid_scope{false, 0, 0u};
+    __shared__ unsigned s_tile_off[kKdSharedTiles];
+    unsigned* const tile_off = (m + 1 + kKdTile - 1) / kKdTile <= kKdSharedTiles ? s_tile_off : nullptr;
+    const KdScope grid_scope{false, 0, 0u, tile_off};
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int gsize = gridDim.x * blockDim.x;
     const int m_warp = (m + 31) & ~31;            // whole warps take part in the tight-box reduction
@@ -615,23 +649,24 @@ __global__ void __launch_bounds__(kThreads, (sizeof(T) == 4 ? 6 : 4)) kd_build_k
         for (int id = lb + gtid; id < le; id += gsize) kd_decide_node<T>(b, id, leaf_cap, pr, n_flagged, true);
         grid.sync();
         // sweep 1: strictly-less-than-the-cut to the front
-        kd_scan_phase<T, 1>(grid, b, pts, m);
+        kd_scan_phase<T, 1>(grid, b, pts, m, tile_off);
+        const bool second = *(volatile int*)&b.counters->any_eq != 0;
         for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 1>(b, s, grid_scope);
+        for (int id = lb + gtid; id < le; id += gsize) kd_children_node<T, 1>(b, id, grid_scope, !second);
         grid.sync();
         for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 1>(b, s, grid_scope);
         grid.sync();
         // sweep 2: equal-to-the-cut next.  planeSplit's second loop (nanoflann.hpp:1143-1158) moves nothing
         // when no point of the node equals the cut (lim2 == lim1); any_eq was raised by sweep 1's scan and
         // is stable since the barrier that ended it, so the whole grid takes the same branch.
-        if (*(volatile int*)&b.counters->any_eq != 0) {
-            kd_scan_phase<T, 2>(grid, b, pts, m);
+        if (second) {
+            kd_scan_phase<T, 2>(grid, b, pts, m, tile_off);
             for (int s = gtid; s < m; s += gsize) kd_partner_slot<T, 2>(b, s, grid_scope);
+            for (int id = lb + gtid; id < le; id += gsize) kd_children_node<T, 2>(b, id, grid_scope, true);
             grid.sync();
             for (int s = gtid; s < m; s += gsize) kd_exchange_slot<T, 2>(b, s, grid_scope);
             grid.sync();
         }
-        for (int id = lb + gtid; id < le; id += gsize) kd_children_node<T>(b, id);
-        grid.sync();
         // slots move down to the child that now owns them (slots of leaves retire) and immediately
         // contribute to that child's tight box
         for (int s = gtid; s < m_warp; s += gsize) {
