@@ -29,7 +29,10 @@
  *     synchronising; results are valid once the stream reaches that point.  "host" entry points
  *     take HOST pointers (pinned or pageable), copy them to device staging owned by the workspace
  *     on the workspace's own streams -- the copy of the second cloud overlaps the first kernels --
- *     and return after the results have landed in the caller's buffers.
+ *     and return after the results have landed in the caller's buffers.  Page-locked inputs are
+ *     DMA'd as they are; pageable inputs of 4 MB and more go through a 32 MB page-locked ring of
+ *     the workspace, filled by eight copy threads in 512 KB chunks and drained in transfers of up
+ *     to 4 MB (pcu_b200_options::host_staging; the threads start with the first such copy).
  *   - Scratch grows with stream-ordered allocation (cudaMallocAsync): no entry point synchronises
  *     the device.  A workspace serves one stream at a time; a call on another stream than the
  *     previous one is ordered after it on the device.
@@ -92,6 +95,9 @@ typedef struct pcu_b200_options {
                              /* zero slack (every walk hits a stub, which exercises the full-rebuild path)        */
     int binning;             /* 0: automatic; 1: always the multi-launch grid build; 2: the one-CTA-per-cloud     */
                              /* build whenever a cloud's cell counters fit in shared memory (diagnostic only)    */
+    int host_staging;        /* host entry points, inputs of >= 4 MB: 0 pageable memory goes through the          */
+                             /* workspace's pinned ring filled by copy threads, pinned memory is DMA'd as it is;  */
+                             /* 1 always the ring; 2 never (plain cudaMemcpyAsync: the driver stages)             */
 } pcu_b200_options;
 
 /* ---- library / error plumbing ------------------------------------------------------------ */

@@ -166,7 +166,7 @@ py::array_t<T> result_array(py::ssize_t rows, py::ssize_t cols) {
     return py::array_t<T>({rows, cols});
 }
 
-struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; int binning = 0; };
+struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; int binning = 0; int host_staging = 0; };
 Options& defaults() { static Options o; return o; }
 
 // Validates the per-call options (with the GIL held); they are applied to the workspace inside the
@@ -178,6 +178,7 @@ pcu_b200_options make_options(int max_points_per_leaf) {
     o.cell_occupancy = defaults().occupancy;
     o.disable_tie_replay = defaults().disable_replay;
     o.binning = defaults().binning;
+    o.host_staging = defaults().host_staging;
     return o;
 }
 
@@ -987,13 +988,15 @@ PYBIND11_MODULE(_pcu_internal, mod) {
         for (int i = 0; i < n; ++i) d[py::str(pcu_b200_profile_stage_name(i))] = ms[i];
         return d;
     });
-    mod.def("_set_defaults", [](float cell_occupancy, int disable_tie_replay, int binning) {
+    mod.def("_set_defaults", [](float cell_occupancy, int disable_tie_replay, int binning, int host_staging) {
+        if (host_staging < 0 || host_staging > 2) throw py::value_error("host_staging must be 0 (auto), 1 (always) or 2 (never)");
+        defaults().host_staging = host_staging;
         if (disable_tie_replay < 0 || disable_tie_replay > 3) throw py::value_error("disable_tie_replay must be 0 .. 3");
         if (binning < 0 || binning > 2) throw py::value_error("binning must be 0 (auto), 1 (multi-launch) or 2 (one CTA per cloud)");
         defaults().occupancy = cell_occupancy;
         defaults().disable_replay = disable_tie_replay;
         defaults().binning = binning;
-    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = 0, py::arg("binning") = 0);
+    }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = 0, py::arg("binning") = 0, py::arg("host_staging") = 0);
     mod.def("_release_workspaces", []() { pool().clear(); });
     mod.def("_release_pinned_results", []() { pinned_pool().clear(false); });
     // destroy workspaces and cached pinned blocks before the CUDA context goes away at interpreter exit

@@ -1,7 +1,23 @@
 // host_entry.inl -- HOST-pointer conveniences of the C ABI: H2D, the device entry point, D2H,
-// one synchronisation at the end.  cudaMemcpyAsync takes the caller's buffers as they are: pinned
-// memory is DMA'd directly, pageable memory goes through the driver's staging.
+// one synchronisation at the end.  Inputs in page-locked memory are DMA'd as they are; large inputs in ordinary
+// (pageable) memory -- what a numpy caller holds -- go through the workspace's pinned ring, filled by copy threads
+// (staging.h); small ones are left to the driver's own staging.
 namespace {
+
+// dst (device) <- src (host), in the order of `stream`
+int h2d(pcu_b200_workspace* ws, void* dst, const void* src, size_t bytes, cudaStream_t stream) {
+    if (ws->opts.host_staging != 2 && (ws->opts.host_staging == 1 || HostStager::wants(src, bytes))) {
+        if (!ws->stager) ws->stager = new (std::nothrow) HostStager();
+        if (ws->stager) {
+            const cudaError_t e = ws->stager->copy(dst, src, bytes, stream);
+            if (e != cudaSuccess) return fail(PCU_B200_CUDA_ERROR, "staged host-to-device copy failed: %s", cudaGetErrorString(e));
+            return PCU_B200_OK;
+        }
+    }
+    PCU_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return PCU_B200_OK;
+}
+
 
 template <typename T>
 int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* dataset, long long m, int k, int squared,
@@ -26,8 +42,8 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     carve(cv, dq, dd, od, oi, nt);
     cudaStream_t st = ws->own_stream;
     mark(ws, 9, st);
-    PCU_CUDA(cudaMemcpyAsync(dq, query, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
-    PCU_CUDA(cudaMemcpyAsync(dd, dataset, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
+    PCU_TRY(h2d(ws, dq, query, sizeof(T) * 3 * n, st));
+    PCU_TRY(h2d(ws, dd, dataset, sizeof(T) * 3 * m, st));
     PCU_TRY(knn_device<T>(ws, dq, n, dd, m, k, squared, od, oi, nt, st));
     PCU_CUDA(cudaMemcpyAsync(out_dist, od, sizeof(T) * n * k, cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaMemcpyAsync(out_idx, oi, sizeof(long long) * n * k, cudaMemcpyDeviceToHost, st));
@@ -77,11 +93,16 @@ int stats_host(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long
     PCU_CUDA(cudaEventRecord(ws->arrived[0], st));
     PCU_CUDA(cudaStreamWaitEvent(ws->copy_stream, ws->arrived[0], 0));
     mark(ws, 9, st);
-    PCU_CUDA(cudaMemcpyAsync(da, a, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, ws->copy_stream));
+    PCU_TRY(h2d(ws, da, a, sizeof(T) * 3 * n, ws->copy_stream));
     PCU_CUDA(cudaEventRecord(ws->arrived[0], ws->copy_stream));
-    if (prepared == nullptr) PCU_CUDA(cudaMemcpyAsync(db, b, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, ws->copy_stream));
-    PCU_CUDA(cudaEventRecord(ws->arrived[1], ws->copy_stream));
-    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, dr->stats, both ? &dr->value : nullptr, st, ws->arrived, prepared));
+    // the second cloud's copy is issued from inside the launch sequence, after the first cloud's passes have been
+    // enqueued: a staged (pageable) copy keeps this thread busy while the GPU already bins the first cloud
+    const std::function<int()> second_copy = [&]() -> int {
+        if (prepared == nullptr) PCU_TRY(h2d(ws, db, b, sizeof(T) * 3 * m, ws->copy_stream));
+        PCU_CUDA(cudaEventRecord(ws->arrived[1], ws->copy_stream));
+        return PCU_B200_OK;
+    };
+    PCU_TRY(stats_device<T>(ws, da, n, db, m, both, dr->stats, both ? &dr->value : nullptr, st, ws->arrived, prepared, &second_copy));
     StatsResult<T>* hr = reinterpret_cast<StatsResult<T>*>(ws->host_slot);
     auto fetch = [&]() -> int {
         PCU_CUDA(cudaMemcpyAsync(hr, dr, sizeof(StatsResult<T>), cudaMemcpyDeviceToHost, st));
@@ -128,8 +149,8 @@ int batched_chamfer_host(pcu_b200_workspace* ws, const T* x, const T* y, long lo
     Carver cv(ws->io);
     carve(cv, dx, dy, dv, dsum);
     cudaStream_t st = ws->own_stream;
-    PCU_CUDA(cudaMemcpyAsync(dx, x, sizeof(T) * 3 * n * batch, cudaMemcpyHostToDevice, st));
-    PCU_CUDA(cudaMemcpyAsync(dy, y, sizeof(T) * 3 * m * batch, cudaMemcpyHostToDevice, st));
+    PCU_TRY(h2d(ws, dx, x, sizeof(T) * 3 * n * batch, st));
+    PCU_TRY(h2d(ws, dy, y, sizeof(T) * 3 * m * batch, st));
     PCU_TRY(batched_chamfer_device<T>(ws, dx, dy, batch, n, m, dv, out_sum ? dsum : nullptr, st));
     PCU_CUDA(cudaMemcpyAsync(out_per_pair, dv, sizeof(T) * batch, cudaMemcpyDeviceToHost, st));
     if (out_sum) PCU_CUDA(cudaMemcpyAsync(out_sum, dsum, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -161,8 +182,8 @@ int normals_host(pcu_b200_workspace* ws, const T* points, long long n, const T* 
     PCU_TRY(ensure_io(ws, measure.off, st));
     Carver cv(ws->io);
     carve(cv, dp, dv, di, dn, dc);
-    PCU_CUDA(cudaMemcpyAsync(dp, points, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
-    if (view_dirs) PCU_CUDA(cudaMemcpyAsync(dv, view_dirs, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    PCU_TRY(h2d(ws, dp, points, sizeof(T) * 3 * n, st));
+    if (view_dirs) PCU_TRY(h2d(ws, dv, view_dirs, sizeof(T) * 3 * n, st));
     PCU_TRY(device_call(dp, view_dirs ? dv : (const T*)nullptr, di, dn, dc, st));
     long long* hc = reinterpret_cast<long long*>(ws->host_slot);
     PCU_CUDA(cudaMemcpyAsync(hc, dc, sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -204,7 +225,7 @@ int cloud_prepare_host(pcu_b200_workspace* ws, const T* points, long long n, pcu
     PCU_ON_DEVICE(ws);
     cudaStream_t st = ws->own_stream;
     PCU_TRY(ensure_io(ws, align_up(sizeof(T) * 3 * (size_t)n), st));
-    PCU_CUDA(cudaMemcpyAsync(ws->io, points, sizeof(T) * 3 * n, cudaMemcpyHostToDevice, st));
+    PCU_TRY(h2d(ws, ws->io, points, sizeof(T) * 3 * n, st));
     PCU_TRY(cloud_prepare_device<T>(ws, reinterpret_cast<const T*>(ws->io), n, out, st));
     PCU_CUDA(cudaStreamSynchronize(st));
     return PCU_B200_OK;
@@ -226,8 +247,8 @@ int morton_host(pcu_b200_workspace* ws, const void* in_a, size_t bytes_a, const 
     unsigned char* da = cv.take<unsigned char>(bytes_a);
     unsigned char* db = cv.take<unsigned char>(bytes_b ? bytes_b : 1);
     unsigned char* dout = cv.take<unsigned char>(bytes_out);
-    PCU_CUDA(cudaMemcpyAsync(da, in_a, bytes_a, cudaMemcpyHostToDevice, st));
-    if (bytes_b) PCU_CUDA(cudaMemcpyAsync(db, in_b, bytes_b, cudaMemcpyHostToDevice, st));
+    PCU_TRY(h2d(ws, da, in_a, bytes_a, st));
+    if (bytes_b) PCU_TRY(h2d(ws, db, in_b, bytes_b, st));
     PCU_TRY(call(da, db, dout, st));
     PCU_CUDA(cudaMemcpyAsync(out, dout, bytes_out, cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaStreamSynchronize(st));
@@ -250,7 +271,7 @@ int debug_kd_tree(pcu_b200_workspace* ws, const T* points, long long m, int leaf
     rb.carve(cv, m);
     dpts = cv.take<T>((size_t)3 * m);
     cudaStream_t st = ws->own_stream;
-    PCU_CUDA(cudaMemcpyAsync(dpts, points, sizeof(T) * 3 * m, cudaMemcpyHostToDevice, st));
+    PCU_TRY(h2d(ws, dpts, points, sizeof(T) * 3 * m, st));
     const int rs = build_kd_replica<T>(rb, dpts, m, leaf, nullptr, KdPrune<T>{}, st, g_launches);
     if (rs != PCU_B200_OK) return fail(rs, "kd replica build failed: %s", cudaGetErrorString(cudaGetLastError()));
     KdCounters hc;

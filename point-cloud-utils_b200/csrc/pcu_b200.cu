@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <type_traits>
@@ -17,6 +18,7 @@
 
 #include "../../include/pcu_b200.h"
 #include "host_util.h"
+#include "staging.h"
 #include "common.cuh"
 #include "grid.cuh"
 #include "search.cuh"
@@ -218,6 +220,7 @@ struct pcu_b200_workspace {
     cudaEvent_t marks[11] = {};   // 0 .. 8: stage boundaries of a device call; 9 / 10: before the H2D / after the D2H of a host call
     int marks_used = 0;
     bool host_marks = false;      // marks 9 and 10 belong to the last call
+    HostStager* stager = nullptr; // pinned ring + copy threads for pageable inputs of the host entry points (created on first use)
 };
 
 // A cloud binned once (pcu_b200_cloud_prepare_*): its cell-sorted points, cell table, grid header, wall tables and
@@ -567,15 +570,19 @@ int prepare_plan(pcu_b200_workspace* ws, Plan<T>& plan, PlanSpec<T>& spec, cudaS
 // `ready` (host entry points, single pairs): two events, recorded on the copy stream when the first / the second
 // cloud has arrived on the device.  The first cloud is then binned -- all five passes -- while the second is
 // still crossing PCIe, and only the second cloud's passes follow its copy.
+// `between` (host entry points; may be null): host work to do once the first cloud's passes have been enqueued and
+// before the second cloud's `ready` event is waited for -- the staged copy of the second cloud, which keeps the host
+// busy, so that the GPU bins the first cloud meanwhile.  It records ready[1] itself.
 template <typename T>
 int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t stream, const cudaEvent_t* ready = nullptr,
-                    bool first_only = false) {
+                    bool first_only = false, const std::function<int()>* between = nullptr) {
     const int nclouds = plan.nclouds;
     if ((ready != nullptr || first_only) && plan.by_value && !plan.one_cta_binning) {
         PCU_CUDA(cudaMemsetAsync(plan.zero_begin, 0, plan.zero_bytes, stream));
         const unsigned scan_blocks = (unsigned)(((long long)plan.max_cap + 1 + kScanTile - 1) / kScanTile);
         const unsigned bin_blocks = (unsigned)((plan.max_n + kThreads - 1) / kThreads);
         for (int s = 0; s < (first_only ? 1 : 2); ++s) {   // first_only: the second cloud is a prepared one
+            if (s == 1 && between != nullptr) PCU_TRY((*between)());
             if (ready != nullptr) PCU_CUDA(cudaStreamWaitEvent(stream, ready[s], 0));
             CloudsVal<T> one;
             one.v[0] = plan.cv.v[s];
@@ -589,8 +596,10 @@ int enqueue_binning(pcu_b200_workspace* ws, const Plan<T>& plan, cudaStream_t st
             PCU_LAUNCH_PDL((scatter_kernel<T, CloudsVal<T>>), dim3(bin_blocks, 1), kThreads, stream, one);
             mark(ws, 5, stream);
         }
+        if (first_only && between != nullptr) PCU_TRY((*between)());
         return PCU_B200_OK;
     }
+    if (between != nullptr) PCU_TRY((*between)());   // the other build paths take both clouds at once
     if (ready != nullptr) {
         PCU_CUDA(cudaStreamWaitEvent(stream, ready[0], 0));
         if (!first_only) PCU_CUDA(cudaStreamWaitEvent(stream, ready[1], 0));
@@ -718,7 +727,7 @@ template <> const Cloud<double>& cloud_desc<double>(const pcu_b200_cloud* c) { r
 template <typename T>
 int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
                  pcu_b200_nn_stats* out_stats, T* out_value, cudaStream_t stream, const cudaEvent_t* ready = nullptr,
-                 const pcu_b200_cloud* prepared = nullptr) {
+                 const pcu_b200_cloud* prepared = nullptr, const std::function<int()>* between = nullptr) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     if (prepared != nullptr) {
         if (prepared->is_f64 != (sizeof(T) == 8 ? 1 : 0)) return fail(PCU_B200_INVALID_ARGUMENT, "the prepared cloud has another precision than the points");
@@ -744,7 +753,7 @@ int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, lo
     mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
     mark(ws, 1, stream);
-    PCU_TRY(enqueue_binning(ws, plan, stream, ready, prepared != nullptr));
+    PCU_TRY(enqueue_binning(ws, plan, stream, ready, prepared != nullptr, between));
     const unsigned qblocks = (unsigned)((std::max(n, m) + kThreads - 1) / kThreads);
     PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, ns), kThreads, false, true);
     mark(ws, 6, stream);
@@ -1323,6 +1332,7 @@ int pcu_b200_workspace_destroy(pcu_b200_workspace* ws) {
     for (auto& e : ws->arrived) if (e) cudaEventDestroy(e);
     if (ws->host_slot) cudaFreeHost(ws->host_slot);
     for (auto& e : ws->marks) if (e) cudaEventDestroy(e);
+    delete ws->stager;            // (the device is idle: nothing is in flight out of the ring)
     delete ws;
     return PCU_B200_OK;
 }
@@ -1381,6 +1391,7 @@ int pcu_b200_workspace_set_options(pcu_b200_workspace* ws, const pcu_b200_option
     if (opts->disable_tie_replay < 0 || opts->disable_tie_replay > 3)
         return fail(PCU_B200_INVALID_ARGUMENT, "disable_tie_replay must be 0 .. 3");
     if (opts->binning < 0 || opts->binning > 2) return fail(PCU_B200_INVALID_ARGUMENT, "binning must be 0, 1 or 2");
+    if (opts->host_staging < 0 || opts->host_staging > 2) return fail(PCU_B200_INVALID_ARGUMENT, "host_staging must be 0, 1 or 2");
     ws->opts = *opts;
     return PCU_B200_OK;
 }

@@ -144,8 +144,8 @@ def test_ctypes_binding_of_the_host_entry_points(pcu):
 
         class Options(ctypes.Structure):
             _fields_ = [("max_points_per_leaf", ctypes.c_int), ("cell_occupancy", ctypes.c_float),
-                        ("disable_tie_replay", ctypes.c_int), ("binning", ctypes.c_int)]
-        opt = Options(leaf, 0.0, 0, 0)
+                        ("disable_tie_replay", ctypes.c_int), ("binning", ctypes.c_int), ("host_staging", ctypes.c_int)]
+        opt = Options(leaf, 0.0, 0, 0, 0)
         assert lib.pcu_b200_workspace_set_options(ws, ctypes.byref(opt)) == 0
         rc = lib.pcu_b200_knn_host_f32(ws, q.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(q)),
                                        d.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(len(d)), k, 0,
@@ -263,3 +263,40 @@ def test_prepared_cloud_gives_the_plain_results(pcu, oracle):
         target.close()
         with pytest.raises(ValueError, match="closed"):
             pcu.chamfer_distance(x, target)
+
+
+@pytest.mark.gpu
+def test_pageable_inputs_through_the_pinned_ring(pcu, oracle):
+    """Large ordinary numpy arrays are staged through the workspace's pinned ring by copy threads (csrc/staging.h):
+    same results as the driver's own staging, for sizes around the chunk (2 MB) and ring (32 MB) boundaries, odd
+    tails, both precisions, back-to-back calls that reuse ring slots still in flight, and a forced ring for small
+    inputs."""
+    import torch
+    I = pcu._pcu_internal
+    rng = np.random.default_rng(21)
+    try:
+        for n, m, dtype in ((349525, 349526, np.float32), (174763, 1500000, np.float32), (3000001, 700000, np.float32),
+                            (400000, 380000, np.float64)):
+            x = rng.random((n, 3)).astype(dtype); y = rng.random((m, 3)).astype(dtype)
+            results = []
+            for mode in (2, 0, 1):                      # never / automatic / always
+                I._set_defaults(host_staging=mode)
+                c = pcu.chamfer_distance(x, y)
+                h = pcu.hausdorff_distance(x, y, return_index=True)
+                d, i = pcu.k_nearest_neighbors(x[:200000], y, 3)
+                results.append((float(c), h, d.copy(), i.copy()))
+            for r in results[1:]:
+                # (the Chamfer value's last bits depend on the order in which the far pass met its queries)
+                assert abs(r[0] - results[0][0]) <= 1e-6 * results[0][0] and r[1] == results[0][1]
+                assert np.array_equal(r[2], results[0][2]) and np.array_equal(r[3], results[0][3])
+        # the same values as from page-locked inputs (which are never staged)
+        I._set_defaults(host_staging=0)
+        xp = torch.from_numpy(x).pin_memory(); yp = torch.from_numpy(y).pin_memory()
+        assert abs(float(pcu.chamfer_distance(xp.numpy(), yp.numpy())) - results[0][0]) <= 1e-6 * results[0][0]
+        # small inputs forced through the ring
+        I._set_defaults(host_staging=1)
+        a = rng.random((1000, 3)).astype(np.float32); b = rng.random((777, 3)).astype(np.float32)
+        ref = oracle.chamfer_distance(a, b)
+        assert abs(float(pcu.chamfer_distance(a, b)) - ref) <= 1e-6 * ref
+    finally:
+        I._set_defaults()
