@@ -469,6 +469,26 @@ def main():
                     "e2e": {"value": res["units"] / host_s, "ms_per_step": host_s * 1e3, "h2d_bytes_per_step": int(xh.nbytes)}}
         target.close()
         del xp
+    elif wl_key in ("c2", "c4") and world == 1:
+        # k-NN against a dataset prepared once (binned, reference tree built): what a serving loop with a fixed dataset pays
+        reps = min(args.steps, 8)
+        dist_t = torch.empty((n, k), dtype=torch.float32, device=dev)
+        target = pcu.prepare_cloud(yd, k=k)
+        for _ in range(3):
+            pcu.k_nearest_neighbors(xd, target, k)
+        B.barrier()
+        a0 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        a1 = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        for s in range(reps):
+            B.flush.fill_(s & 0xff)
+            a0[s].record(); pcu.k_nearest_neighbors(xd, target, k); a1[s].record()
+        B.barrier()
+        dev_ms = B.reduce_max(sum(a.elapsed_time(b) for a, b in zip(a0, a1))) / reps
+        prepared = {"note": "k_nearest_neighbors(x, pcu.prepare_cloud(y, k=k)): y binned and its reference tree built once outside "
+                            "the timed region (the plain call, like the reference, rebuilds both every time)",
+                    "value": res["units"] / (dev_ms * 1e-3), "ms_per_step": dev_ms}
+        target.close()
+        del dist_t
     del xd, yd
 
     # ---- C5 strong scaling beside the headline (BASELINE configs[4]) -----------------------------------
@@ -549,7 +569,7 @@ def main():
         if c5 is not None:
             line["c5_strong"] = c5
         if prepared is not None:
-            line["prepared_target"] = prepared
+            line["prepared_target" if wl_key == "c3" else "prepared_dataset"] = prepared
         print(json.dumps(line), flush=True)
     if world > 1:
         B.dist.barrier()

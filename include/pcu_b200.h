@@ -201,6 +201,28 @@ int pcu_b200_cloud_prepare_f32(pcu_b200_workspace* ws, const float* points, int6
 int pcu_b200_cloud_prepare_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud, void* stream);
 int pcu_b200_cloud_prepare_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, pcu_b200_cloud** out_cloud);
 int pcu_b200_cloud_prepare_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud);
+/* The same for k-NN calls: the cell size is chosen for searches with this k, and the reference's kd-tree replica (leaf
+ * size max_points_per_leaf, 0 = 10) is built once into the handle, so that pcu_b200_knn_prepared_* neither bins the
+ * dataset nor builds the tree -- it only replays its tied rows on it (the reference builds its tree in every call,
+ * src/point_cloud_distance.cpp:41-42).  A call whose options name another leaf size builds its own tree as usual.
+ * The handle's tree counters and pyramid are shared state: one k-NN call at a time per handle. */
+int pcu_b200_cloud_prepare_knn_f32(pcu_b200_workspace* ws, const float* points, int64_t n, int k, int max_points_per_leaf,
+                                   pcu_b200_cloud** out_cloud, void* stream);
+int pcu_b200_cloud_prepare_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, int k, int max_points_per_leaf,
+                                   pcu_b200_cloud** out_cloud, void* stream);
+int pcu_b200_cloud_prepare_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, int k, int max_points_per_leaf,
+                                        pcu_b200_cloud** out_cloud);
+int pcu_b200_cloud_prepare_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, int k, int max_points_per_leaf,
+                                        pcu_b200_cloud** out_cloud);
+/* k nearest neighbours of `query` in a prepared cloud: outputs as pcu_b200_knn_* (same results, bit for bit). */
+int pcu_b200_knn_prepared_f32(pcu_b200_workspace* ws, const float* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                              float* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream);
+int pcu_b200_knn_prepared_f64(pcu_b200_workspace* ws, const double* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                              double* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream);
+int pcu_b200_knn_prepared_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                                   float* out_dist, int64_t* out_idx, int64_t* out_n_tied);
+int pcu_b200_knn_prepared_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                                   double* out_dist, int64_t* out_idx, int64_t* out_n_tied);
 int pcu_b200_cloud_destroy(pcu_b200_cloud* cloud);
 int64_t pcu_b200_cloud_size(const pcu_b200_cloud* cloud);
 /* DEVICE pointer to the handle's private (n, 3) copy of the points (what pcu_b200_resolve_witness_* wants as the

@@ -175,15 +175,18 @@ def _metric_value(max_sq, squared, dtype):
 
 # ---------------------------------------------------------------------------------------------
 class PreparedCloud:
-    """A point cloud binned once on the GPU (``prepare_cloud``), to be passed as the SECOND argument -- y / target --
-    of ``chamfer_distance``, ``hausdorff_distance`` and ``one_sided_hausdorff_distance`` as often as wanted: every such
-    call bins only its first argument (and, for numpy inputs, copies only that one over PCIe).  The reference rebuilds
+    """A point cloud binned once on the GPU (``prepare_cloud``), to be passed as the SECOND argument -- y / target /
+    dataset_points -- of ``chamfer_distance``, ``hausdorff_distance``, ``one_sided_hausdorff_distance`` and
+    ``k_nearest_neighbors`` as often as wanted: every such call bins only its first argument (and, for numpy inputs,
+    copies only that one over PCIe).  Prepared with ``k=...`` the handle also owns the reference's kd-tree replica, so
+    k-NN calls neither bin the dataset nor build the tree -- they only replay their tied rows on it.  The reference rebuilds
     its kd-tree three times per direction on every call (/root/reference/src/point_cloud_distance.cpp:41-42).
     Results are those of the plain calls.  Holds a private copy of the points; ``close()`` (or garbage collection)
     frees the device memory."""
 
-    def __init__(self, handle, n, is_f64, device_index, on_device):
+    def __init__(self, handle, n, is_f64, device_index, on_device, knn_k=None, max_points_per_leaf=None):
         self._handle, self.shape, self._f64, self.device_index, self._on_device = handle, (int(n), 3), bool(is_f64), int(device_index), on_device
+        self.k, self.max_points_per_leaf = knn_k, max_points_per_leaf     # set when prepared for k-NN calls
 
     @property
     def dtype(self):
@@ -204,23 +207,33 @@ class PreparedCloud:
         return self.shape[0]
 
 
-def prepare_cloud(points, *, device=None):
-    """Bin ``points`` ((n, 3) float32 / float64 numpy array or CUDA tensor) once; returns a ``PreparedCloud``."""
+def prepare_cloud(points, *, k=None, max_points_per_leaf=10, device=None):
+    """Bin ``points`` ((n, 3) float32 / float64 numpy array or CUDA tensor) once; returns a ``PreparedCloud``.
+    ``k``: the handle is meant as the dataset of ``k_nearest_neighbors`` calls with (about) this k -- the cell size is
+    chosen for it and the reference tree for ``max_points_per_leaf`` is built into the handle (any k works on any
+    handle; results never depend on it)."""
+    kk = 0 if k is None else int(k)
+    if k is not None and kk <= 0:
+        raise ValueError("Invalid value for k (%d) must be greater than 0." % kk)
+    if int(max_points_per_leaf) <= 0:
+        raise ValueError("max_points_per_leaf must be greater than 0.")
+    meta = dict(knn_k=(kk or None), max_points_per_leaf=(int(max_points_per_leaf) if kk else None))
     if _is_tensor(points):
         torch = _torch()
         if points.dtype not in (torch.float32, torch.float64) or points.dim() != 2 or points.shape[1] != 3 or points.shape[0] == 0:
             raise ValueError("points must be a float32 / float64 tensor of shape (n, 3) with n > 0")
         if not points.is_cuda:
-            return prepare_cloud(points.detach().numpy(), device=device)
+            return prepare_cloud(points.detach().numpy(), k=k, max_points_per_leaf=max_points_per_leaf, device=device)
         _same_device(points, device)
         p = points.detach().contiguous()
         dev = p.device.index or 0
-        h = _pcu_internal._cloud_prepare_device(p.dtype == torch.float64, p.data_ptr(), p.shape[0], dev, _stream_of(p))
-        return PreparedCloud(h, p.shape[0], p.dtype == torch.float64, dev, True)
+        h = _pcu_internal._cloud_prepare_device(p.dtype == torch.float64, p.data_ptr(), p.shape[0], dev, _stream_of(p), kk,
+                                                int(max_points_per_leaf))
+        return PreparedCloud(h, p.shape[0], p.dtype == torch.float64, dev, True, **meta)
     pts = _np.asarray(points)
     d = _dev(device)
-    h = _pcu_internal._cloud_prepare(pts, d)
-    return PreparedCloud(h, pts.shape[0], pts.dtype == _np.float64, _pcu_internal._current_device() if d < 0 else d, False)
+    h = _pcu_internal._cloud_prepare(pts, d, kk, int(max_points_per_leaf))
+    return PreparedCloud(h, pts.shape[0], pts.dtype == _np.float64, _pcu_internal._current_device() if d < 0 else d, False, **meta)
 
 
 def _prepared_resolved(buf, which, xs, cloud, leaf):
@@ -285,6 +298,8 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
 
     Mirrors /root/reference/src/point_cloud_distance.cpp:123-164.
     """
+    if isinstance(dataset_points, PreparedCloud):
+        return _knn_prepared(query_points, dataset_points, int(k), bool(squared_distances), int(max_points_per_leaf), device)
     if _is_tensor(query_points) or _is_tensor(dataset_points):
         torch = _torch()
         if not _is_tensor(query_points):
@@ -307,6 +322,38 @@ def k_nearest_neighbors(query_points, dataset_points, k, squared_distances=False
     return _pcu_internal.k_nearest_neighbors(_np.asarray(query_points), _np.asarray(dataset_points), int(k),
                                              bool(squared_distances), int(max_points_per_leaf), int(num_threads),
                                              _dev(device))
+
+
+def _knn_prepared(query_points, cloud, k, squared, leaf, device):
+    """k_nearest_neighbors against a PreparedCloud: numpy in -> numpy out, CUDA tensor in -> CUDA tensors out."""
+    if not cloud._handle:
+        raise ValueError("the prepared cloud has been closed")
+    if k <= 0:
+        raise ValueError("Invalid value for k (%d) must be greater than 0." % k)
+    if _is_tensor(query_points) and query_points.is_cuda:
+        torch = _torch()
+        q = query_points.detach().contiguous()
+        if q.dtype != (torch.float64 if cloud._f64 else torch.float32) or q.dim() != 2 or q.shape[1] != 3 or q.shape[0] == 0:
+            raise ValueError("query_points must be a non-empty (n, 3) tensor of the prepared cloud's precision (%s)" % cloud.dtype)
+        if (q.device.index or 0) != cloud.device_index:
+            raise ValueError("query_points live on %s, the prepared cloud on device %d" % (q.device, cloud.device_index))
+        _same_device(q, device)
+        n = q.shape[0]
+        dists = torch.empty((n, k), dtype=q.dtype, device=q.device)
+        corrs = torch.empty((n, k), dtype=torch.int64, device=q.device)
+        _pcu_internal._knn_prepared_device(cloud._f64, q.data_ptr(), n, cloud._handle, k, squared, dists.data_ptr(),
+                                           corrs.data_ptr(), 0, leaf, cloud.device_index, _stream_of(q))
+        return dists.squeeze(), corrs.squeeze()
+    as_tensor = _is_tensor(query_points)
+    qn = query_points.detach().numpy() if as_tensor else _np.asarray(query_points)
+    d = _dev(device)
+    if d >= 0 and d != cloud.device_index:
+        raise ValueError("device=%d was given but the prepared cloud lives on device %d" % (d, cloud.device_index))
+    dn, cn = _pcu_internal._knn_prepared(qn, cloud._handle, cloud._f64, k, squared, leaf, cloud.device_index)
+    if as_tensor:
+        torch = _torch()
+        return torch.from_numpy(_np.asarray(dn)), torch.from_numpy(_np.asarray(cn))
+    return dn, cn
 
 
 def one_sided_hausdorff_distance(source, target, return_index=True, squared_distances=False, max_points_per_leaf=10,

@@ -603,7 +603,7 @@ py::array morton_knn(const py::array& codes_in, const py::array& qcodes_in, int 
 }
 
 // ---- prepared clouds (handles travel as integers; point-cloud-utils_b200/__init__.py wraps them in PreparedCloud) ----
-uintptr_t cloud_prepare_numpy(const py::array& pts_in, int device) {
+uintptr_t cloud_prepare_numpy(const py::array& pts_in, int device, int knn_k, int leaf) {
     const bool f32 = pts_in.dtype().is(py::dtype::of<float>()), f64 = pts_in.dtype().is(py::dtype::of<double>());
     if (!f32 && !f64)
         throw py::value_error("Invalid scalar type (" + std::string(py::str(pts_in.dtype())) + ") for argument 'points'. Expected one of ['float32', 'float64'].");
@@ -616,23 +616,29 @@ uintptr_t cloud_prepare_numpy(const py::array& pts_in, int device) {
     if (f32) {
         auto p = dense<float>(pts_in);
         CallScope scope(slot);
-        status = pcu_b200_cloud_prepare_host_f32(slot.ws, p.data(), p.shape(0), &cloud);
+        status = knn_k > 0 ? pcu_b200_cloud_prepare_knn_host_f32(slot.ws, p.data(), p.shape(0), knn_k, leaf, &cloud)
+                           : pcu_b200_cloud_prepare_host_f32(slot.ws, p.data(), p.shape(0), &cloud);
     } else {
         auto p = dense<double>(pts_in);
         CallScope scope(slot);
-        status = pcu_b200_cloud_prepare_host_f64(slot.ws, p.data(), p.shape(0), &cloud);
+        status = knn_k > 0 ? pcu_b200_cloud_prepare_knn_host_f64(slot.ws, p.data(), p.shape(0), knn_k, leaf, &cloud)
+                           : pcu_b200_cloud_prepare_host_f64(slot.ws, p.data(), p.shape(0), &cloud);
     }
     check(status);
     return (uintptr_t)cloud;
 }
-uintptr_t cloud_prepare_device(bool is_f64, uintptr_t pts, int64_t n, int device, uintptr_t stream) {
+uintptr_t cloud_prepare_device(bool is_f64, uintptr_t pts, int64_t n, int device, uintptr_t stream, int knn_k, int leaf) {
     Slot& slot = pool().get(device, stream);
     pcu_b200_cloud* cloud = nullptr;
     int status;
     {
         CallScope scope(slot);
-        status = is_f64 ? pcu_b200_cloud_prepare_f64(slot.ws, (const double*)pts, n, &cloud, (void*)stream)
-                        : pcu_b200_cloud_prepare_f32(slot.ws, (const float*)pts, n, &cloud, (void*)stream);
+        if (knn_k > 0)
+            status = is_f64 ? pcu_b200_cloud_prepare_knn_f64(slot.ws, (const double*)pts, n, knn_k, leaf, &cloud, (void*)stream)
+                            : pcu_b200_cloud_prepare_knn_f32(slot.ws, (const float*)pts, n, knn_k, leaf, &cloud, (void*)stream);
+        else
+            status = is_f64 ? pcu_b200_cloud_prepare_f64(slot.ws, (const double*)pts, n, &cloud, (void*)stream)
+                            : pcu_b200_cloud_prepare_f32(slot.ws, (const float*)pts, n, &cloud, (void*)stream);
     }
     check(status);
     return (uintptr_t)cloud;
@@ -641,6 +647,60 @@ void cloud_destroy(uintptr_t cloud) {
     py::gil_scoped_release nogil;
     pcu_b200_cloud_destroy((pcu_b200_cloud*)cloud);
 }
+// k nearest neighbours of numpy points in a prepared cloud: (dists, corrs) like k_nearest_neighbors
+template <typename T>
+py::tuple knn_prepared_numpy_t(const py::array& q_in, pcu_b200_cloud* cloud, int k, bool squared, int leaf, int device) {
+    auto q = dense<T>(q_in);
+    const int64_t n = q.shape(0);
+    py::array_t<T> dists = result_array<T>((py::ssize_t)n, (py::ssize_t)k);
+    py::array_t<int64_t> corrs = result_array<int64_t>((py::ssize_t)n, (py::ssize_t)k);
+    Slot& slot = pool().get(device, kHostKey);
+    const pcu_b200_options opts = make_options(leaf);
+    int status;
+    int64_t tied = 0;
+    {
+        CallScope scope(slot);
+        pcu_b200_workspace_set_options(slot.ws, &opts);
+        if (sizeof(T) == 4)
+            status = pcu_b200_knn_prepared_host_f32(slot.ws, (const float*)q.data(), n, cloud, k, squared, (float*)dists.mutable_data(),
+                                                    corrs.mutable_data(), &tied);
+        else
+            status = pcu_b200_knn_prepared_host_f64(slot.ws, (const double*)q.data(), n, cloud, k, squared, (double*)dists.mutable_data(),
+                                                    corrs.mutable_data(), &tied);
+    }
+    check(status);
+    return py::make_tuple(dists.attr("squeeze")(), corrs.attr("squeeze")());
+}
+py::tuple knn_prepared_numpy(const py::array& q_in, uintptr_t cloud, bool cloud_is_f64, int k, bool squared, int max_points_per_leaf, int device) {
+    if (k <= 0) throw py::value_error("Invalid value for k (" + std::to_string(k) + ") must be greater than 0.");
+    const bool f32 = q_in.dtype().is(py::dtype::of<float>()), f64 = q_in.dtype().is(py::dtype::of<double>());
+    if ((!f32 && !f64) || f64 != cloud_is_f64)
+        throw py::value_error("Invalid scalar type (" + std::string(py::str(q_in.dtype())) + "): expected the prepared cloud's " +
+                              (cloud_is_f64 ? "float64" : "float32") + ".");
+    if (q_in.ndim() != 2 || q_in.shape(1) != 3)
+        throw py::value_error("Only 3D inputs are supported: points must have shape (n, 3).");
+    if (q_in.shape(0) == 0) throw py::value_error("Invalid input set with zero elements: points must have shape (n, 3) with n > 0.");
+    const int dev = current_device_or_default(device);
+    return f32 ? knn_prepared_numpy_t<float>(q_in, (pcu_b200_cloud*)cloud, k, squared, max_points_per_leaf, dev)
+               : knn_prepared_numpy_t<double>(q_in, (pcu_b200_cloud*)cloud, k, squared, max_points_per_leaf, dev);
+}
+void knn_prepared_device(bool is_f64, uintptr_t query, int64_t n, uintptr_t cloud, int k, bool squared, uintptr_t out_dist,
+                         uintptr_t out_idx, uintptr_t out_n_tied, int max_points_per_leaf, int device, uintptr_t stream) {
+    if (k <= 0) throw py::value_error("Invalid value for k (" + std::to_string(k) + ") must be greater than 0.");
+    Slot& slot = pool().get(device, stream);
+    const pcu_b200_options opts = make_options(max_points_per_leaf);
+    int status;
+    {
+        CallScope scope(slot);
+        pcu_b200_workspace_set_options(slot.ws, &opts);
+        status = is_f64 ? pcu_b200_knn_prepared_f64(slot.ws, (const double*)query, n, (pcu_b200_cloud*)cloud, k, squared, (double*)out_dist,
+                                                    (int64_t*)out_idx, (int64_t*)out_n_tied, (void*)stream)
+                        : pcu_b200_knn_prepared_f32(slot.ws, (const float*)query, n, (pcu_b200_cloud*)cloud, k, squared, (float*)out_dist,
+                                                    (int64_t*)out_idx, (int64_t*)out_n_tied, (void*)stream);
+    }
+    check(status);
+}
+
 // fused sweep(s) of numpy points against a prepared cloud: (value or None, stats[, stats])
 py::tuple stats_prepared_numpy(const py::array& x_in, uintptr_t cloud, bool cloud_is_f64, bool both, int max_points_per_leaf, int device) {
     const bool f32 = x_in.dtype().is(py::dtype::of<float>()), f64 = x_in.dtype().is(py::dtype::of<double>());
@@ -919,8 +979,12 @@ PYBIND11_MODULE(_pcu_internal, mod) {
             py::arg("weight_function") = "constant", py::arg("random_seed") = -1, py::arg("device") = -1,
             "Indices of the kept points and their unit normals (plane fit to the points in a ball around each point).");
     mod.def("_normals_ball_device", &normals_ball_device);
-    mod.def("_cloud_prepare", &cloud_prepare_numpy, py::arg("points"), py::arg("device") = -1);
-    mod.def("_cloud_prepare_device", &cloud_prepare_device);
+    mod.def("_cloud_prepare", &cloud_prepare_numpy, py::arg("points"), py::arg("device") = -1, py::arg("knn_k") = 0,
+            py::arg("max_points_per_leaf") = 10);
+    mod.def("_cloud_prepare_device", &cloud_prepare_device, py::arg("is_f64"), py::arg("points"), py::arg("n"), py::arg("device"),
+            py::arg("stream"), py::arg("knn_k") = 0, py::arg("max_points_per_leaf") = 10);
+    mod.def("_knn_prepared", &knn_prepared_numpy);
+    mod.def("_knn_prepared_device", &knn_prepared_device);
     mod.def("_cloud_destroy", &cloud_destroy);
     mod.def("_cloud_points", [](uintptr_t cloud) { return (uintptr_t)pcu_b200_cloud_points((const pcu_b200_cloud*)cloud); });
     mod.def("_stats_prepared", &stats_prepared_numpy);

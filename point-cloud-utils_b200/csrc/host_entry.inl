@@ -21,9 +21,10 @@ int h2d(pcu_b200_workspace* ws, void* dst, const void* src, size_t bytes, cudaSt
 
 template <typename T>
 int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* dataset, long long m, int k, int squared,
-             T* out_dist, long long* out_idx, long long* out_n_tied) {
+             T* out_dist, long long* out_idx, long long* out_n_tied, pcu_b200_cloud* prepared = nullptr) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid value for k (%d) must be greater than 0.", k);
+    if (prepared != nullptr) { dataset = query; m = 1; }   // placeholders for the checks and the staging layout: nothing of it is copied
     PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
     if (!out_dist || !out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     PCU_ON_DEVICE(ws);
@@ -43,8 +44,8 @@ int knn_host(pcu_b200_workspace* ws, const T* query, long long n, const T* datas
     cudaStream_t st = ws->own_stream;
     mark(ws, 9, st);
     PCU_TRY(h2d(ws, dq, query, sizeof(T) * 3 * n, st));
-    PCU_TRY(h2d(ws, dd, dataset, sizeof(T) * 3 * m, st));
-    PCU_TRY(knn_device<T>(ws, dq, n, dd, m, k, squared, od, oi, nt, st));
+    if (prepared == nullptr) PCU_TRY(h2d(ws, dd, dataset, sizeof(T) * 3 * m, st));
+    PCU_TRY(knn_device<T>(ws, dq, n, dd, m, k, squared, od, oi, nt, st, prepared));
     PCU_CUDA(cudaMemcpyAsync(out_dist, od, sizeof(T) * n * k, cudaMemcpyDeviceToHost, st));
     PCU_CUDA(cudaMemcpyAsync(out_idx, oi, sizeof(long long) * n * k, cudaMemcpyDeviceToHost, st));
     long long tied = 0;
@@ -219,14 +220,14 @@ int normals_ball_host(pcu_b200_workspace* ws, const T* points, long long n, cons
 
 // Prepares a cloud from HOST points: staged through the workspace, binned into the handle's own block.
 template <typename T>
-int cloud_prepare_host(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out) {
+int cloud_prepare_host(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out, int knn_k = 1, int leaf = 0) {
     if (!ws || !out) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
     PCU_TRY(check_cloud_args<T>(points, n, points, 1));
     PCU_ON_DEVICE(ws);
     cudaStream_t st = ws->own_stream;
     PCU_TRY(ensure_io(ws, align_up(sizeof(T) * 3 * (size_t)n), st));
     PCU_TRY(h2d(ws, ws->io, points, sizeof(T) * 3 * n, st));
-    PCU_TRY(cloud_prepare_device<T>(ws, reinterpret_cast<const T*>(ws->io), n, out, st));
+    PCU_TRY(cloud_prepare_device<T>(ws, reinterpret_cast<const T*>(ws->io), n, out, st, knn_k, leaf));
     PCU_CUDA(cudaStreamSynchronize(st));
     return PCU_B200_OK;
 }
@@ -328,6 +329,24 @@ int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int
                                int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes) {
     return debug_kd_tree<double>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
                                  kid0, kid1, out_nodes);
+}
+int pcu_b200_cloud_prepare_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, int k, int max_points_per_leaf,
+                                        pcu_b200_cloud** out_cloud) {
+    return cloud_prepare_host<float>(ws, points, n, out_cloud, k, max_points_per_leaf > 0 ? max_points_per_leaf : 10);
+}
+int pcu_b200_cloud_prepare_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, int k, int max_points_per_leaf,
+                                        pcu_b200_cloud** out_cloud) {
+    return cloud_prepare_host<double>(ws, points, n, out_cloud, k, max_points_per_leaf > 0 ? max_points_per_leaf : 10);
+}
+int pcu_b200_knn_prepared_host_f32(pcu_b200_workspace* ws, const float* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                                   float* out_dist, int64_t* out_idx, int64_t* out_n_tied) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return knn_host<float>(ws, query, n, nullptr, 0, k, squared, out_dist, (long long*)out_idx, (long long*)out_n_tied, dataset);
+}
+int pcu_b200_knn_prepared_host_f64(pcu_b200_workspace* ws, const double* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                                   double* out_dist, int64_t* out_idx, int64_t* out_n_tied) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return knn_host<double>(ws, query, n, nullptr, 0, k, squared, out_dist, (long long*)out_idx, (long long*)out_n_tied, dataset);
 }
 int pcu_b200_cloud_prepare_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, pcu_b200_cloud** out_cloud) {
     return cloud_prepare_host<float>(ws, points, n, out_cloud);

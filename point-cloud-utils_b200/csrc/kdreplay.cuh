@@ -858,6 +858,19 @@ int build_kd_replica(KdReplayBuffers<T>& b, const T* pts, long long m_ll, int le
     return PCU_B200_OK;
 }
 
+// The same for a tree that already exists (a prepared cloud owns it: pcu_b200_cloud_prepare_knn_*): one launch,
+// a no-op when no row was flagged.
+template <typename T>
+int enqueue_tie_replay_prebuilt(KdReplayBuffers<T>& b, const T* query, const T* dataset, int k, int squared,
+                                const long long* tie_list, const unsigned* tie_count, long long max_rows, T* out_dist,
+                                long long* out_idx, cudaStream_t stream, std::atomic<long long>& launches) {
+    if (cudaMemsetAsync(b.overflows, 0, sizeof(unsigned), stream) != cudaSuccess) return PCU_B200_CUDA_ERROR;
+    const unsigned blocks = (unsigned)std::max<long long>(1, std::min<long long>((max_rows + 127) / 128, 1184));
+    // (the gate argument only tells the kernel not to count stub hits: a full tree has no stubs)
+    KD_LAUNCH(kd_replay_kernel<T>, blocks, 128, stream, b, query, dataset, k, squared, tie_list, tie_count, out_dist, out_idx, tie_count);
+    return PCU_B200_OK;
+}
+
 // Re-answers the rows listed in tie_list with the reference's own tie order.  Both launches are gated on
 // the device-side list length: nothing happens (and nothing synchronises) when no query was flagged.
 template <typename T>

@@ -234,7 +234,14 @@ struct pcu_b200_cloud {
     Cloud<float> desc32{};
     Cloud<double> desc64{};
     const void* raw = nullptr;   // the handle's own copy of the caller's (n, 3) array (inside block)
+    int knn_k = 1;               // the k the cell size was chosen for
+    int leaf = 0;                // > 0: the block also holds the reference-tree replica built with this leaf size
+    KdReplayBuffers<float> kd32{};
+    KdReplayBuffers<double> kd64{};
 };
+template <typename T> KdReplayBuffers<T>& cloud_tree(pcu_b200_cloud* c);
+template <> KdReplayBuffers<float>& cloud_tree<float>(pcu_b200_cloud* c) { return c->kd32; }
+template <> KdReplayBuffers<double>& cloud_tree<double>(pcu_b200_cloud* c) { return c->kd64; }
 
 #define PCU_STAGE_NAMES "descriptors", "bbox+grid", "histogram", "scan", "scatter", "search", "search_far", "finalize", "h2d", "d2h"
 
@@ -654,12 +661,22 @@ int check_cloud_args(const void* a, long long n, const void* b, long long m) {
     return PCU_B200_OK;
 }
 
+template <typename T> const Cloud<T>& cloud_desc(const pcu_b200_cloud* c);
+template <> const Cloud<float>& cloud_desc<float>(const pcu_b200_cloud* c) { return c->desc32; }
+template <> const Cloud<double>& cloud_desc<double>(const pcu_b200_cloud* c) { return c->desc64; }
+
 // ---- k nearest neighbours ---------------------------------------------------------------------
 template <typename T>
 int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dataset, long long m, int k, int squared,
-               T* out_dist, long long* out_idx, long long* out_n_tied, cudaStream_t stream) {
+               T* out_dist, long long* out_idx, long long* out_n_tied, cudaStream_t stream, pcu_b200_cloud* prepared = nullptr) {
     if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
     if (k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid value for k (%d) must be greater than 0.", k);
+    if (prepared != nullptr) {
+        if (prepared->is_f64 != (sizeof(T) == 8 ? 1 : 0)) return fail(PCU_B200_INVALID_ARGUMENT, "the prepared cloud has another precision than the points");
+        if (prepared->device != ws->device) return fail(PCU_B200_INVALID_ARGUMENT, "the prepared cloud lives on device %d, the workspace on %d", prepared->device, ws->device);
+        dataset = (const T*)prepared->raw;
+        m = prepared->n;
+    }
     PCU_TRY(check_cloud_args<T>(query, n, dataset, m));
     if (!out_dist || !out_idx) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
     if ((double)n * (double)k >= 9e18) return fail(PCU_B200_INVALID_ARGUMENT, "n * k overflows");
@@ -671,13 +688,18 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
     spec.occupancy = occupancy_for(ws, k);
     spec.binning = ws->opts.binning;
     spec.out_dist = out_dist; spec.out_idx = out_idx;
-    spec.replay_points = ws->opts.disable_tie_replay == 1 ? 0 : m;
+    const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
+    // a prepared cloud that owns the reference tree (same leaf size) spares the call the build
+    const bool own_tree = prepared != nullptr && prepared->leaf == leaf && ws->opts.disable_tie_replay == 0;
+    spec.replay_points = (ws->opts.disable_tie_replay == 1 || own_tree) ? 0 : m;
+    spec.prepared_second = prepared != nullptr;
     Plan<T> plan;
     PCU_TRY(prepare_plan(ws, plan, spec, stream));
+    if (prepared != nullptr) plan.cv.v[1] = cloud_desc<T>(prepared);   // a single pair: descriptors travel by value
     mark(ws, 0, stream);
     PCU_TRY(upload_descriptors(plan, stream));
     mark(ws, 1, stream);
-    PCU_TRY(enqueue_binning(ws, plan, stream));
+    PCU_TRY(enqueue_binning(ws, plan, stream, nullptr, prepared != nullptr));
     const unsigned qblocks = (unsigned)((n + kThreads - 1) / kThreads);
     if (k == 1) {
         PCU_LAUNCH_CS(nn1_kernel, dim3(qblocks, 1), kThreads, true, false);
@@ -702,8 +724,13 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
         mark(ws, 6, stream);
         mark(ws, 7, stream);
     }
-    if (ws->opts.disable_tie_replay != 1) {
-        const int leaf = ws->opts.max_points_per_leaf > 0 ? ws->opts.max_points_per_leaf : 10;
+    if (own_tree) {
+        KdReplayBuffers<T>& tree = cloud_tree<T>(prepared);
+        const int rs = enqueue_tie_replay_prebuilt<T>(tree, query, dataset, k, squared, plan.args.sweep[0].tie_list,
+                                                      plan.args.sweep[0].counters + 1, n, out_dist, out_idx, stream, g_launches);
+        if (rs != PCU_B200_OK) return fail(rs, "tie replay failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ws->replay_overflows = tree.overflows;
+    } else if (ws->opts.disable_tie_replay != 1) {
         const int rs = enqueue_tie_replay<T>(plan.replay, query, dataset, m, k, squared, leaf, plan.args.sweep[0].tie_list,
                                              plan.args.sweep[0].counters + 1, n, out_dist, out_idx, ws->opts.disable_tie_replay, stream, g_launches);
         if (rs != PCU_B200_OK) return fail(rs, "tie replay failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -720,9 +747,6 @@ int knn_device(pcu_b200_workspace* ws, const T* query, long long n, const T* dat
 
 // ---- fused k = 1 statistics -------------------------------------------------------------------
 // nsweeps == 1: query -> dataset.  nsweeps == 2: x -> y and y -> x over the same two binned clouds.
-template <typename T> const Cloud<T>& cloud_desc(const pcu_b200_cloud* c);
-template <> const Cloud<float>& cloud_desc<float>(const pcu_b200_cloud* c) { return c->desc32; }
-template <> const Cloud<double>& cloud_desc<double>(const pcu_b200_cloud* c) { return c->desc64; }
 
 template <typename T>
 int stats_device(pcu_b200_workspace* ws, const T* a, long long n, const T* b, long long m, bool both,
@@ -1021,23 +1045,34 @@ int morton_knn_device(pcu_b200_workspace* ws, const unsigned long long* codes, l
 // Bins `points` once into a private block: the layout of an ordinary plan whose second cloud is a one-point
 // dummy, with only the first cloud binned; the handle keeps that cloud's descriptor.
 template <typename T>
-int cloud_prepare_device(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out, cudaStream_t stream) {
+int cloud_prepare_device(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out, cudaStream_t stream,
+                         int knn_k = 1, int leaf = 0) {
     if (!ws || !out) return fail(PCU_B200_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
+    if (knn_k <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "Invalid value for k (%d) must be greater than 0.", knn_k);
+    if (leaf < 0) return fail(PCU_B200_INVALID_ARGUMENT, "max_points_per_leaf must be >= 0");
     PCU_TRY(check_cloud_args<T>(points, n, points, 1));
     PCU_ON_DEVICE(ws);
     PlanSpec<T> spec;
     spec.a = points; spec.n = n; spec.b = points; spec.m = 1;
     spec.nsweeps = 1; spec.k = 1;
-    spec.occupancy = occupancy_for(ws, 1);
+    spec.occupancy = occupancy_for(ws, knn_k);   // the cell size the searches with this k want
     spec.binning = 1;                 // the grid-wide passes: the handle's buffers are global memory either way
     spec.prepared_second = true;      // (also keeps the dummy out of the one-CTA build)
     Plan<T> plan;
     plan.layout(nullptr, spec);
     const size_t raw_bytes = align_up(sizeof(T) * 3 * (size_t)n);
+    size_t tree_bytes = 0;
+    if (leaf > 0) {
+        Carver measure(nullptr);
+        KdReplayBuffers<T> probe;
+        probe.carve(measure, n);
+        tree_bytes = measure.off;
+    }
     pcu_b200_cloud* c = new (std::nothrow) pcu_b200_cloud();
     if (!c) return fail(PCU_B200_OUT_OF_MEMORY, "out of host memory");
-    c->device = ws->device; c->is_f64 = sizeof(T) == 8 ? 1 : 0; c->n = n; c->bytes = plan.total + raw_bytes;
+    c->device = ws->device; c->is_f64 = sizeof(T) == 8 ? 1 : 0; c->n = n; c->bytes = plan.total + raw_bytes + tree_bytes;
+    c->knn_k = knn_k;
     cudaError_t e = cudaMalloc((void**)&c->block, c->bytes);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1052,6 +1087,14 @@ int cloud_prepare_device(pcu_b200_workspace* ws, const T* points, long long n, p
     plan.layout(c->block, spec);
     const int st = enqueue_binning(ws, plan, stream, nullptr, true);
     if (st != PCU_B200_OK) return bail(st);
+    if (leaf > 0) {   // the full reference tree, once: k-NN calls against the handle only replay their tied rows on it
+        Carver cv(c->block + plan.total + raw_bytes);
+        KdReplayBuffers<T>& tree = cloud_tree<T>(c);
+        tree.carve(cv, n);
+        const int ts = build_kd_replica<T>(tree, raw_copy, n, leaf, nullptr, KdPrune<T>{}, stream, g_launches);
+        if (ts != PCU_B200_OK) return bail(fail(ts, "building the reference tree failed: %s", cudaGetErrorString(cudaGetLastError())));
+        c->leaf = leaf;
+    }
     Cloud<T> d = plan.cv.v[0];
     d.hint_out = nullptr;             // a prepared cloud takes no part in the grid-sizing feedback
     if (sizeof(T) == 8) std::memcpy(&c->desc64, &d, sizeof d); else std::memcpy(&c->desc32, &d, sizeof d);
@@ -1436,6 +1479,26 @@ int pcu_b200_cloud_prepare_f32(pcu_b200_workspace* ws, const float* points, int6
 }
 int pcu_b200_cloud_prepare_f64(pcu_b200_workspace* ws, const double* points, int64_t n, pcu_b200_cloud** out_cloud, void* stream) {
     return cloud_prepare_device<double>(ws, points, n, out_cloud, (cudaStream_t)stream);
+}
+int pcu_b200_cloud_prepare_knn_f32(pcu_b200_workspace* ws, const float* points, int64_t n, int k, int max_points_per_leaf,
+                                   pcu_b200_cloud** out_cloud, void* stream) {
+    return cloud_prepare_device<float>(ws, points, n, out_cloud, (cudaStream_t)stream, k, max_points_per_leaf > 0 ? max_points_per_leaf : 10);
+}
+int pcu_b200_cloud_prepare_knn_f64(pcu_b200_workspace* ws, const double* points, int64_t n, int k, int max_points_per_leaf,
+                                   pcu_b200_cloud** out_cloud, void* stream) {
+    return cloud_prepare_device<double>(ws, points, n, out_cloud, (cudaStream_t)stream, k, max_points_per_leaf > 0 ? max_points_per_leaf : 10);
+}
+int pcu_b200_knn_prepared_f32(pcu_b200_workspace* ws, const float* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                              float* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return knn_device<float>(ws, query, n, nullptr, 0, k, squared, out_dist, (long long*)out_idx, (long long*)out_n_tied,
+                             (cudaStream_t)stream, dataset);
+}
+int pcu_b200_knn_prepared_f64(pcu_b200_workspace* ws, const double* query, int64_t n, pcu_b200_cloud* dataset, int k, int squared,
+                              double* out_dist, int64_t* out_idx, int64_t* out_n_tied, void* stream) {
+    if (!dataset) return fail(PCU_B200_INVALID_ARGUMENT, "null prepared cloud");
+    return knn_device<double>(ws, query, n, nullptr, 0, k, squared, out_dist, (long long*)out_idx, (long long*)out_n_tied,
+                              (cudaStream_t)stream, dataset);
 }
 int pcu_b200_cloud_destroy(pcu_b200_cloud* cloud) {
     if (!cloud) return PCU_B200_OK;

@@ -300,3 +300,56 @@ def test_pageable_inputs_through_the_pinned_ring(pcu, oracle):
         assert abs(float(pcu.chamfer_distance(a, b)) - ref) <= 1e-6 * ref
     finally:
         I._set_defaults()
+
+
+@pytest.mark.gpu
+def test_prepared_dataset_for_knn_gives_the_plain_results(pcu, oracle):
+    """k_nearest_neighbors(query, prepare_cloud(dataset, k=...)): the handle owns the binned dataset AND the reference
+    tree; a call only bins its queries, searches, and replays its tied rows on the handle's tree.  Bit-identical to the
+    plain call and to the reference -- also where tie order decides (lattice, duplicated points), for other k than the
+    one the handle was prepared for, for another leaf size (the call then builds its own tree), for a handle prepared
+    without k, for CUDA tensors."""
+    import torch
+    rng = np.random.default_rng(77)
+    for dtype in (np.float32, np.float64):
+        d = rng.random((60000, 3)).astype(dtype)
+        d[:3000] = d[3000:6000]                                        # duplicates: ties for every query near them
+        q = np.concatenate([rng.random((40000, 3)), d[:2000]]).astype(dtype)
+        for k_prep, leaf in ((16, 10), (1, 10), (4, 3)):
+            h = pcu.prepare_cloud(d, k=k_prep, max_points_per_leaf=leaf)
+            assert h.k == k_prep and h.max_points_per_leaf == leaf
+            for k in (1, 4, 16):
+                ref = oracle.k_nearest_neighbors(q, d, k, max_points_per_leaf=leaf)
+                got = pcu.k_nearest_neighbors(q, h, k, max_points_per_leaf=leaf)
+                assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+                plain = pcu.k_nearest_neighbors(q, d, k, max_points_per_leaf=leaf)
+                assert np.array_equal(got[1], plain[1]) and np.array_equal(got[0], plain[0])
+            # another leaf size than the handle's tree: the call builds its own, results follow the call's leaf size
+            ref = oracle.k_nearest_neighbors(q, d, 8, True, 25)
+            got = pcu.k_nearest_neighbors(q, h, 8, True, 25)
+            assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+            h.close()
+        # a handle prepared without k (statistics calls) serves k-NN too
+        h0 = pcu.prepare_cloud(d)
+        assert h0.k is None
+        ref = oracle.k_nearest_neighbors(q, d, 5)
+        got = pcu.k_nearest_neighbors(q, h0, 5)
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+        assert abs(float(pcu.chamfer_distance(q, h0)) - float(oracle.chamfer_distance(q, d))) <= REL * float(oracle.chamfer_distance(q, d))
+        # CUDA tensors
+        ht = pcu.prepare_cloud(torch.from_numpy(d).cuda(), k=8)
+        gd, gi = pcu.k_nearest_neighbors(torch.from_numpy(q).cuda(), ht, 8)
+        ref = oracle.k_nearest_neighbors(q, d, 8)
+        assert gd.is_cuda and np.array_equal(gi.cpu().numpy(), ref[1]) and np.array_equal(gd.cpu().numpy(), ref[0])
+        # ... and the metrics against a k-NN handle
+        assert pcu.one_sided_hausdorff_distance(q, ht) == oracle.one_sided_hausdorff_distance(q, d)
+        with pytest.raises(ValueError):
+            pcu.k_nearest_neighbors(q.astype(np.float64 if dtype == np.float32 else np.float32), h0, 3)
+        with pytest.raises(ValueError, match="greater than 0"):
+            pcu.k_nearest_neighbors(q, h0, 0)
+    lat = np.stack(np.meshgrid(*[np.arange(20)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32) / 20
+    hl = pcu.prepare_cloud(lat, k=8)
+    ql = (lat[::3] + np.float32(0.025)).astype(np.float32)            # cell centres: 8 equidistant lattice points each
+    ref = oracle.k_nearest_neighbors(ql, lat, 8)
+    got = pcu.k_nearest_neighbors(ql, hl, 8)
+    assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
