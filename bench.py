@@ -352,19 +352,31 @@ class Bench:
             d, i = pcu.k_nearest_neighbors(a, b, k)
             return float(d[0].sum())
 
+        # Warm-up: the first ~60 calls on freshly page-locked buffers see the H2D rate switch between ~52 and ~24 GB/s
+        # in windows of 5 - 15 calls (tools/e2e_trace.py: 0.69 / 1.29 ms per call, the H2D wait inside 465 / 992 us),
+        # after which it stays at the link's rate; the light workloads therefore warm up for 60 calls, not 3.
+        warm = 60 if wl_key in ("c3", "c2") else 3
+        per_call = []
+
         def timed(a, b, reps):
-            for _ in range(3):
+            for _ in range(warm):
                 host_step(a, b)
             self.barrier()
+            del per_call[:]
             t0 = time.perf_counter()
             for _ in range(reps):
+                t1 = time.perf_counter()
                 host_step(a, b)
+                per_call.append(time.perf_counter() - t1)
             self.torch.cuda.synchronize(self.dev)
             return self.reduce_max(time.perf_counter() - t0) / reps
 
         xp = self.torch.from_numpy(xh).pin_memory()
         yp = self.torch.from_numpy(yh).pin_memory()
         pinned_s = timed(xp.numpy(), yp.numpy(), steps)
+        spread = sorted(per_call)
+        self.e2e_spread = {"median_ms": round(spread[len(spread) // 2] * 1e3, 4), "min_ms": round(spread[0] * 1e3, 4),
+                           "max_ms": round(spread[-1] * 1e3, 4), "warmup_calls": warm}
         # where the time of such a call goes: the library's own CUDA events on the host path's streams (a few extra
         # calls, outside the timed loop); "h2d" = from the call's start to the first kernel, "d2h" = results + sync
         internal = pcu._pcu_internal
@@ -439,6 +451,7 @@ def main():
            "d2h_bytes_per_step": d2h, "ms_per_step": pinned_s * 1e3, "steps": e2e_steps,
            "api": E2E_API[wl_key] + " (pinned host buffers; every rank on its own GPU)",
            "stage_ms": host_stages,
+           "per_call": getattr(B, "e2e_spread", None),
            "pageable": {"value": res["units"] / pageable_s, "ms_per_step": pageable_s * 1e3,
                         "note": "same call on ordinary (pageable) numpy arrays"}}
     # ---- the same step against a PREPARED target (the fixed cloud of a loss loop binned once) -----------
@@ -557,7 +570,9 @@ def main():
                 "l2": "inputs (24 MB) < L2: a 256 MiB buffer is overwritten before every timed step, outside the interval",
                 "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
                 "e2e_note": ("e2e is PCIe-bound: e2e.stage_ms['bbox+grid'] is the wait for the 24 MB of input; that copy ran at "
-                             "15 - 55 GB/s depending on the box and the moment (shared hosts), CPU placement made no difference"),
+                             "15 - 55 GB/s depending on the box and the moment (shared hosts; within one process it switches "
+                             "between ~52 and ~24 GB/s in windows of 5 - 15 calls during the first ~60 calls on fresh page-locked "
+                             "buffers, tools/e2e_trace.py), CPU placement made no difference; e2e.per_call gives the spread"),
                 "ratio_note": "N GPUs process N pairs per step; the reference arm is one CPU process: a throughput ratio",
             },
             "clocks": res["clocks"],
