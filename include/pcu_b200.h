@@ -117,7 +117,9 @@ int64_t pcu_b200_launch_count(void);
 /* Page-locked host memory (cudaHostAlloc / cudaFreeHost), for callers that want their big result buffers to
  * be copy targets the DMA engines can write directly: the numpy-facing binding backs k-NN results of 1 MiB and
  * more with such blocks (recycled through a small pool), because a device-to-host copy into freshly allocated
- * pageable memory runs at ~3 GB/s -- the page faults, not PCIe -- against ~50 GB/s into pinned memory. */
+ * pageable memory runs at ~3 GB/s -- the page faults, not PCIe -- against ~50 GB/s into pinned memory.
+ * The block is placed on the NUMA node of the calling thread's current GPU (the PCI device's numa_node in sysfs):
+ * on two-socket hosts a page-locked buffer on the other node is copied at half the rate or less. */
 int pcu_b200_host_alloc(void** out_ptr, int64_t bytes);
 int pcu_b200_host_free(void* ptr);
 

@@ -1297,7 +1297,15 @@ int pcu_b200_workspace_device(const pcu_b200_workspace* ws) { return ws ? ws->de
 int pcu_b200_host_alloc(void** out_ptr, int64_t bytes) {
     if (!out_ptr || bytes <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "bad argument");
     *out_ptr = nullptr;
-    cudaError_t e = cudaHostAlloc(out_ptr, (size_t)bytes, cudaHostAllocPortable);
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
+    cudaError_t e;
+    {
+        NearDevice near(device);   // pages on the NUMA node of the calling thread's current GPU (staging.h)
+        e = cudaHostAlloc(out_ptr, (size_t)bytes, cudaHostAllocPortable);
+        // touch the pages while bound: placement is decided at first touch if the driver left any of it lazy
+        if (e == cudaSuccess) for (size_t off = 0; off < (size_t)bytes; off += 4096) static_cast<volatile char*>(*out_ptr)[off] = 0;
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         *out_ptr = nullptr;

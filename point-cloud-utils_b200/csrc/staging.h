@@ -16,11 +16,74 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 #include <mutex>
 #include <thread>
 
 namespace pcu {
+
+// While alive, the calling thread runs on the CPUs of the NUMA node the given GPU hangs off (sysfs: the PCI device's
+// numa_node, that node's cpulist), so that page-locked memory allocated meanwhile is placed next to the GPU.  Where a
+// page-locked buffer lives decides the copy rate on two-socket hosts: measured on these boxes, 24 MB H2D in 0.44 ms
+// from the GPU's node against 0.6 - 1.5 ms from the other one (and fluctuating with the traffic on the socket link).
+// Does nothing when the topology cannot be read (no sysfs, one node, numa_node = -1).
+class NearDevice {
+public:
+    explicit NearDevice(int device) {
+#if defined(__linux__)
+        char bus[32] = {0};
+        if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return; }
+        for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+        char path[128];
+        std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+        int node = -1;
+        if (std::FILE* f = std::fopen(path, "r")) { if (std::fscanf(f, "%d", &node) != 1) node = -1; std::fclose(f); }
+        if (node < 0) return;
+        std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+        std::FILE* f = std::fopen(path, "r");
+        if (!f) return;
+        char list[4096] = {0};
+        const bool got = std::fgets(list, (int)sizeof list, f) != nullptr;
+        std::fclose(f);
+        if (!got || sched_getaffinity(0, sizeof old_, &old_) != 0) return;
+        cpu_set_t want;
+        CPU_ZERO(&want);
+        int any = 0;
+        for (char* p = list; *p;) {                    // "0-31,64-95"
+            char* end = nullptr;
+            const long a = std::strtol(p, &end, 10);
+            if (end == p) break;
+            long b = a;
+            p = end;
+            if (*p == '-') { b = std::strtol(p + 1, &end, 10); p = end; }
+            for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+                if (CPU_ISSET((int)c, &old_)) { CPU_SET((int)c, &want); ++any; }
+            while (*p == ',' || *p == ' ' || *p == '\n') ++p;
+        }
+        if (any && sched_setaffinity(0, sizeof want, &want) == 0) bound_ = true;
+#else
+        (void)device;
+#endif
+    }
+    ~NearDevice() {
+#if defined(__linux__)
+        if (bound_) sched_setaffinity(0, sizeof old_, &old_);
+#endif
+    }
+    NearDevice(const NearDevice&) = delete;
+    NearDevice& operator=(const NearDevice&) = delete;
+
+private:
+#if defined(__linux__)
+    cpu_set_t old_;
+#endif
+    bool bound_ = false;
+};
 
 class HostStager {
 public:
@@ -117,7 +180,14 @@ private:
         if (started_) return cudaSuccess;
         // write-combined: the CPU only ever streams into the ring and the GPU only reads it (numpy-in Chamfer of
         // 2 x 10^6 points 0.92 -> 0.82 ms against an ordinary page-locked ring)
-        cudaError_t e = cudaHostAlloc((void**)&ring_, kChunk * kSlots, cudaHostAllocWriteCombined);
+        int device = 0;
+        if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; }
+        cudaError_t e;
+        {
+            NearDevice near(device);       // the ring's pages next to the GPU that reads them
+            e = cudaHostAlloc((void**)&ring_, kChunk * kSlots, cudaHostAllocWriteCombined);
+            if (e == cudaSuccess) std::memset(ring_, 0, kChunk * kSlots);
+        }
         if (e != cudaSuccess) return e;
         for (auto& ev : sent_) {
             e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
