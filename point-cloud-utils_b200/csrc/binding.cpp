@@ -166,6 +166,18 @@ py::array_t<T> result_array(py::ssize_t rows, py::ssize_t cols) {
     return py::array_t<T>({rows, cols});
 }
 
+// pcu.pinned_empty: an (n, 3) array of T in page-locked memory next to the current GPU, for callers who fill their
+// clouds in place (what torch's pin_memory() gives, with the placement taken care of: pcu_b200_host_alloc)
+template <typename T>
+py::array pinned_cloud(py::ssize_t rows, py::ssize_t cols) {
+    if (rows <= 0 || cols <= 0) throw py::value_error("shape must be positive");
+    const size_t bytes = (size_t)rows * (size_t)cols * sizeof(T);
+    void* p = nullptr;
+    check(pcu_b200_host_alloc(&p, (int64_t)bytes));
+    py::capsule owner(p, [](void* q) { pcu_b200_host_free(q); });
+    return py::array_t<T>({rows, cols}, {(py::ssize_t)(cols * sizeof(T)), (py::ssize_t)sizeof(T)}, static_cast<T*>(p), owner);
+}
+
 struct Options { int leaf = 10; float occupancy = 0.f; int disable_replay = 0; int binning = 0; int host_staging = 0; };
 Options& defaults() { static Options o; return o; }
 
@@ -1061,6 +1073,9 @@ PYBIND11_MODULE(_pcu_internal, mod) {
         defaults().disable_replay = disable_tie_replay;
         defaults().binning = binning;
     }, py::arg("cell_occupancy") = 0.f, py::arg("disable_tie_replay") = 0, py::arg("binning") = 0, py::arg("host_staging") = 0);
+    mod.def("_pinned_empty", [](py::ssize_t rows, py::ssize_t cols, bool is_f64) {
+        return is_f64 ? pinned_cloud<double>(rows, cols) : pinned_cloud<float>(rows, cols);
+    });
     mod.def("_release_workspaces", []() { pool().clear(); });
     mod.def("_release_pinned_results", []() { pinned_pool().clear(false); });
     // destroy workspaces and cached pinned blocks before the CUDA context goes away at interpreter exit

@@ -353,3 +353,16 @@ def test_prepared_dataset_for_knn_gives_the_plain_results(pcu, oracle):
     ref = oracle.k_nearest_neighbors(ql, lat, 8)
     got = pcu.k_nearest_neighbors(ql, hl, 8)
     assert np.array_equal(got[1], ref[1]) and np.array_equal(got[0], ref[0])
+
+
+@pytest.mark.gpu
+def test_pinned_empty_is_a_dma_source(pcu, oracle):
+    rng = np.random.default_rng(3)
+    x = pcu.pinned_empty(50000); y = pcu.pinned_empty(40000, np.float64)
+    assert x.shape == (50000, 3) and x.dtype == np.float32 and y.dtype == np.float64 and x.flags.c_contiguous
+    x[:] = rng.random((50000, 3)); y[:] = rng.random((40000, 3))
+    y32 = pcu.pinned_empty(40000); y32[:] = y
+    ref = float(oracle.chamfer_distance(np.array(x), np.array(y32)))
+    assert abs(float(pcu.chamfer_distance(x, y32)) - ref) <= REL * ref
+    with pytest.raises(ValueError):
+        pcu.pinned_empty(10, np.int32)
