@@ -33,3 +33,25 @@ timed("voxel down-sampling, 100^3 voxels", lambda: pcu.downsample_point_cloud_on
 dup = torch.cat([x, x[: n // 4]])
 timed("deduplicate_point_cloud fp32, %d rows (20 %% duplicates)" % dup.shape[0], lambda: pcu.deduplicate_point_cloud(dup, 1e-11))
 timed("deduplicate_point_cloud fp64", lambda: pcu.deduplicate_point_cloud(dup.double(), 1e-11))
+# N3 Morton codes (numpy in / numpy out through the host entry points: H2D + kernel + D2H) and on-device kernel time
+I = pcu._pcu_internal
+pts_i = np.random.default_rng(0).integers(-(1 << 20), 1 << 20, (10_000_000, 3)).astype(np.int32)
+import time
+def wall(label, fn, reps=3):
+    fn(); best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter(); fn(); best = min(best, (time.perf_counter() - t0) * 1e3)
+    print("%-58s %9.3f ms (wall, host arrays)" % (label, best), flush=True)
+codes = pcu.morton_encode(pts_i)
+wall("morton_encode 10^7 points (120 MB in, 80 MB out)", lambda: pcu.morton_encode(pts_i))
+wall("morton_decode 10^7 codes", lambda: pcu.morton_decode(codes))
+sc = np.sort(codes)
+wall("morton_knn k=15, 10^6 queries in 10^7 sorted codes", lambda: pcu.morton_knn(sc, codes[:1_000_000], 15))
+# N4 dense metrics on device tensors
+a = torch.rand((4, 2048, 3), generator=g, device="cuda", dtype=torch.float32); b = torch.rand((4, 2048, 3), generator=g, device="cuda", dtype=torch.float32)
+timed("pairwise_distances 4 x 2048 x 2048 (fp32)", lambda: pcu.pairwise_distances(a, b))
+M = pcu.pairwise_distances(a, b)
+wa = torch.full((4, 2048), 1.0 / 2048, device="cuda"); wb = torch.full((4, 2048), 1.0 / 2048, device="cuda")
+timed("sinkhorn 4 x 2048 x 2048, eps 1e-2, 100 iterations (no early stop)", lambda: pcu.sinkhorn(wa, wb, M, eps=1e-2, max_iters=100, stop_thresh=0.0))
+p64 = a[0].double(); q64 = b[0].double()     # like the reference, EMD wants float64 points (its weights are np.ones(n) / n)
+timed("earth_movers_distance 2048 vs 2048 (fp64), 100 iterations", lambda: pcu.earth_movers_distance(p64, q64, eps=1e-2, max_iters=100, stop_thresh=0.0))
