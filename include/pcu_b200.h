@@ -391,6 +391,20 @@ int pcu_b200_normals_knn_host_f32(pcu_b200_workspace* ws, const float* points, i
                                   double drop_angle_threshold, int64_t* out_idx, float* out_normals, int64_t* out_count);
 int pcu_b200_normals_knn_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs, int k,
                                   double drop_angle_threshold, int64_t* out_idx, double* out_normals, int64_t* out_count);
+/* voxel-grid down-sampling / duplicate removal on HOST arrays (outputs sized for the worst case as in the device
+ * forms; out_rows / out_counts are HOST integers here) */
+int pcu_b200_voxel_downsample_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const void* attrib, int attrib_cols,
+                                       int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                       int min_points_per_voxel, float* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows);
+int pcu_b200_voxel_downsample_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const void* attrib, int attrib_cols,
+                                       int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                       int min_points_per_voxel, double* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows);
+int pcu_b200_deduplicate_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                                  int face_cols, int faces_are_i64, float* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                                  int64_t* out_counts);
+int pcu_b200_deduplicate_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                                  int face_cols, int faces_are_i64, double* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                                  int64_t* out_counts);
 int pcu_b200_normals_ball_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const float* view_dirs,
                                    const pcu_b200_ball_options* options, int64_t* out_idx, float* out_normals, int64_t* out_count);
 int pcu_b200_normals_ball_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const double* view_dirs,

@@ -218,6 +218,96 @@ int normals_ball_host(pcu_b200_workspace* ws, const T* points, long long n, cons
                            });
 }
 
+// voxel-grid down-sampling on HOST arrays: stage, run, fetch the row count, then exactly the rows that exist
+template <typename T>
+int voxel_downsample_host(pcu_b200_workspace* ws, const T* points, long long n, const void* attrib, int attrib_cols, int attrib_is_f64,
+                          const double size[3], const double min_bound[3], const double max_bound[3], int min_points, T* out_points,
+                          void* out_attrib, int32_t* out_counts, long long* out_rows) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!points || n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "points must be a non-empty (n, 3) array");
+    if (!out_points || !out_rows || attrib_cols < 0 || (attrib_cols > 0 && (!attrib || !out_attrib)))
+        return fail(PCU_B200_INVALID_ARGUMENT, "null pointer");
+    PCU_ON_DEVICE(ws);
+    const size_t abytes = (size_t)(attrib_is_f64 ? 8 : 4) * (size_t)attrib_cols;      // per row
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& dp, unsigned char*& da, T*& op, unsigned char*& oa, int*& oc, long long*& orows) {
+        dp = cv.take<T>((size_t)3 * n);
+        da = cv.take<unsigned char>(abytes * (size_t)n + 1);
+        op = cv.take<T>((size_t)3 * n);
+        oa = cv.take<unsigned char>(abytes * (size_t)n + 1);
+        oc = cv.take<int>((size_t)n);
+        orows = cv.take<long long>(1);
+    };
+    T *dp, *op; unsigned char *da, *oa; int* oc; long long* orows;
+    carve(measure, dp, da, op, oa, oc, orows);
+    cudaStream_t st = ws->own_stream;
+    PCU_TRY(ensure_io(ws, measure.off, st));
+    Carver cv(ws->io);
+    carve(cv, dp, da, op, oa, oc, orows);
+    PCU_TRY(h2d(ws, dp, points, sizeof(T) * 3 * n, st));
+    if (attrib_cols > 0) PCU_TRY(h2d(ws, da, attrib, abytes * (size_t)n, st));
+    PCU_TRY(voxel_downsample_dispatch<T>(ws, dp, n, attrib_cols > 0 ? da : nullptr, attrib_cols, attrib_is_f64, size, min_bound, max_bound,
+                                         min_points, op, attrib_cols > 0 ? oa : nullptr, out_counts ? oc : nullptr, orows, st));
+    long long* hr = reinterpret_cast<long long*>(ws->host_slot);
+    PCU_CUDA(cudaMemcpyAsync(hr, orows, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    const long long rows = *hr;
+    if (rows > 0) {
+        PCU_CUDA(cudaMemcpyAsync(out_points, op, sizeof(T) * 3 * rows, cudaMemcpyDeviceToHost, st));
+        if (attrib_cols > 0) PCU_CUDA(cudaMemcpyAsync(out_attrib, oa, abytes * (size_t)rows, cudaMemcpyDeviceToHost, st));
+        if (out_counts) PCU_CUDA(cudaMemcpyAsync(out_counts, oc, sizeof(int) * rows, cudaMemcpyDeviceToHost, st));
+        PCU_CUDA(cudaStreamSynchronize(st));
+    }
+    *out_rows = rows;
+    return PCU_B200_OK;
+}
+
+// duplicate removal on HOST arrays (faces may be null)
+template <typename T>
+int deduplicate_host(pcu_b200_workspace* ws, const T* points, long long n, double epsilon, const void* faces, long long nf, int cols,
+                     int faces_are_i64, T* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces, long long* out_counts) {
+    if (!ws) return fail(PCU_B200_INVALID_ARGUMENT, "null workspace");
+    if (!points || n <= 0) return fail(PCU_B200_INVALID_ARGUMENT, "points must be a non-empty (n, 3) array");
+    if (!out_points || !out_svi || !out_svj || !out_counts) return fail(PCU_B200_INVALID_ARGUMENT, "null output pointer");
+    if (faces != nullptr && (nf < 0 || cols <= 0 || cols > 16 || (nf > 0 && !out_faces)))
+        return fail(PCU_B200_INVALID_ARGUMENT, "faces must be an (m, c) array with 1 <= c <= 16");
+    PCU_ON_DEVICE(ws);
+    const bool with_faces = faces != nullptr && nf > 0;
+    const size_t fbytes = with_faces ? (size_t)(faces_are_i64 ? 8 : 4) * (size_t)cols * (size_t)nf : 0;
+    Carver measure(nullptr);
+    auto carve = [&](Carver& cv, T*& dp, unsigned char*& df, T*& op, int*& svi, int*& svj, unsigned char*& of, long long*& oc) {
+        dp = cv.take<T>((size_t)3 * n);
+        df = cv.take<unsigned char>(fbytes + 1);
+        op = cv.take<T>((size_t)3 * n);
+        svi = cv.take<int>((size_t)n);
+        svj = cv.take<int>((size_t)n);
+        of = cv.take<unsigned char>(fbytes + 1);
+        oc = cv.take<long long>(3);
+    };
+    T *dp, *op; unsigned char *df, *of; int *svi, *svj; long long* oc;
+    carve(measure, dp, df, op, svi, svj, of, oc);
+    cudaStream_t st = ws->own_stream;
+    PCU_TRY(ensure_io(ws, measure.off, st));
+    Carver cv(ws->io);
+    carve(cv, dp, df, op, svi, svj, of, oc);
+    PCU_TRY(h2d(ws, dp, points, sizeof(T) * 3 * n, st));
+    if (with_faces) PCU_TRY(h2d(ws, df, faces, fbytes, st));
+    PCU_TRY(dedup_dispatch<T>(ws, dp, n, epsilon, with_faces ? df : nullptr, with_faces ? nf : 0, cols, faces_are_i64, op, svi, svj,
+                              with_faces ? of : nullptr, oc, st));
+    long long* hc = reinterpret_cast<long long*>(ws->host_slot);
+    PCU_CUDA(cudaMemcpyAsync(hc, oc, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    const long long unique = hc[0], kept = hc[1];
+    PCU_CUDA(cudaMemcpyAsync(out_points, op, sizeof(T) * 3 * unique, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaMemcpyAsync(out_svi, svi, sizeof(int) * unique, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaMemcpyAsync(out_svj, svj, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    if (with_faces && kept > 0)
+        PCU_CUDA(cudaMemcpyAsync(out_faces, of, (size_t)(faces_are_i64 ? 8 : 4) * (size_t)cols * (size_t)kept, cudaMemcpyDeviceToHost, st));
+    PCU_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 3; ++i) out_counts[i] = hc[i];
+    return PCU_B200_OK;
+}
+
 // Prepares a cloud from HOST points: staged through the workspace, binned into the handle's own block.
 template <typename T>
 int cloud_prepare_host(pcu_b200_workspace* ws, const T* points, long long n, pcu_b200_cloud** out, int knn_k = 1, int leaf = 0) {
@@ -329,6 +419,30 @@ int pcu_b200_debug_kd_tree_f64(pcu_b200_workspace* ws, const double* points, int
                                int32_t* first, int32_t* last, int32_t* kid0, int32_t* kid1, int64_t* out_nodes) {
     return debug_kd_tree<double>(ws, points, m, max_points_per_leaf, order, node_cap, feat, div_lo, div_hi, first, last,
                                  kid0, kid1, out_nodes);
+}
+int pcu_b200_voxel_downsample_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, const void* attrib, int attrib_cols,
+                                       int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                       int min_points_per_voxel, float* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows) {
+    return voxel_downsample_host<float>(ws, points, n, attrib, attrib_cols, attrib_is_f64, voxel_size, min_bound, max_bound,
+                                        min_points_per_voxel, out_points, out_attrib, out_counts, (long long*)out_rows);
+}
+int pcu_b200_voxel_downsample_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, const void* attrib, int attrib_cols,
+                                       int attrib_is_f64, const double voxel_size[3], const double min_bound[3], const double max_bound[3],
+                                       int min_points_per_voxel, double* out_points, void* out_attrib, int32_t* out_counts, int64_t* out_rows) {
+    return voxel_downsample_host<double>(ws, points, n, attrib, attrib_cols, attrib_is_f64, voxel_size, min_bound, max_bound,
+                                         min_points_per_voxel, out_points, out_attrib, out_counts, (long long*)out_rows);
+}
+int pcu_b200_deduplicate_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                                  int face_cols, int faces_are_i64, float* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                                  int64_t* out_counts) {
+    return deduplicate_host<float>(ws, points, n, epsilon, faces, n_faces, face_cols, faces_are_i64, out_points, out_svi, out_svj, out_faces,
+                                   (long long*)out_counts);
+}
+int pcu_b200_deduplicate_host_f64(pcu_b200_workspace* ws, const double* points, int64_t n, double epsilon, const void* faces, int64_t n_faces,
+                                  int face_cols, int faces_are_i64, double* out_points, int32_t* out_svi, int32_t* out_svj, void* out_faces,
+                                  int64_t* out_counts) {
+    return deduplicate_host<double>(ws, points, n, epsilon, faces, n_faces, face_cols, faces_are_i64, out_points, out_svi, out_svj, out_faces,
+                                    (long long*)out_counts);
 }
 int pcu_b200_cloud_prepare_knn_host_f32(pcu_b200_workspace* ws, const float* points, int64_t n, int k, int max_points_per_leaf,
                                         pcu_b200_cloud** out_cloud) {

@@ -366,3 +366,56 @@ def test_pinned_empty_is_a_dma_source(pcu, oracle):
     assert abs(float(pcu.chamfer_distance(x, y32)) - ref) <= REL * ref
     with pytest.raises(ValueError):
         pcu.pinned_empty(10, np.int32)
+
+
+@pytest.mark.gpu
+def test_ctypes_host_forms_of_voxel_grid_and_duplicate_removal(pcu, oracle):
+    """pcu_b200_voxel_downsample_host_* / pcu_b200_deduplicate_host_* (numpy memory in and out, what an npe binding of
+    src/sample_point_cloud.cpp:336-367 / src/remove_duplicates.cpp:108-176 would call) give the Python layer's results."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "point-cloud-utils_b200", "libpcu_b200.so"))
+    lib.pcu_b200_last_error.restype = ctypes.c_char_p
+    ws = ctypes.c_void_p()
+    assert lib.pcu_b200_workspace_create(0, ctypes.byref(ws)) == 0, lib.pcu_b200_last_error()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    try:
+        rng = np.random.default_rng(12)
+        pts = rng.random((40000, 3)).astype(np.float32)
+        col = rng.random((40000, 2)).astype(np.float64)
+        # voxel grid, with a float64 attribute of two columns and the per-voxel counts
+        size = (ctypes.c_double * 3)(0.05, 0.05, 0.05)
+        lo64 = pts.min(0).astype(np.float64) - 0.025; hi64 = pts.max(0).astype(np.float64) + 0.025    # the wrapper's default bounds
+        lo = (ctypes.c_double * 3)(*lo64); hi = (ctypes.c_double * 3)(*hi64)
+        out_p = np.empty((40000, 3), np.float32); out_a = np.empty((40000, 2), np.float64); out_c = np.empty(40000, np.int32)
+        rows = ctypes.c_int64(-1)
+        rc = lib.pcu_b200_voxel_downsample_host_f32(ws, vp(pts), ctypes.c_int64(40000), vp(col), 2, 1, size, lo, hi, 2,
+                                                    vp(out_p), vp(out_a), vp(out_c), ctypes.byref(rows))
+        assert rc == 0, lib.pcu_b200_last_error()
+        ref_p, ref_a, ref_c = oracle.downsample_point_cloud_on_voxel_grid(0.05, pts, col, min_bound=lo64, max_bound=hi64,
+                                                                          min_points_per_voxel=2, return_counts=True)
+        m = rows.value
+        assert m == len(ref_p) and 0 < m < 40000
+        # rows come in the order of each voxel's first point, in the library and in the oracle alike
+        assert np.array_equal(out_c[:m], ref_c)
+        assert np.allclose(out_p[:m], ref_p, rtol=0, atol=2e-6)          # the oracle sums in float32, the kernel in fp64
+        assert np.allclose(out_a[:m], ref_a, rtol=0, atol=1e-12)
+        # duplicate removal of a mesh (int64 faces), then of the bare cloud in double precision
+        v = np.concatenate([pts[:20000], pts[:5000]]).astype(np.float32)
+        f = rng.integers(0, len(v), (30000, 3)).astype(np.int64)
+        o_p = np.empty((len(v), 3), np.float32); svi = np.empty(len(v), np.int32); svj = np.empty(len(v), np.int32)
+        o_f = np.empty_like(f); counts = (ctypes.c_int64 * 3)()
+        rc = lib.pcu_b200_deduplicate_host_f32(ws, vp(v), ctypes.c_int64(len(v)), ctypes.c_double(1e-11), vp(f), ctypes.c_int64(len(f)), 3, 1,
+                                               vp(o_p), vp(svi), vp(svj), vp(o_f), counts)
+        assert rc == 0, lib.pcu_b200_last_error()
+        rv, rf, rsvi, rsvj = oracle.deduplicate_mesh_vertices(v, f, 1e-11)
+        assert counts[0] == len(rv) == 20000 and counts[1] == len(rf) and counts[2] == 0
+        assert np.array_equal(o_p[:counts[0]], rv) and np.array_equal(svi[:counts[0]], rsvi) and np.array_equal(svj, rsvj)
+        assert np.array_equal(o_f[:counts[1]], rf)
+        v64 = v.astype(np.float64)
+        o_p64 = np.empty((len(v), 3), np.float64)
+        rc = lib.pcu_b200_deduplicate_host_f64(ws, vp(v64), ctypes.c_int64(len(v64)), ctypes.c_double(0.0), None, ctypes.c_int64(0), 0, 0,
+                                               vp(o_p64), vp(svi), vp(svj), None, counts)
+        assert rc == 0, lib.pcu_b200_last_error()
+        rv, rsvi, rsvj = oracle.deduplicate_point_cloud(v64, 0.0)
+        assert counts[0] == len(rv) and np.array_equal(o_p64[:counts[0]], rv) and np.array_equal(svj, rsvj)
+    finally:
+        assert lib.pcu_b200_workspace_destroy(ws) == 0
