@@ -89,7 +89,8 @@ typedef struct pcu_b200_nn_stats {
 /* Tunables; zero-initialise and override what you need.  0 always means "library default". */
 typedef struct pcu_b200_options {
     int max_points_per_leaf; /* reference kwarg; only influences how exact-distance ties are ordered (default 10) */
-    float cell_occupancy;    /* target dataset points per grid cell (default: 2 for k = 1, ~k/2 otherwise)        */
+    float cell_occupancy;    /* target dataset points per grid cell (0 = default: 1.5 for k = 1; 3 / 4 / 7 / 12  */
+                             /* at k = 4 / 8 / 16 / 32, interpolated in between -- measured) */
     int disable_tie_replay;  /* diagnostic only.  1: keep the (distance, lowest index) order for tied queries;        */
                              /* 2: replay on full reference trees only (no pruned build); 3: pruned build with    */
                              /* zero slack (every walk hits a stub, which exercises the full-rebuild path)        */
